@@ -1,0 +1,678 @@
+// gp_batch.cu — batches of environments on one device: SoA state in HBM, host<->device
+// staging, launches of the kernel variants, and the compute entry points of the C ABI.
+//
+// There is NO CPU fallback in this file or anywhere in the library: without a usable CUDA
+// device every entry point returns GP_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstring>
+
+#include "gp_host.h"
+#include "gp_topology.cuh"
+
+using namespace gp;
+
+struct gp_batch {
+  const gp_mechanism* mech = nullptr;
+  unsigned long long mech_revision = 0;
+  long long n = 0, ld = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double* q = nullptr;       // [n_q][ld]
+  double* v = nullptr;       // [n_v][ld]
+  double* tau = nullptr;     // [n_v][ld]
+  bool tau_set = false;
+  unsigned* status = nullptr;  // [ld]
+  double* stage = nullptr;     // staging for AoS<->SoA and outputs
+  size_t stage_bytes = 0;
+  double* scratch = nullptr;   // SoA outputs of dynamics / energy
+  size_t scratch_bytes = 0;
+  long long launches = 0;
+};
+
+namespace {
+
+#define GP_CUDA(call)                                                               \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return GP_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+int ensure(double** buf, size_t* have, size_t need) {
+  if (*have >= need) return GP_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  GP_CUDA(cudaMalloc((void**)buf, need));
+  *have = need;
+  return GP_OK;
+}
+
+// ---- layout kernels ---------------------------------------------------------------------------
+// host "AoS" rows [env][K] <-> device planes [K][ld]; a block moves 128 environments through
+// shared memory so both sides are coalesced.
+constexpr int kTile = 128;
+
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, long long n,
+                                  long long ld, int K) {
+  extern __shared__ double tile[];
+  const long long e0 = (long long)blockIdx.x * kTile;
+  const int ne = (int)min((long long)kTile, n - e0);
+  const double* src = aos + e0 * K;
+  for (int idx = threadIdx.x; idx < ne * K; idx += blockDim.x) tile[idx] = src[idx];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < ne * K; idx += blockDim.x) {
+    const int k = idx / ne, e = idx - k * ne;
+    soa[(long long)k * ld + e0 + e] = tile[e * K + k];
+  }
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos, long long n,
+                                  long long ld, int K) {
+  extern __shared__ double tile[];
+  const long long e0 = (long long)blockIdx.x * kTile;
+  const int ne = (int)min((long long)kTile, n - e0);
+  for (int idx = threadIdx.x; idx < ne * K; idx += blockDim.x) {
+    const int k = idx / ne, e = idx - k * ne;
+    tile[e * K + k] = soa[(long long)k * ld + e0 + e];
+  }
+  __syncthreads();
+  double* dst = aos + e0 * K;
+  for (int idx = threadIdx.x; idx < ne * K; idx += blockDim.x) dst[idx] = tile[idx];
+}
+
+__global__ void init_state_kernel(double* q, double* v, long long n, long long ld, MechParams P) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ld) return;
+  // MechanismState::new (reference mechanism.rs:71-88): zeros, identity pose for floating joints
+  for (int k = 0; k < P.n_q; ++k) q[(long long)k * ld + e] = 0.0;
+  for (int k = 0; k < P.n_v; ++k) v[(long long)k * ld + e] = 0.0;
+  for (int i = 0; i < P.nb; ++i)
+    if (P.jtype[i] == JFloating) q[(long long)(P.qoff[i] + 3) * ld + e] = 1.0;
+  (void)n;
+}
+
+// counter-based RNG: splitmix64 of (seed, env, slot) -> uniform [0,1)
+__host__ __device__ inline double u01(unsigned long long seed, unsigned long long env, unsigned long long slot) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (env * 64ull + slot + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void randomize_kernel(double* q, double* v, long long n, long long ld, MechParams P,
+                                 unsigned long long seed, gp_state_dist D) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  unsigned long long slot = 0;
+  for (int i = 0; i < P.nb; ++i) {
+    const int jt = P.jtype[i], qo = P.qoff[i], vo = P.voff[i];
+    if (jt == JRevolute || jt == JPrismatic) {
+      q[(long long)qo * ld + e] = D.q_lo + (D.q_hi - D.q_lo) * u01(seed, e, slot++);
+      v[(long long)vo * ld + e] = D.v_lo + (D.v_hi - D.v_lo) * u01(seed, e, slot++);
+    } else if (jt == JFloating) {
+      double rpy[3], t[3];
+      for (int k = 0; k < 3; ++k) rpy[k] = D.rpy_jitter * (2.0 * u01(seed, e, slot++) - 1.0);
+      for (int k = 0; k < 3; ++k) t[k] = D.base_t[k] + D.t_jitter[k] * (2.0 * u01(seed, e, slot++) - 1.0);
+      // UnitQuaternion::from_euler_angles(roll, pitch, yaw)
+      double sr, cr, sp, cp, sy, cy;
+      sincos(rpy[0] * 0.5, &sr, &cr);
+      sincos(rpy[1] * 0.5, &sp, &cp);
+      sincos(rpy[2] * 0.5, &sy, &cy);
+      q[(long long)(qo + 0) * ld + e] = sr * cp * cy - cr * sp * sy;
+      q[(long long)(qo + 1) * ld + e] = cr * sp * cy + sr * cp * sy;
+      q[(long long)(qo + 2) * ld + e] = cr * cp * sy - sr * sp * cy;
+      q[(long long)(qo + 3) * ld + e] = cr * cp * cy + sr * sp * sy;
+      for (int k = 0; k < 3; ++k) q[(long long)(qo + 4 + k) * ld + e] = t[k];
+      for (int k = 0; k < 6; ++k)
+        v[(long long)(vo + k) * ld + e] = D.base_v[k] + D.v_jitter * (2.0 * u01(seed, e, slot++) - 1.0);
+    }
+  }
+}
+
+// sums of ke / pe / spring / flagged environments -> out[4] (one atomicAdd per block and value)
+__global__ void energy_sums_kernel(const double* ke, const double* pe, const double* se, const unsigned* status,
+                                   long long n, double* out) {
+  __shared__ double sh[4][32];
+  double a[4] = {0, 0, 0, 0};
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    a[0] += ke[e];
+    a[1] += pe[e];
+    a[2] += se[e];
+    a[3] += status[e] ? 1.0 : 0.0;
+  }
+  for (int k = 0; k < 4; ++k)
+    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < 4; ++k) sh[k][w] = a[k];
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 4; ++k) {
+      double x = lane < nw ? sh[k][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) atomicAdd(&out[k], x);
+    }
+  }
+}
+
+// FP64 FMA-chain probe: 8 independent chains per thread, fully unrolled
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int to_device_soa(gp_batch* b, const double* host_aos, double* soa, int K) {
+  if (K == 0) return GP_OK;
+  const size_t bytes = (size_t)b->n * K * sizeof(double);
+  int rc = ensure(&b->stage, &b->stage_bytes, bytes);
+  if (rc) return rc;
+  GP_CUDA(cudaMemcpyAsync(b->stage, host_aos, bytes, cudaMemcpyHostToDevice, b->stream));
+  const unsigned grid = (unsigned)((b->n + kTile - 1) / kTile);
+  aos_to_soa_kernel<<<grid, 256, (size_t)kTile * K * sizeof(double), b->stream>>>(b->stage, soa, b->n, b->ld, K);
+  GP_CUDA(cudaGetLastError());
+  b->launches++;
+  return GP_OK;
+}
+
+// SoA planes -> host AoS, synchronous on return
+int to_host_aos(gp_batch* b, const double* soa, double* host_aos, int K) {
+  if (K == 0) return GP_OK;
+  const size_t bytes = (size_t)b->n * K * sizeof(double);
+  int rc = ensure(&b->stage, &b->stage_bytes, bytes);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)((b->n + kTile - 1) / kTile);
+  const size_t sh = (size_t)kTile * K * sizeof(double);
+  if (sh > 48 * 1024)
+    GP_CUDA(cudaFuncSetAttribute(soa_to_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  soa_to_aos_kernel<<<grid, 256, sh, b->stream>>>(soa, b->stage, b->n, b->ld, K);
+  GP_CUDA(cudaGetLastError());
+  b->launches++;
+  GP_CUDA(cudaMemcpyAsync(host_aos, b->stage, bytes, cudaMemcpyDeviceToHost, b->stream));
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int check_batch(gp_batch* b, const char* fn) {
+  if (!b) {
+    set_error("%s: null batch", fn);
+    return GP_ERR_INVALID;
+  }
+  GP_CUDA(cudaSetDevice(b->device));
+  return GP_OK;
+}
+
+bool has_contact(const gp_mechanism* m) { return m->n_cp() > 0 && m->n_hs() > 0; }
+
+int64_t step_count(double final_time, double dt) {
+  // reference simulate.rs:97-109: `let mut t = 0.0; while t < final_time { ...; t += dt; }`
+  double t = 0.0;
+  int64_t n = 0;
+  while (t < final_time) {
+    t += dt;
+    ++n;
+  }
+  return n;
+}
+
+int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
+                 int n_cp) {
+  const gp_mechanism* m = b->mech;
+  if (integrator == GP_VELOCITY_STEPPING || integrator == GP_CCD_VELOCITY_STEPPING) {
+    set_error("VelocityStepping / CCDVelocityStepping need the SOCP contact solver (out of scope)");
+    return GP_ERR_UNSUPPORTED;
+  }
+  if (integrator < GP_SEMI_IMPLICIT_EULER || integrator > GP_RUNGE_KUTTA_4) {
+    set_error("unknown integrator %d", integrator);
+    return GP_ERR_INVALID;
+  }
+  if (n_steps < 0 || !(dt == dt)) {
+    set_error("bad n_steps / dt");
+    return GP_ERR_INVALID;
+  }
+  StepArgs A{};
+  A.q = b->q;
+  A.v = b->v;
+  A.tau = b->tau_set ? b->tau : nullptr;
+  A.status = b->status;
+  A.n = b->n;
+  A.ld = b->ld;
+  A.dt = dt;
+  A.n_steps = n_steps;
+  A.integrator = integrator;
+  A.controller = controller;
+  for (int k = 0; k < 4; ++k) A.cp[k] = (cp && k < n_cp) ? cp[k] : 0.0;
+  const TopoData& td = m->table->topo;
+  switch (controller) {
+    case GP_CTRL_NONE:
+      break;
+    case GP_CTRL_SO101_PD:
+      if (n_cp < 3) {
+        set_error("GP_CTRL_SO101_PD needs [kp, kd, clamp]");
+        return GP_ERR_INVALID;
+      }
+      break;
+    case GP_CTRL_ACROBOT_SWINGUP:
+      if (!(m->table->is_static && td.nb == 2 && td.jtype[0] == JRevolute && td.jtype[1] == JRevolute) || n_cp < 2) {
+        set_error("GP_CTRL_ACROBOT_SWINGUP needs a revolute-revolute chain and [m, l]");
+        return GP_ERR_INVALID;
+      }
+      break;
+    case GP_CTRL_CARTPOLE_SWINGUP:
+      if (!(m->table->is_static && td.nb == 2 && td.jtype[0] == JPrismatic && td.jtype[1] == JRevolute) || n_cp < 3) {
+        set_error("GP_CTRL_CARTPOLE_SWINGUP needs a prismatic-revolute chain and [m_c, m_p, l]");
+        return GP_ERR_INVALID;
+      }
+      break;
+    default:
+      set_error("unknown controller %d", controller);
+      return GP_ERR_INVALID;
+  }
+  if (n_steps == 0) return GP_OK;
+  const int ic = integrator == GP_SEMI_IMPLICIT_EULER ? IntegSIE : IntegRK;
+  GP_CUDA(m->table->step(has_contact(m), ic, b->stream, m->params, A));
+  b->launches++;
+  return GP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int gp_batch_create(const gp_mechanism* mech, int64_t n_envs, int device, gp_batch** out) {
+  if (!mech || !out || n_envs < 1) {
+    set_error("gp_batch_create: bad argument");
+    return GP_ERR_INVALID;
+  }
+  *out = nullptr;
+  const int ndev = gp_device_count();
+  if (ndev <= 0) {
+    set_error("no CUDA device available; this library has no CPU fallback");
+    return GP_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("device %d out of range (%d visible)", device, ndev);
+    return GP_ERR_INVALID;
+  }
+  GP_CUDA(cudaSetDevice(device));
+  gp_batch* b = new gp_batch();
+  b->mech = mech;
+  b->mech_revision = mech->revision;
+  b->n = n_envs;
+  b->ld = (n_envs + 31) / 32 * 32;
+  b->device = device;
+  auto fail = [&](int rc) {
+    gp_batch_destroy(b);
+    return rc;
+  };
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    return fail(GP_ERR_CUDA);
+  }
+  const size_t nq = mech->n_q > 0 ? mech->n_q : 1, nv = mech->n_v > 0 ? mech->n_v : 1;
+  if (cudaMalloc((void**)&b->q, nq * b->ld * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&b->v, nv * b->ld * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&b->tau, nv * b->ld * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&b->status, b->ld * sizeof(unsigned)) != cudaSuccess) {
+    set_error("cudaMalloc failed for %lld environments: %s", (long long)n_envs,
+              cudaGetErrorString(cudaGetLastError()));
+    return fail(GP_ERR_CUDA);
+  }
+  cudaMemsetAsync(b->tau, 0, nv * b->ld * sizeof(double), b->stream);
+  cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream);
+  init_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->q, b->v, b->n, b->ld, mech->params);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    set_error("state initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(GP_ERR_CUDA);
+  }
+  b->launches++;
+  *out = b;
+  return GP_OK;
+}
+
+void gp_batch_destroy(gp_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  cudaFree(b->q);
+  cudaFree(b->v);
+  cudaFree(b->tau);
+  cudaFree(b->status);
+  cudaFree(b->stage);
+  cudaFree(b->scratch);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int64_t gp_batch_n_envs(const gp_batch* b) { return b ? b->n : 0; }
+int64_t gp_batch_ld(const gp_batch* b) { return b ? b->ld : 0; }
+int gp_batch_device(const gp_batch* b) { return b ? b->device : -1; }
+double* gp_batch_q_device(gp_batch* b) { return b ? b->q : nullptr; }
+double* gp_batch_v_device(gp_batch* b) { return b ? b->v : nullptr; }
+double* gp_batch_tau_device(gp_batch* b) {
+  if (!b) return nullptr;
+  b->tau_set = true;  // the caller is going to write torques through the pointer
+  return b->tau;
+}
+void* gp_batch_stream(gp_batch* b) { return b ? (void*)b->stream : nullptr; }
+int64_t gp_batch_launch_count(const gp_batch* b) { return b ? b->launches : 0; }
+
+int gp_batch_sync(gp_batch* b) {
+  int rc = check_batch(b, "gp_batch_sync");
+  if (rc) return rc;
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int gp_batch_set_state(gp_batch* b, const double* q_host, const double* v_host) {
+  int rc = check_batch(b, "gp_batch_set_state");
+  if (rc) return rc;
+  if (q_host && (rc = to_device_soa(b, q_host, b->q, b->mech->n_q))) return rc;
+  if (q_host && v_host) GP_CUDA(cudaStreamSynchronize(b->stream));  // staging buffer is reused
+  if (v_host && (rc = to_device_soa(b, v_host, b->v, b->mech->n_v))) return rc;
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int gp_batch_get_state(gp_batch* b, double* q_host, double* v_host) {
+  int rc = check_batch(b, "gp_batch_get_state");
+  if (rc) return rc;
+  if (q_host && (rc = to_host_aos(b, b->q, q_host, b->mech->n_q))) return rc;
+  if (v_host && (rc = to_host_aos(b, b->v, v_host, b->mech->n_v))) return rc;
+  return GP_OK;
+}
+
+int gp_batch_set_tau(gp_batch* b, const double* tau_host) {
+  int rc = check_batch(b, "gp_batch_set_tau");
+  if (rc) return rc;
+  if (!tau_host) {
+    b->tau_set = false;
+    return GP_OK;
+  }
+  if ((rc = to_device_soa(b, tau_host, b->tau, b->mech->n_v))) return rc;
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  b->tau_set = true;
+  return GP_OK;
+}
+
+int gp_batch_randomize(gp_batch* b, uint64_t seed, const gp_state_dist* dist) {
+  int rc = check_batch(b, "gp_batch_randomize");
+  if (rc) return rc;
+  if (!dist) {
+    set_error("gp_batch_randomize: null distribution");
+    return GP_ERR_INVALID;
+  }
+  randomize_kernel<<<(unsigned)((b->n + 255) / 256), 256, 0, b->stream>>>(b->q, b->v, b->n, b->ld,
+                                                                          b->mech->params, seed, *dist);
+  GP_CUDA(cudaGetLastError());
+  b->launches++;
+  return GP_OK;
+}
+
+int gp_batch_dynamics(gp_batch* b, double* vdot_host, double* contact_force_host) {
+  int rc = check_batch(b, "gp_batch_dynamics");
+  if (rc) return rc;
+  const gp_mechanism* m = b->mech;
+  if (!vdot_host) {
+    set_error("gp_batch_dynamics: vdot_host is null");
+    return GP_ERR_INVALID;
+  }
+  const int nv = m->n_v, ncf = 3 * m->n_cp();
+  if ((rc = ensure(&b->scratch, &b->scratch_bytes, (size_t)(nv + ncf + 1) * b->ld * sizeof(double)))) return rc;
+  DynArgs A{};
+  A.q = b->q;
+  A.v = b->v;
+  A.tau = b->tau_set ? b->tau : nullptr;
+  A.vdot = b->scratch;
+  A.contact_force = (contact_force_host && ncf) ? b->scratch + (size_t)nv * b->ld : nullptr;
+  A.status = b->status;
+  A.n = b->n;
+  A.ld = b->ld;
+  GP_CUDA(m->table->dynamics(has_contact(m), b->stream, m->params, A));
+  b->launches++;
+  if ((rc = to_host_aos(b, A.vdot, vdot_host, nv))) return rc;
+  if (contact_force_host && ncf) {
+    if (!has_contact(m)) {  // no halfspace: every contact force is zero
+      std::memset(contact_force_host, 0, sizeof(double) * (size_t)b->n * ncf);
+    } else if ((rc = to_host_aos(b, A.contact_force, contact_force_host, ncf))) {
+      return rc;
+    }
+  }
+  return GP_OK;
+}
+
+int gp_batch_mass_matrix(gp_batch* b, double* mass_matrix_host, double* bias_host) {
+  int rc = check_batch(b, "gp_batch_mass_matrix");
+  if (rc) return rc;
+  const gp_mechanism* m = b->mech;
+  const int nv = m->n_v;
+  if ((rc = ensure(&b->scratch, &b->scratch_bytes, (size_t)(nv + nv * nv + nv + 1) * b->ld * sizeof(double))))
+    return rc;
+  DynArgs A{};
+  A.q = b->q;
+  A.v = b->v;
+  A.tau = b->tau_set ? b->tau : nullptr;
+  A.vdot = b->scratch;
+  A.mass_matrix = b->scratch + (size_t)nv * b->ld;
+  A.bias = b->scratch + (size_t)(nv + nv * nv) * b->ld;
+  A.status = b->status;
+  A.n = b->n;
+  A.ld = b->ld;
+  GP_CUDA(m->table->dynamics(has_contact(m), b->stream, m->params, A));
+  b->launches++;
+  if (mass_matrix_host) {
+    // nv*nv planes can exceed one tile's shared memory: move them nv planes (one row) at a time
+    std::vector<double> row((size_t)b->n * nv);
+    for (int r = 0; r < nv; ++r) {
+      if ((rc = to_host_aos(b, A.mass_matrix + (size_t)r * nv * b->ld, row.data(), nv))) return rc;
+      for (long long e = 0; e < b->n; ++e)
+        std::memcpy(mass_matrix_host + ((size_t)e * nv + r) * nv, row.data() + (size_t)e * nv, sizeof(double) * nv);
+    }
+  }
+  if (bias_host && (rc = to_host_aos(b, A.bias, bias_host, nv))) return rc;
+  return GP_OK;
+}
+
+int gp_batch_step(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
+                  int n_cp) {
+  int rc = check_batch(b, "gp_batch_step");
+  if (rc) return rc;
+  return launch_steps(b, dt, integrator, n_steps, controller, cp, n_cp);
+}
+
+int64_t gp_simulate_step_count(double final_time, double dt) { return step_count(final_time, dt); }
+
+int gp_batch_simulate(gp_batch* b, double* q_host, double* v_host, const double* tau_host, double final_time,
+                      double dt, int integrator, int controller, const double* cp, int n_cp,
+                      int64_t* n_steps_out, double* history_q, double* history_v) {
+  int rc = check_batch(b, "gp_batch_simulate");
+  if (rc) return rc;
+  if (!q_host || !v_host) {
+    set_error("gp_batch_simulate: q_host / v_host are required");
+    return GP_ERR_INVALID;
+  }
+  if (!(dt > 0.0)) {
+    set_error("gp_batch_simulate: dt must be positive");
+    return GP_ERR_INVALID;
+  }
+  const int64_t n_steps = step_count(final_time, dt);
+  if (n_steps_out) *n_steps_out = n_steps;
+  if (n_steps > 2147483647LL) {
+    set_error("too many steps");
+    return GP_ERR_INVALID;
+  }
+  const gp_mechanism* m = b->mech;
+  if ((rc = gp_batch_set_state(b, q_host, v_host))) return rc;
+  if ((rc = gp_batch_set_tau(b, tau_host))) return rc;
+  if (!history_q && !history_v) {
+    if ((rc = launch_steps(b, dt, integrator, (int)n_steps, controller, cp, n_cp))) return rc;
+  } else {
+    // simulate() records every state (reference simulate.rs:99-108)
+    const size_t sq = (size_t)b->n * m->n_q, sv = (size_t)b->n * m->n_v;
+    if (history_q) std::memcpy(history_q, q_host, sq * sizeof(double));
+    if (history_v) std::memcpy(history_v, v_host, sv * sizeof(double));
+    for (int64_t s = 0; s < n_steps; ++s) {
+      if ((rc = launch_steps(b, dt, integrator, 1, controller, cp, n_cp))) return rc;
+      if ((rc = gp_batch_get_state(b, history_q ? history_q + (s + 1) * sq : nullptr,
+                                   history_v ? history_v + (s + 1) * sv : nullptr)))
+        return rc;
+    }
+  }
+  return gp_batch_get_state(b, q_host, v_host);
+}
+
+static int run_energy(gp_batch* b, bool poses, double** ke, double** pe, double** se, double** pz) {
+  const gp_mechanism* m = b->mech;
+  const size_t need = (size_t)(3 + (poses ? 7 * m->nb : 0)) * b->ld * sizeof(double);
+  int rc = ensure(&b->scratch, &b->scratch_bytes, need);
+  if (rc) return rc;
+  EnergyArgs A{};
+  A.q = b->q;
+  A.v = b->v;
+  A.ke = b->scratch;
+  A.pe = b->scratch + b->ld;
+  A.spring = b->scratch + 2 * b->ld;
+  A.poses = poses ? b->scratch + 3 * b->ld : nullptr;
+  A.n = b->n;
+  A.ld = b->ld;
+  GP_CUDA(m->table->energy(b->stream, m->params, A));
+  b->launches++;
+  *ke = A.ke;
+  *pe = A.pe;
+  *se = A.spring;
+  if (pz) *pz = A.poses;
+  return GP_OK;
+}
+
+int gp_batch_energy(gp_batch* b, double* ke_host, double* pe_host, double* spring_host) {
+  int rc = check_batch(b, "gp_batch_energy");
+  if (rc) return rc;
+  double *ke, *pe, *se;
+  if ((rc = run_energy(b, false, &ke, &pe, &se, nullptr))) return rc;
+  const size_t bytes = (size_t)b->n * sizeof(double);
+  if (ke_host) GP_CUDA(cudaMemcpyAsync(ke_host, ke, bytes, cudaMemcpyDeviceToHost, b->stream));
+  if (pe_host) GP_CUDA(cudaMemcpyAsync(pe_host, pe, bytes, cudaMemcpyDeviceToHost, b->stream));
+  if (spring_host) GP_CUDA(cudaMemcpyAsync(spring_host, se, bytes, cudaMemcpyDeviceToHost, b->stream));
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int gp_batch_energy_sums_device(gp_batch* b, double* out_dev) {
+  int rc = check_batch(b, "gp_batch_energy_sums_device");
+  if (rc) return rc;
+  if (!out_dev) {
+    set_error("gp_batch_energy_sums_device: null output");
+    return GP_ERR_INVALID;
+  }
+  double *ke, *pe, *se;
+  if ((rc = run_energy(b, false, &ke, &pe, &se, nullptr))) return rc;
+  GP_CUDA(cudaMemsetAsync(out_dev, 0, 4 * sizeof(double), b->stream));
+  energy_sums_kernel<<<296, 256, 0, b->stream>>>(ke, pe, se, b->status, b->n, out_dev);
+  GP_CUDA(cudaGetLastError());
+  b->launches++;
+  return GP_OK;
+}
+
+int gp_batch_poses(gp_batch* b, double* poses_host) {
+  int rc = check_batch(b, "gp_batch_poses");
+  if (rc) return rc;
+  if (!poses_host) {
+    set_error("gp_batch_poses: null output");
+    return GP_ERR_INVALID;
+  }
+  double *ke, *pe, *se, *pz;
+  if ((rc = run_energy(b, true, &ke, &pe, &se, &pz))) return rc;
+  // 7*NB planes: move one body (7 planes) at a time through the tile transposer
+  const int nb = b->mech->nb;
+  std::vector<double> one((size_t)b->n * 7);
+  for (int i = 0; i < nb; ++i) {
+    if ((rc = to_host_aos(b, pz + (size_t)7 * i * b->ld, one.data(), 7))) return rc;
+    for (long long e = 0; e < b->n; ++e)
+      std::memcpy(poses_host + ((size_t)e * nb + i) * 7, one.data() + (size_t)e * 7, 7 * sizeof(double));
+  }
+  return GP_OK;
+}
+
+int gp_batch_status(gp_batch* b, uint32_t* status_host) {
+  int rc = check_batch(b, "gp_batch_status");
+  if (rc) return rc;
+  if (!status_host) {
+    set_error("gp_batch_status: null output");
+    return GP_ERR_INVALID;
+  }
+  GP_CUDA(cudaMemcpyAsync(status_host, b->status, (size_t)b->n * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                          b->stream));
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int gp_measure_fp64_peak(int device, double seconds, double* tflops_out) {
+  if (!tflops_out) {
+    set_error("gp_measure_fp64_peak: null output");
+    return GP_ERR_INVALID;
+  }
+  if (gp_device_count() <= 0) {
+    set_error("no CUDA device available");
+    return GP_ERR_NO_DEVICE;
+  }
+  GP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GP_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* out = nullptr;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  GP_CUDA(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 2000;
+  const double flop_per_launch = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+  fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);  // warm-up
+  cudaDeviceSynchronize();
+  double best = 0.0, elapsed = 0.0;
+  int reps = 0;
+  while (elapsed < seconds || reps < 3) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    elapsed += ms * 1e-3;
+    ++reps;
+    // report the sustained figure: the median-ish of the later half is what a long step sees;
+    // keep the LAST measurement after `seconds` of continuous load
+    best = flop_per_launch / (ms * 1e-3) / 1e12;
+    if (reps > 100000) break;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  GP_CUDA(cudaGetLastError());
+  *tflops_out = best;
+  return GP_OK;
+}
+
+}  // extern "C"

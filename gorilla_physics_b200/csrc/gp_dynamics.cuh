@@ -1,0 +1,445 @@
+// gp_dynamics.cuh — one environment's dynamics, integrators, controllers and energies.
+//
+// Thread-per-environment device functions. What the reference computes with world-frame
+// quantities, heap vectors and an LU solve (dynamics_continuous, src/dynamics.rs:322-364)
+// is computed here in BODY coordinates:
+//   pass 1 (root -> leaf)  joint transforms, body twists, Coriolis + gravity bias
+//                          accelerations, point-vs-halfspace contact, Newton-Euler body
+//                          forces                     [reference K1-K3, C1-C3, D1-D3]
+//   pass 2 (leaf -> root)  bias torques c = S^T f (RNEA), composite inertias and the
+//                          joint-space mass matrix H (CRBA)          [reference K5-K7, D4]
+//   solve                  sparse L^T D L factorisation of H in registers (Cholesky family,
+//                          exploits branch-induced sparsity), vdot = H^-1 (tau - c)  [D5-D6]
+// Body-frame inertias are constants, motion subspaces are unit axes, and the floating-base
+// block of H is the composite inertia itself, so far fewer flops are needed than in the
+// reference's world-frame formulation; results agree to rounding (tests: 1e-10 relative).
+#pragma once
+#include <cmath>
+
+#include "gp_math.cuh"
+
+namespace gp {
+
+constexpr unsigned kEnvNaN = GP_ENV_NAN;
+constexpr unsigned kEnvNotSPD = GP_ENV_NOT_SPD;
+
+// optional per-environment outputs of one dynamics evaluation (all SoA, stride ld)
+struct DynOut {
+  double* contact_force;  // [n_cp][3][ld] world-frame force per contact point, or nullptr
+  double* mass_matrix;    // [n_v][n_v][ld] dense symmetric, or nullptr
+  double* bias;           // [n_v][ld], or nullptr
+  long long ld;
+  long long env;
+};
+
+GP_HD int hidx(int r, int c) { return r * (r + 1) / 2 + c; }  // packed lower triangle, c <= r
+
+// ---- joint axis helpers (AxZ folds the unit axis away) ------------------------------------
+template <class Topo>
+GP_D V3 axis_scaled(const MechParams& P, int i, double s) {
+  if (Topo::axis_kind(P, i) == AxZ) return V3{0.0, 0.0, s};
+  return V3{P.axis[i][0] * s, P.axis[i][1] * s, P.axis[i][2] * s};
+}
+template <class Topo>
+GP_D double axis_dot(const MechParams& P, int i, V3 v) {
+  if (Topo::axis_kind(P, i) == AxZ) return v.z;
+  return P.axis[i][0] * v.x + P.axis[i][1] * v.y + P.axis[i][2] * v.z;
+}
+// v + axis * s
+template <class Topo>
+GP_D V3 axis_add(const MechParams& P, int i, V3 v, double s) {
+  if (Topo::axis_kind(P, i) == AxZ) return V3{v.x, v.y, v.z + s};
+  return V3{v.x + P.axis[i][0] * s, v.y + P.axis[i][1] * s, v.z + P.axis[i][2] * s};
+}
+// v x (axis * s)
+template <class Topo>
+GP_D V3 cross_axis(const MechParams& P, int i, V3 v, double s) {
+  if (Topo::axis_kind(P, i) == AxZ) return V3{v.y * s, -(v.x * s), 0.0};
+  return cross(v, V3{P.axis[i][0] * s, P.axis[i][1] * s, P.axis[i][2] * s});
+}
+// J * axis
+template <class Topo>
+GP_D V3 sym_mul_axis(const MechParams& P, int i, const S3& J) {
+  if (Topo::axis_kind(P, i) == AxZ) return V3{J.xz, J.yz, J.zz};
+  return mul(J, V3{P.axis[i][0], P.axis[i][1], P.axis[i][2]});
+}
+
+// ---- joint transform: successor -> predecessor (E, r) --------------------------------------
+// reference: revolute.rs:97-102, prismatic.rs:82-87, floating.rs:26-31 + pose.rs:30-33
+template <class Topo>
+GP_D void joint_xform(const MechParams& P, int i, const double* q, double s, double c, M3& E, V3& r) {
+  const int jt = Topo::jtype(P, i);
+  if (jt == JRevolute) {
+    if (Topo::axis_kind(P, i) == AxZ) {
+      // E0 * Rz(q): columns (c e0 + s e1, c e1 - s e0, e2); e0,e1 are columns of A, e2 of Cm
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double e0 = P.A[i][3 * k], e1 = P.A[i][3 * k + 1];
+        E.m[3 * k] = c * e0 + s * e1;
+        E.m[3 * k + 1] = c * e1 - s * e0;
+        E.m[3 * k + 2] = P.Cm[i][3 * k + 2];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) E.m[k] = P.Cm[i][k] + c * P.A[i][k] + s * P.B[i][k];
+    }
+    r = ld3(P.r0[i]);
+  } else if (jt == JPrismatic) {
+    E = ldm3(P.Cm[i]);
+    const double d = q[Topo::qoff(P, i)];
+    r = V3{P.r0[i][0] + P.Ea[i][0] * d, P.r0[i][1] + P.Ea[i][1] * d, P.r0[i][2] + P.Ea[i][2] * d};
+  } else if (jt == JFloating) {
+    const double* p = q + Topo::qoff(P, i);  // x,y,z,w, tx,ty,tz (joint/mod.rs:216-218)
+    M3 R = quat_to_mat(p[0], p[1], p[2], p[3]);
+    M3 E0 = ldm3(P.Cm[i]);
+    E = mul(E0, R);
+    r = ld3(P.r0[i]) + mul(E0, V3{p[4], p[5], p[6]});
+  } else {
+    E = ldm3(P.Cm[i]);
+    r = ld3(P.r0[i]);
+  }
+}
+
+// ---- contact force law, reference contact.rs:260-302 (Hunt-Crossley + regularised Coulomb)
+// k = k_A k_B / (k_A + k_B) is folded on the host (cp_k holds it). Returns the world-frame force.
+GP_D V3 contact_force(double z, V3 n, V3 vel, double k, double alpha, double mu) {
+  // z <= 0 inside the 1e-8 margin: the reference's powf(negative, 1.5) is NaN and
+  // f64::max(NaN, 0) = 0, i.e. no force
+  if (!(z > 0.0)) return v3z();
+  const double z_dot = -dot(vel, n);
+  const double zn = z * sqrt(z);
+  const double lambda = 1.5 * alpha * k;
+  const double pi_n = fmax(lambda * zn * z_dot + k * zn, 0.0);
+  V3 f = n * pi_n;
+  V3 v_t = vel + n * z_dot;
+  const double v_t_norm = sqrt(dot(v_t, v_t));
+  if (v_t_norm != 0.0) {
+    const double s = v_t_norm / 1e-3;
+    const double mu_eff = (s > 1.0) ? mu : mu * s;
+    const double g = -mu_eff * pi_n / v_t_norm;
+    f += v_t * g;
+  }
+  return f;
+}
+
+// ---- CRBA: carry F = Ic S (one column, dof row `row`) from body i towards the root, filling
+// H[row][dofs of each supporting joint]. E, r are body i's joint transform (already built).
+template <class Topo>
+GP_D void mass_matrix_walk(const MechParams& P, int i, int row, SV F, const M3& E, V3 r, const double* q,
+                           const double* sn, const double* cs, double* H) {
+  constexpr int U = Topo::kUnroll;
+  const int depth = Topo::depth(P, i);
+  int cur = i;
+#pragma unroll U
+  for (int k = 1; k < Topo::lim(depth, Topo::NB); ++k) {
+    if (k < depth) {
+      if (k == 1) {
+        F = force_to_parent(E, r, F);
+      } else {
+        M3 Ec;
+        V3 rc;
+        joint_xform<Topo>(P, cur, q, sn[cur], cs[cur], Ec, rc);
+        F = force_to_parent(Ec, rc, F);
+      }
+      cur = Topo::anc_at(P, i, k);
+      const int jc = Topo::jtype(P, cur);
+      const int vc = Topo::voff(P, cur);
+      if (jc == JRevolute) H[hidx(row, vc)] = axis_dot<Topo>(P, cur, F.a);
+      else if (jc == JPrismatic) H[hidx(row, vc)] = axis_dot<Topo>(P, cur, F.l);
+      else if (jc == JFloating) {
+        H[hidx(row, vc)] = F.a.x; H[hidx(row, vc + 1)] = F.a.y; H[hidx(row, vc + 2)] = F.a.z;
+        H[hidx(row, vc + 3)] = F.l.x; H[hidx(row, vc + 4)] = F.l.y; H[hidx(row, vc + 5)] = F.l.z;
+      }
+    }
+  }
+}
+
+// ---- dynamics_continuous for one environment ------------------------------------------------
+// q[NQ], v[NV], tau[NV] (caller passes zeros for "no torque"); writes vdot[NV]; returns status.
+template <class Topo, bool CONTACT, bool DUMP>
+GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* v, const double* tau,
+                            double* vdot, const DynOut& out) {
+  constexpr int NB = Topo::NB;
+  constexpr int NV = Topo::NV;
+  constexpr int U = Topo::kUnroll;
+  const int nv = Topo::nv(P);
+  unsigned status = 0u;
+
+  double sn[NB], cs[NB];  // cached sin/cos of revolute joints
+  SV vel[NB], acc[NB], frc[NB];
+  M3 Rw[CONTACT ? NB : 1];
+  V3 tw[CONTACT ? NB : 1];
+
+  // ------------------------------------------------------------------ pass 1: root -> leaf
+  for_bodies<Topo>(P, [&](auto ii) {
+    const int i = ii;
+    const int p = Topo::parent(P, i);
+    const int jt = Topo::jtype(P, i);
+    const int vo = Topo::voff(P, i);
+    sn[i] = 0.0;
+    cs[i] = 1.0;
+    if (jt == JRevolute) sincos(q[Topo::qoff(P, i)], &sn[i], &cs[i]);
+    M3 E;
+    V3 r;
+    joint_xform<Topo>(P, i, q, sn[i], cs[i], E, r);
+
+    // parent twist / bias acceleration in parent coordinates. The world "accelerates upwards
+    // at g" (reference dynamics.rs:200-224) which is how gravity enters.
+    SV vi, ai;
+    if (p >= 0) {
+      vi = motion_to_child(E, r, vel[p]);
+      ai = motion_to_child(E, r, acc[p]);
+    } else {  // world: zero twist, acceleration (0; 0,0,g) -> E^T (0,0,g)
+      vi = svz();
+      ai = SV{v3z(), V3{E.m[6] * kGravity, E.m[7] * kGravity, E.m[8] * kGravity}};
+    }
+    // joint twist vJ = S qdot and Coriolis term c = v_i x vJ (reference dynamics.rs:105-139,
+    // util.rs:44-53 se3_commutator; the joint bias S-dot term is zero for all joint types).
+    // For a joint on the world the parent-induced twist is zero, hence c = vJ x vJ = 0.
+    if (jt == JRevolute) {
+      const double qd = v[vo];
+      if (p >= 0) {
+        ai.a += cross_axis<Topo>(P, i, vi.a, qd);  // w x (a qd)
+        ai.l += cross_axis<Topo>(P, i, vi.l, qd);  // vl x (a qd)
+        vi.a = axis_add<Topo>(P, i, vi.a, qd);
+      } else {
+        vi.a = axis_scaled<Topo>(P, i, qd);
+      }
+    } else if (jt == JPrismatic) {
+      const double qd = v[vo];
+      if (p >= 0) {
+        ai.l += cross_axis<Topo>(P, i, vi.a, qd);  // w x (a qd)
+        vi.l = axis_add<Topo>(P, i, vi.l, qd);
+      } else {
+        vi.l = axis_scaled<Topo>(P, i, qd);
+      }
+    } else if (jt == JFloating) {
+      const V3 wj = V3{v[vo], v[vo + 1], v[vo + 2]};
+      const V3 vj = V3{v[vo + 3], v[vo + 4], v[vo + 5]};
+      if (p >= 0) {
+        ai.a += cross(vi.a, wj);
+        ai.l += cross(vi.a, vj) + cross(vi.l, wj);
+        vi.a += wj;
+        vi.l += vj;
+      } else {
+        vi = SV{wj, vj};
+      }
+    }
+    vel[i] = vi;
+    acc[i] = ai;
+
+    // Newton-Euler: f = I a + v x* (I v)   (reference dynamics.rs:41-100, body coordinates)
+    RBI I{lds3(P.J[i]), ld3(P.mc[i]), P.mass[i]};
+    SV h = mul(I, vi);
+    SV f = mul(I, ai);
+    f.a += cross(vi.a, h.a) + cross(vi.l, h.l);
+    f.l += cross(vi.a, h.l);
+
+    if (CONTACT) {
+      // body -> world pose (reference mechanism.rs:153-170)
+      M3 Rwi;
+      V3 twi;
+      if (p >= 0) {
+        Rwi = mul(Rw[p], E);
+        twi = tw[p] + mul(Rw[p], r);
+      } else {
+        Rwi = E;
+        twi = r;
+      }
+      Rw[i] = Rwi;
+      tw[i] = twi;
+      // point-vs-halfspace contact (reference contact.rs:103-128), wrench subtracted from the
+      // body force (dynamics.rs:244-246)
+      const int c0 = P.cp_begin[i], c1 = P.cp_begin[i + 1];
+      for (int c = c0; c < c1; ++c) {
+        const V3 loc = ld3(P.cp_loc[c]);
+        const V3 pw = mul(Rwi, loc) + twi;                   // contact.rs:41-58
+        const V3 vw = mul(Rwi, vi.l + cross(vi.a, loc));     // twist.rs:130-132
+        V3 fw = v3z();
+        for (int hsi = 0; hsi < P.n_hs; ++hsi) {
+          const V3 n = ld3(P.hs_normal[hsi]);
+          const double d = dot(pw - ld3(P.hs_point[hsi]), n);
+          if (d <= 1e-8)  // halfspace.rs:39-44 has_inside
+            fw += contact_force(-d, n, vw, P.cp_k[c], P.hs_alpha[hsi], P.hs_mu[hsi]);
+        }
+        const V3 fb = mulT(Rwi, fw);
+        f.a -= cross(loc, fb);
+        f.l -= fb;
+        if (DUMP && out.contact_force) {
+          double* o = out.contact_force + (long long)(3 * c) * out.ld + out.env;
+          o[0] = fw.x;
+          o[out.ld] = fw.y;
+          o[2 * out.ld] = fw.z;
+        }
+      }
+    }
+    frc[i] = f;
+  });
+
+  // ------------------------------------------------------------------ pass 2: leaf -> root
+  double H[NV * (NV + 1) / 2];
+  double b[NV];
+  RBI Iacc[NB];  // children's composite inertias expressed in this body's frame
+  if (!Topo::kStatic) {
+    for (int k = 0; k < nv * (nv + 1) / 2; ++k) H[k] = 0.0;
+  }
+  for_bodies<Topo>(P, [&](auto ii) {
+    const int i = ii;
+    if (Topo::has_children(P, i)) Iacc[i] = RBI{S3{0, 0, 0, 0, 0, 0}, v3z(), 0.0};
+  });
+
+  for_bodies_reverse<Topo>(P, [&](auto ii) {
+    const int i = ii;
+    const int p = Topo::parent(P, i);
+    const int jt = Topo::jtype(P, i);
+    const int vo = Topo::voff(P, i);
+
+    // composite rigid-body inertia of the subtree rooted at i (reference mechanism.rs:606-625)
+    RBI Ic{lds3(P.J[i]), ld3(P.mc[i]), P.mass[i]};
+    if (Topo::has_children(P, i)) {
+      Ic.J = Ic.J + Iacc[i].J;
+      Ic.c += Iacc[i].c;
+      Ic.m += Iacc[i].m;
+    }
+
+    // bias torque c_i = S^T f_i (reference wrench.rs:96-126)
+    const SV f = frc[i];
+    if (jt == JRevolute) b[vo] = axis_dot<Topo>(P, i, f.a);
+    else if (jt == JPrismatic) b[vo] = axis_dot<Topo>(P, i, f.l);
+    else if (jt == JFloating) {
+      b[vo] = f.a.x; b[vo + 1] = f.a.y; b[vo + 2] = f.a.z;
+      b[vo + 3] = f.l.x; b[vo + 4] = f.l.y; b[vo + 5] = f.l.z;
+    }
+
+    M3 E;
+    V3 r;
+    if (p >= 0) {
+      joint_xform<Topo>(P, i, q, sn[i], cs[i], E, r);
+      SV fp = force_to_parent(E, r, f);
+      frc[p].a += fp.a;
+      frc[p].l += fp.l;
+      RBI Ip = inertia_to_parent(E, r, Ic);
+      Iacc[p].J = Iacc[p].J + Ip.J;
+      Iacc[p].c += Ip.c;
+      Iacc[p].m += Ip.m;
+    }
+
+    // mass-matrix rows of joint i: F = Ic S_i, H_ij = S_j^T F for every joint j supporting i
+    // (reference mechanism.rs:637-696, momentum.rs:17-47)
+    if (jt == JRevolute) {
+      SV F;
+      F.a = sym_mul_axis<Topo>(P, i, Ic.J);
+      F.l = cross_axis<Topo>(P, i, Ic.c, -1.0);  // m*0 - c x a
+      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a);
+      mass_matrix_walk<Topo>(P, i, vo, F, E, r, q, sn, cs, H);
+    } else if (jt == JPrismatic) {
+      SV F;
+      F.a = cross_axis<Topo>(P, i, Ic.c, 1.0);  // J*0 + c x a
+      F.l = axis_scaled<Topo>(P, i, Ic.m);
+      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.l);
+      mass_matrix_walk<Topo>(P, i, vo, F, E, r, q, sn, cs, H);
+    } else if (jt == JFloating) {
+      // S = identity: the F columns are the columns of the 6x6 composite inertia
+      //   [ J   c^ ]      c^ = skew(c)
+      //   [ c^T m1 ]
+#pragma unroll
+      for (int col = 0; col < 6; ++col) {
+        const V3 e = V3{col % 3 == 0 ? 1.0 : 0.0, col % 3 == 1 ? 1.0 : 0.0, col % 3 == 2 ? 1.0 : 0.0};
+        SV F;
+        if (col < 3) {
+          F.a = (col == 0) ? V3{Ic.J.xx, Ic.J.xy, Ic.J.xz}
+                           : ((col == 1) ? V3{Ic.J.xy, Ic.J.yy, Ic.J.yz} : V3{Ic.J.xz, Ic.J.yz, Ic.J.zz});
+          F.l = V3{col == 1 ? -Ic.c.z : (col == 2 ? Ic.c.y : 0.0), col == 0 ? Ic.c.z : (col == 2 ? -Ic.c.x : 0.0),
+                   col == 0 ? -Ic.c.y : (col == 1 ? Ic.c.x : 0.0)};  // e x c
+        } else {
+          F.a = V3{col == 4 ? Ic.c.z : (col == 5 ? -Ic.c.y : 0.0), col == 3 ? -Ic.c.z : (col == 5 ? Ic.c.x : 0.0),
+                   col == 3 ? Ic.c.y : (col == 4 ? -Ic.c.x : 0.0)};  // c x e
+          F.l = e * Ic.m;
+        }
+        const double Fv[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2)
+          if (c2 <= col) H[hidx(vo + col, vo + c2)] = Fv[c2];
+        if (p >= 0) mass_matrix_walk<Topo>(P, i, vo + col, F, E, r, q, sn, cs, H);
+      }
+    }
+  });
+
+  if (DUMP) {
+    if (out.bias) {
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) out.bias[(long long)k * out.ld + out.env] = b[k];
+    }
+    if (out.mass_matrix) {
+#pragma unroll U
+      for (int r_ = 0; r_ < nv; ++r_) {
+#pragma unroll U
+        for (int c_ = 0; c_ < Topo::lim(r_ + 1, NV); ++c_) {
+          if (c_ <= r_) {
+            const double h = Topo::dof_anc(P, c_, r_) ? H[hidx(r_, c_)] : 0.0;
+            out.mass_matrix[(long long)(r_ * nv + c_) * out.ld + out.env] = h;
+            out.mass_matrix[(long long)(c_ * nv + r_) * out.ld + out.env] = h;
+          }
+        }
+      }
+    }
+  }
+
+  // rhs = tau + joint springs - c   (reference dynamics.rs:298-315, :255-276)
+  for_bodies<Topo>(P, [&](auto ii) {
+    const int i = ii;
+    const int jt = Topo::jtype(P, i);
+    const int vo = Topo::voff(P, i);
+    if (jt == JRevolute) b[vo] = tau[vo] - b[vo];
+    else if (jt == JPrismatic) {
+      double t = tau[vo];
+      if (P.has_spring[i]) t += -P.spring_k[i] * (q[Topo::qoff(P, i)] - P.spring_l[i]);
+      b[vo] = t - b[vo];
+    } else if (jt == JFloating) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) b[vo + k] = tau[vo + k] - b[vo + k];
+    }
+  });
+
+  // ------------------------------------------------------------------ sparse L^T D L solve
+  // H = L^T D L with unit lower-triangular L, eliminated from the last dof upwards so that
+  // branch-induced sparsity is preserved (no fill-in); entries with dof_anc == false are
+  // structural zeros and never touched.
+  for_dofs_reverse<Topo>(P, [&](auto kk) {
+    const int k = kk;
+    const double d = H[hidx(k, k)];
+    if (!(d > 0.0)) status |= kEnvNotSPD;
+    const double invd = 1.0 / d;
+#pragma unroll U
+    for (int i2 = 0; i2 < Topo::lim(k, NV); ++i2) {
+      const int i = k - 1 - i2;
+      if (i >= 0 && Topo::dof_anc(P, i, k)) {
+        const double a = H[hidx(k, i)] * invd;
+#pragma unroll U
+        for (int j = 0; j < Topo::lim(i + 1, NV); ++j)
+          if (j <= i && Topo::dof_anc(P, j, k)) H[hidx(i, j)] -= a * H[hidx(k, j)];
+        H[hidx(k, i)] = a;
+      }
+    }
+    H[hidx(k, k)] = invd;
+  });
+  // x = L^-T b
+  for_dofs_reverse<Topo>(P, [&](auto kk) {
+    const int k = kk;
+#pragma unroll U
+    for (int j = 0; j < Topo::lim(k, NV); ++j)
+      if (j < k && Topo::dof_anc(P, j, k)) b[j] -= H[hidx(k, j)] * b[k];
+  });
+  // x = D^-1 x ; x = L^-1 x
+  for_dofs<Topo>(P, [&](auto kk) {
+    const int k = kk;
+    double x = b[k] * H[hidx(k, k)];
+#pragma unroll U
+    for (int j = 0; j < Topo::lim(k, NV); ++j)
+      if (j < k && Topo::dof_anc(P, j, k)) x -= H[hidx(k, j)] * vdot[j];
+    vdot[k] = x;
+  });
+  return status;
+}
+
+}  // namespace gp

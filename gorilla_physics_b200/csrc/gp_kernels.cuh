@@ -1,0 +1,377 @@
+// gp_kernels.cuh — the CUDA kernels (sm_100a) and the per-topology launch table.
+//
+// One thread advances one environment. State is structure-of-arrays (plane k of q at
+// q[k * ld + env]) so every load/store is a coalesced 8-byte access per lane; a step kernel
+// keeps q and v in registers across `n_steps` fused time steps (reference simulate.rs:102-109
+// runs them one by one). Mechanism constants arrive as one __grid_constant__ kernel parameter
+// (constant bank), so FP64 instructions read them as direct operands.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gp_dynamics.cuh"
+#include "gp_launch.h"
+
+namespace gp {
+
+// ---- pose integration, reference integrators.rs:296-319 / :230-271 + util.rs:83-102 --------
+// quat' = normalize(quat + 1/2 Q(quat) w dt), t' = t + (quat * v_lin) dt ; w, v_lin in body frame
+GP_D void integrate_pose(const double* qi, V3 w, V3 vl, double dt, double* qo) {
+  const double x = qi[0], y = qi[1], z = qi[2], s = qi[3];
+  const double dw = 0.5 * (-x * w.x - y * w.y - z * w.z);
+  const double dx = 0.5 * (s * w.x - z * w.y + y * w.z);
+  const double dy = 0.5 * (z * w.x + s * w.y - x * w.z);
+  const double dz = 0.5 * (-y * w.x + x * w.y + s * w.z);
+  // rotate v_lin by the (current) unit quaternion: v + w t + q x t, t = 2 q x v
+  const V3 qv = V3{x, y, z};
+  const V3 t = cross(qv, vl) * 2.0;
+  const V3 tdot = vl + t * s + cross(qv, t);
+  const double nx = x + dx * dt, ny = y + dy * dt, nz = z + dz * dt, nw = s + dw * dt;
+  const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+  qo[0] = nx * inv;
+  qo[1] = ny * inv;
+  qo[2] = nz * inv;
+  qo[3] = nw * inv;
+  qo[4] = qi[4] + tdot.x * dt;
+  qo[5] = qi[5] + tdot.y * dt;
+  qo[6] = qi[6] + tdot.z * dt;
+}
+
+// q_out = q (+) v_q dt for every joint (v_q = new v for semi-implicit, old v for explicit Euler)
+template <class Topo>
+GP_D void advance_q(const MechParams& P, const double* q, const double* vq, double dt, double* qo) {
+  for_bodies<Topo>(P, [&](auto ii) {
+    const int i = ii;
+    const int jt = Topo::jtype(P, i);
+    const int qo_ = Topo::qoff(P, i), vo = Topo::voff(P, i);
+    if (jt == JRevolute || jt == JPrismatic) {
+      qo[qo_] = q[qo_] + vq[vo] * dt;
+    } else if (jt == JFloating) {
+      integrate_pose(q + qo_, V3{vq[vo], vq[vo + 1], vq[vo + 2]}, V3{vq[vo + 3], vq[vo + 4], vq[vo + 5]}, dt,
+                     qo + qo_);
+    }
+  });
+}
+
+// ---- kinetic / potential / spring energy and poses, reference mechanism.rs:334-377, :403 ----
+template <class Topo>
+GP_D void energy_core(const MechParams& P, const double* q, const double* v, double& ke, double& pe,
+                      double& se, double* poses, long long ld, long long env) {
+  constexpr int NB = Topo::NB;
+  SV vel[NB];
+  M3 Rw[NB];
+  V3 tw[NB];
+  double qw[NB][4];  // body->world rotation as quaternion x,y,z,w (same product chain as the reference)
+  ke = 0.0;
+  pe = 0.0;
+  se = 0.0;
+  for_bodies<Topo>(P, [&](auto ii) {
+    const int i = ii;
+    const int p = Topo::parent(P, i);
+    const int jt = Topo::jtype(P, i);
+    const int vo = Topo::voff(P, i), qo = Topo::qoff(P, i);
+    double sn = 0.0, cs = 1.0;
+    if (jt == JRevolute) sincos(q[qo], &sn, &cs);
+    M3 E;
+    V3 r;
+    joint_xform<Topo>(P, i, q, sn, cs, E, r);
+    SV vi = (p >= 0) ? motion_to_child(E, r, vel[p]) : svz();
+    if (jt == JRevolute) vi.a = axis_add<Topo>(P, i, vi.a, v[vo]);
+    else if (jt == JPrismatic) vi.l = axis_add<Topo>(P, i, vi.l, v[vo]);
+    else if (jt == JFloating) {
+      vi.a += V3{v[vo], v[vo + 1], v[vo + 2]};
+      vi.l += V3{v[vo + 3], v[vo + 4], v[vo + 5]};
+    }
+    vel[i] = vi;
+    if (p >= 0) {
+      Rw[i] = mul(Rw[p], E);
+      tw[i] = tw[p] + mul(Rw[p], r);
+    } else {
+      Rw[i] = E;
+      tw[i] = r;
+    }
+    // KE_i = (w.(J w) + v.(m v + 2 w x c)) / 2   (reference inertia.rs:182-202, frame invariant)
+    const S3 J = lds3(P.J[i]);
+    const V3 c = ld3(P.mc[i]);
+    ke += (dot(vi.a, mul(J, vi.a)) + dot(vi.l, vi.l * P.mass[i] + cross(vi.a, c) * 2.0)) * 0.5;
+    // PE_i = m g z of the FRAME ORIGIN (reference mechanism.rs:352-362)
+    pe += P.mass[i] * kGravity * tw[i].z;
+    if (jt == JPrismatic && P.has_spring[i]) {
+      const double dl = q[qo] - P.spring_l[i];
+      se += 0.5 * P.spring_k[i] * dl * dl;  // reference energy.rs:3-5
+    }
+    if (poses) {
+      // joint quaternion: init * Rot(axis, q) | init | init * pose  (Hamilton products)
+      double jq[4] = {P.iq[i][0], P.iq[i][1], P.iq[i][2], P.iq[i][3]};
+      double lq[4] = {0, 0, 0, 1};
+      bool has_l = false;
+      if (jt == JRevolute) {
+        double sh, ch;
+        sincos(0.5 * q[qo], &sh, &ch);
+        lq[0] = P.axis[i][0] * sh; lq[1] = P.axis[i][1] * sh; lq[2] = P.axis[i][2] * sh; lq[3] = ch;
+        has_l = true;
+      } else if (jt == JFloating) {
+        lq[0] = q[qo]; lq[1] = q[qo + 1]; lq[2] = q[qo + 2]; lq[3] = q[qo + 3];
+        has_l = true;
+      }
+      auto qmul = [](const double* a, const double* b, double* o) {
+        const double ax = a[0], ay = a[1], az = a[2], aw = a[3];
+        const double bx = b[0], by = b[1], bz = b[2], bw = b[3];
+        o[0] = aw * bx + ax * bw + ay * bz - az * by;
+        o[1] = aw * by - ax * bz + ay * bw + az * bx;
+        o[2] = aw * bz + ax * by - ay * bx + az * bw;
+        o[3] = aw * bw - ax * bx - ay * by - az * bz;
+      };
+      double jq2[4];
+      if (has_l) qmul(jq, lq, jq2);
+      else { jq2[0] = jq[0]; jq2[1] = jq[1]; jq2[2] = jq[2]; jq2[3] = jq[3]; }
+      if (p >= 0) qmul(qw[p], jq2, qw[i]);
+      else { qw[i][0] = jq2[0]; qw[i][1] = jq2[1]; qw[i][2] = jq2[2]; qw[i][3] = jq2[3]; }
+      double* o = poses + (long long)(7 * i) * ld + env;
+      o[0] = qw[i][0]; o[ld] = qw[i][1]; o[2 * ld] = qw[i][2]; o[3 * ld] = qw[i][3];
+      o[4 * ld] = tw[i].x; o[5 * ld] = tw[i].y; o[6 * ld] = tw[i].z;
+    }
+  });
+}
+
+// ---- in-kernel controllers (reference closures Fn(&MechanismState) -> Vec<JointTorque>) -----
+template <class Topo>
+GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q, const double* v,
+                         const double* tau_in, double* tau) {
+  constexpr int NV = Topo::NV;
+  constexpr int U = Topo::kUnroll;
+  if (A.controller == GP_CTRL_SO101_PD) {
+    // SO101PositionController, reference control/so101_control.rs:12-34
+    const double kp = A.cp[0], kd = A.cp[1], cl = A.cp[2];
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      const int jt = Topo::jtype(P, i);
+      if (jt == JRevolute || jt == JPrismatic) {
+        const double t = kp * (0.0 - q[Topo::qoff(P, i)]) - kd * v[Topo::voff(P, i)];
+        tau[Topo::voff(P, i)] = copysign(fmin(fabs(t), cl), t);
+      } else if (jt == JFloating) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tau[Topo::voff(P, i) + k] = 0.0;
+      }
+    });
+    return;
+  }
+  if constexpr (Topo::NQ == 2 && Topo::NV == 2) {
+    if (A.controller == GP_CTRL_ACROBOT_SWINGUP) {
+      // swingup_acrobot, reference control/swingup.rs:9-69
+      const double m = A.cp[0], l = A.cp[1];
+      const double q1 = q[0], q1dot = v[0], q2dot = v[1];
+      double KE, PEu, SEu;
+      energy_core<Topo>(P, q, v, KE, PEu, SEu, nullptr, 0, 0);
+      const double PE = m * kGravity * (l * sin(q1) + (l * sin(q1) + l * sin(q1 + q[1])));  // energy.rs:19-26
+      const double E_target = m * kGravity * (l + 2.0 * l);
+      const double dE = KE + PE - E_target;
+      double u_bar = 2.0 * (dE * q1dot);
+      u_bar = fmin(fmax(u_bar, -10.0), 10.0);
+      const double two_pi = 6.283185307179586476925286766559;
+      double q2 = fmod(q[1], two_pi);
+      if (q2 < 0.0) q2 += two_pi;  // rem_euclid
+      if (q2 > 3.14159265358979323846) q2 -= two_pi;
+      const double u_pd = -2.0 * q2 - 2.0 * q2dot;
+      const double c1 = cos(q1), s2 = sin(q2), c2 = cos(q2), c12 = cos(q1 + q2);
+      const double ll = l * l;
+      const double m11 = m * ll + m * (ll + ll + 2. * ll * c2);
+      const double m22 = m * ll;
+      const double m12 = m * (ll + ll * c2);
+      const double h1 = -m * ll * s2 * q2dot * q2dot - 2. * m * ll * s2 * q2dot * q1dot;
+      const double h2 = m * ll * s2 * q1dot * q1dot;
+      const double phi1 = (m * l + m * l) * kGravity * c1 + m * l * kGravity * c12;
+      const double phi2 = m * l * kGravity * c12;
+      const double m22_bar = m22 - m12 * m12 / m11;
+      const double h2_bar = h2 - m12 * h1 / m11;
+      const double phi2_bar = phi2 - m12 * phi1 / m11;
+      tau[0] = 0.0;
+      tau[1] = m22_bar * (u_bar + u_pd) + h2_bar + phi2_bar;
+      return;
+    }
+    if (A.controller == GP_CTRL_CARTPOLE_SWINGUP) {
+      // swingup_cart_pole, reference control/swingup.rs:76-110
+      const double m_c = A.cp[0], m_p = A.cp[1], l = A.cp[2];
+      const double theta = q[1], theta_dot = v[1];
+      double st, ct;
+      sincos(theta, &st, &ct);
+      const double KE = 0.5 * m_p * l * l * theta_dot * theta_dot;
+      const double PE = -m_p * kGravity * l * ct;
+      const double dE = KE + PE - m_p * kGravity * l;
+      const double u_bar = 2.0 * theta_dot * ct * dE / (m_p * l);
+      const double u = u_bar + (-1.0 * q[0] - 1.0 * v[0]);
+      tau[0] = (m_c + m_p * st * st) * u - m_p * kGravity * st * ct - m_p * l * st * theta_dot * theta_dot;
+      tau[1] = 0.0;
+      return;
+    }
+  }
+  // GP_CTRL_NONE: torques as loaded
+#pragma unroll U
+  for (int k = 0; k < Topo::nv(P); ++k) tau[k] = tau_in[k];
+  (void)NV;
+}
+
+GP_D bool all_finite(const double* a, int n) {
+  bool ok = true;
+  for (int k = 0; k < n; ++k) ok = ok && isfinite(a[k]);
+  return ok;
+}
+
+// ---- step kernel: n_steps of step() per launch (reference simulate.rs:20-83) -----------------
+template <class Topo, bool CONTACT, int INTEG>
+__global__ void __launch_bounds__(kBlock)
+step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
+  constexpr int NQ = Topo::NQ, NV = Topo::NV;
+  constexpr int U = Topo::kUnroll;
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= A.n) return;
+  const int nq = Topo::nq(P), nv = Topo::nv(P);
+
+  double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
+#pragma unroll U
+  for (int k = 0; k < nq; ++k) q[k] = A.q[(long long)k * A.ld + env];
+#pragma unroll U
+  for (int k = 0; k < nv; ++k) {
+    v[k] = A.v[(long long)k * A.ld + env];
+    tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
+  }
+  unsigned status = 0u;
+  DynOut none{nullptr, nullptr, nullptr, 0, 0};
+
+#pragma unroll 1
+  for (int s = 0; s < A.n_steps; ++s) {
+    controller_tau<Topo>(P, A, q, v, tau_in, tau);
+    if (INTEG == IntegSIE) {
+      // semi_implicit_euler, reference integrators.rs:25-39, :276-319
+      status |= dynamics_core<Topo, CONTACT, false>(P, q, v, tau, vdot, none);
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) v[k] = v[k] + vdot[k] * A.dt;
+      advance_q<Topo>(P, q, v, A.dt, q);
+    } else {
+      // runge_kutta_2 / runge_kutta_4, reference integrators.rs:177-225 with euler_step :230-271
+      const bool rk4 = (A.integrator == GP_RUNGE_KUTTA_4);
+      const int n_stage = rk4 ? 4 : 2;
+      double q0[NQ], v0[NV], facc[NV];
+#pragma unroll U
+      for (int k = 0; k < nq; ++k) q0[k] = q[k];
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) { v0[k] = v[k]; facc[k] = 0.0; }
+#pragma unroll 1
+      for (int st = 0; st < n_stage; ++st) {
+        status |= dynamics_core<Topo, CONTACT, false>(P, q, v, tau, vdot, none);
+        if (st + 1 < n_stage) {
+          // RK4: f1 + 2 f2 + 2 f3 (+ f4 below), stage steps dt/2, dt/2, dt ; RK2: stage step dt/2
+          const double wgt = (st == 0) ? 1.0 : 2.0;
+          const double h = (rk4 && st == 2) ? A.dt : A.dt / 2.0;
+#pragma unroll U
+          for (int k = 0; k < nv; ++k) facc[k] = facc[k] + vdot[k] * wgt;
+          advance_q<Topo>(P, q0, v0, h, q);
+#pragma unroll U
+          for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * h;
+        }
+      }
+      if (rk4) {
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) vdot[k] = (facc[k] + vdot[k]) / 6.0;
+      }
+      advance_q<Topo>(P, q0, v0, A.dt, q);
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * A.dt;
+    }
+  }
+
+#pragma unroll U
+  for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
+#pragma unroll U
+  for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
+  if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
+  if (status) A.status[env] |= status;
+}
+
+// ---- dynamics kernel: dynamics_continuous once, with the parity outputs ----------------------
+template <class Topo, bool CONTACT>
+__global__ void __launch_bounds__(kBlock)
+dynamics_kernel(const __grid_constant__ MechParams P, const __grid_constant__ DynArgs A) {
+  constexpr int NQ = Topo::NQ, NV = Topo::NV;
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= A.n) return;
+  const int nq = Topo::nq(P), nv = Topo::nv(P);
+  constexpr int U = Topo::kUnroll;
+  double q[NQ], v[NV], tau[NV], vdot[NV];
+#pragma unroll U
+  for (int k = 0; k < nq; ++k) q[k] = A.q[(long long)k * A.ld + env];
+#pragma unroll U
+  for (int k = 0; k < nv; ++k) {
+    v[k] = A.v[(long long)k * A.ld + env];
+    tau[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
+  }
+  DynOut out{A.contact_force, A.mass_matrix, A.bias, A.ld, env};
+  if (A.contact_force)
+    for (int c = 0; c < 3 * P.n_cp; ++c) A.contact_force[(long long)c * A.ld + env] = 0.0;
+  unsigned status = dynamics_core<Topo, CONTACT, true>(P, q, v, tau, vdot, out);
+#pragma unroll U
+  for (int k = 0; k < nv; ++k) A.vdot[(long long)k * A.ld + env] = vdot[k];
+  if (!all_finite(vdot, nv)) status |= kEnvNaN;
+  if (status) A.status[env] |= status;
+}
+
+// ---- energy / poses kernel -------------------------------------------------------------------
+template <class Topo>
+__global__ void __launch_bounds__(kBlock)
+energy_kernel(const __grid_constant__ MechParams P, const __grid_constant__ EnergyArgs A) {
+  constexpr int NQ = Topo::NQ, NV = Topo::NV;
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= A.n) return;
+  constexpr int U = Topo::kUnroll;
+  double q[NQ], v[NV];
+#pragma unroll U
+  for (int k = 0; k < Topo::nq(P); ++k) q[k] = A.q[(long long)k * A.ld + env];
+#pragma unroll U
+  for (int k = 0; k < Topo::nv(P); ++k) v[k] = A.v[(long long)k * A.ld + env];
+  double ke, pe, se;
+  energy_core<Topo>(P, q, v, ke, pe, se, A.poses, A.ld, env);
+  if (A.ke) A.ke[env] = ke;
+  if (A.pe) A.pe[env] = pe;
+  if (A.spring) A.spring[env] = se;
+}
+
+// ---- launchers (table type in gp_launch.h) ------------------------------------------------
+inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+template <class Topo>
+cudaError_t launch_step(bool contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
+  const dim3 g(grid_for(A.n)), b(kBlock);
+  if (integ_class == IntegSIE) {
+    if (contact) step_kernel<Topo, true, IntegSIE><<<g, b, 0, s>>>(P, A);
+    else step_kernel<Topo, false, IntegSIE><<<g, b, 0, s>>>(P, A);
+  } else {
+    if (contact) step_kernel<Topo, true, IntegRK><<<g, b, 0, s>>>(P, A);
+    else step_kernel<Topo, false, IntegRK><<<g, b, 0, s>>>(P, A);
+  }
+  return cudaGetLastError();
+}
+template <class Topo>
+cudaError_t launch_dynamics(bool contact, cudaStream_t s, const MechParams& P, const DynArgs& A) {
+  const dim3 g(grid_for(A.n)), b(kBlock);
+  if (contact) dynamics_kernel<Topo, true><<<g, b, 0, s>>>(P, A);
+  else dynamics_kernel<Topo, false><<<g, b, 0, s>>>(P, A);
+  return cudaGetLastError();
+}
+template <class Topo>
+cudaError_t launch_energy(cudaStream_t s, const MechParams& P, const EnergyArgs& A) {
+  const dim3 g(grid_for(A.n)), b(kBlock);
+  energy_kernel<Topo><<<g, b, 0, s>>>(P, A);
+  return cudaGetLastError();
+}
+
+template <class Topo, class Spec>
+KernelTable make_static_table() {
+  return KernelTable{Spec::name(), Spec::data(), true, &launch_step<Topo>, &launch_dynamics<Topo>,
+                     &launch_energy<Topo>};
+}
+template <class Topo>
+KernelTable make_generic_table() {
+  return KernelTable{"generic", TopoData{}, false, &launch_step<Topo>, &launch_dynamics<Topo>,
+                     &launch_energy<Topo>};
+}
+
+}  // namespace gp

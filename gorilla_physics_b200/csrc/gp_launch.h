@@ -1,0 +1,81 @@
+// gp_launch.h — host-visible launch interface of the kernel variants (no device code).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gp_params.h"
+
+namespace gp {
+
+constexpr int kBlock = 128;
+
+enum IntegClass : int { IntegSIE = 0, IntegRK = 1 };
+
+struct StepArgs {
+  double* q;          // [n_q][ld]
+  double* v;          // [n_v][ld]
+  const double* tau;  // [n_v][ld] or nullptr (zeros: reference simulate.rs:27-48)
+  unsigned* status;   // [n]
+  long long n, ld;
+  double dt;
+  int n_steps;
+  int integrator;  // gp_integrator
+  int controller;  // gp_controller
+  double cp[4];    // controller parameters
+};
+
+struct DynArgs {
+  const double* q;
+  const double* v;
+  const double* tau;
+  double* vdot;           // [n_v][ld]
+  double* contact_force;  // [n_cp][3][ld] or nullptr
+  double* mass_matrix;    // [n_v][n_v][ld] or nullptr
+  double* bias;           // [n_v][ld] or nullptr
+  unsigned* status;
+  long long n, ld;
+};
+
+struct EnergyArgs {
+  const double* q;
+  const double* v;
+  double* ke;      // [n] or nullptr
+  double* pe;      // [n] or nullptr
+  double* spring;  // [n] or nullptr
+  double* poses;   // [nb][7][ld] or nullptr
+  long long n, ld;
+};
+
+// ---- launch table -------------------------------------------------------------------------------
+struct KernelTable {
+  const char* name;
+  TopoData topo;
+  bool is_static;
+  cudaError_t (*step)(bool contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
+  cudaError_t (*dynamics)(bool contact, cudaStream_t, const MechParams&, const DynArgs&);
+  cudaError_t (*energy)(cudaStream_t, const MechParams&, const EnergyArgs&);
+};
+
+// defined one per translation unit under variants/
+const KernelTable* variant_generic();
+const KernelTable* variant_pendulum();
+const KernelTable* variant_double_pendulum();
+const KernelTable* variant_cart_pole();
+const KernelTable* variant_so101();
+const KernelTable* variant_floating();
+const KernelTable* variant_hopper1d();
+const KernelTable* variant_hopper();
+const KernelTable* variant_quadruped();
+const KernelTable* variant_navbot();
+
+
+// every compiled variant, generic last
+inline const KernelTable* const* all_variants(int* n) {
+  static const KernelTable* v[] = {variant_pendulum(),  variant_double_pendulum(), variant_cart_pole(),
+                                   variant_so101(),     variant_floating(),        variant_hopper1d(),
+                                   variant_hopper(),    variant_quadruped(),       variant_navbot(),
+                                   variant_generic()};
+  *n = (int)(sizeof(v) / sizeof(v[0]));
+  return v;
+}
+
+}  // namespace gp

@@ -1,0 +1,145 @@
+// gp_math.cuh — 3-vectors, 3x3 rotations and spatial (Pluecker) transforms in f64.
+// Device-side replacements for the nalgebra operations the reference leans on
+// (SURVEY.md §8c table); everything is expressed in body coordinates.
+#pragma once
+#include "gp_topology.cuh"
+
+namespace gp {
+
+struct V3 {
+  double x, y, z;
+};
+GP_HD V3 v3(double x, double y, double z) { return V3{x, y, z}; }
+GP_HD V3 v3z() { return V3{0.0, 0.0, 0.0}; }
+GP_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+GP_HD V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+GP_HD V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+GP_HD V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+GP_HD V3 operator*(double s, V3 a) { return {a.x * s, a.y * s, a.z * s}; }
+GP_HD V3& operator+=(V3& a, V3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
+GP_HD V3& operator-=(V3& a, V3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
+GP_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+GP_HD V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+GP_HD V3 ld3(const double* p) { return {p[0], p[1], p[2]}; }
+
+// rotation / general 3x3, row-major
+struct M3 {
+  double m[9];
+};
+GP_HD V3 mul(const M3& E, V3 v) {
+  return {E.m[0] * v.x + E.m[1] * v.y + E.m[2] * v.z, E.m[3] * v.x + E.m[4] * v.y + E.m[5] * v.z,
+          E.m[6] * v.x + E.m[7] * v.y + E.m[8] * v.z};
+}
+GP_HD V3 mulT(const M3& E, V3 v) {
+  return {E.m[0] * v.x + E.m[3] * v.y + E.m[6] * v.z, E.m[1] * v.x + E.m[4] * v.y + E.m[7] * v.z,
+          E.m[2] * v.x + E.m[5] * v.y + E.m[8] * v.z};
+}
+GP_HD M3 mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      R.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+  return R;
+}
+GP_HD M3 ldm3(const double* p) {
+  M3 R;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R.m[i] = p[i];
+  return R;
+}
+GP_HD M3 m3_identity() { return M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+
+// unit quaternion (x,y,z,w) -> rotation matrix, the formula nalgebra's to_rotation_matrix uses
+GP_HD M3 quat_to_mat(double i, double j, double k, double w) {
+  double ww = w * w, ii = i * i, jj = j * j, kk = k * k;
+  double ij = i * j * 2.0, wk = w * k * 2.0, wj = w * j * 2.0;
+  double ik = i * k * 2.0, jk = j * k * 2.0, wi = w * i * 2.0;
+  return M3{{ww + ii - jj - kk, ij - wk, wj + ik, wk + ij, ww - ii + jj - kk, jk - wi, ik - wj, wi + jk,
+             ww - ii - jj + kk}};
+}
+
+// symmetric 3x3 stored xx,xy,xz,yy,yz,zz
+struct S3 {
+  double xx, xy, xz, yy, yz, zz;
+};
+GP_HD S3 lds3(const double* p) { return {p[0], p[1], p[2], p[3], p[4], p[5]}; }
+GP_HD V3 mul(const S3& J, V3 v) {
+  return {J.xx * v.x + J.xy * v.y + J.xz * v.z, J.xy * v.x + J.yy * v.y + J.yz * v.z,
+          J.xz * v.x + J.yz * v.y + J.zz * v.z};
+}
+GP_HD S3 operator+(const S3& a, const S3& b) {
+  return {a.xx + b.xx, a.xy + b.xy, a.xz + b.xz, a.yy + b.yy, a.yz + b.yz, a.zz + b.zz};
+}
+
+// E J E^T for symmetric J
+GP_HD S3 rotate_sym(const M3& E, const S3& J) {
+  // T = E J (rows of E times symmetric J)
+  double t[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double a = E.m[3 * i], b = E.m[3 * i + 1], c = E.m[3 * i + 2];
+    t[3 * i + 0] = a * J.xx + b * J.xy + c * J.xz;
+    t[3 * i + 1] = a * J.xy + b * J.yy + c * J.yz;
+    t[3 * i + 2] = a * J.xz + b * J.yz + c * J.zz;
+  }
+  S3 R;
+  R.xx = t[0] * E.m[0] + t[1] * E.m[1] + t[2] * E.m[2];
+  R.xy = t[0] * E.m[3] + t[1] * E.m[4] + t[2] * E.m[5];
+  R.xz = t[0] * E.m[6] + t[1] * E.m[7] + t[2] * E.m[8];
+  R.yy = t[3] * E.m[3] + t[4] * E.m[4] + t[5] * E.m[5];
+  R.yz = t[3] * E.m[6] + t[4] * E.m[7] + t[5] * E.m[8];
+  R.zz = t[6] * E.m[6] + t[7] * E.m[7] + t[8] * E.m[8];
+  return R;
+}
+
+// spatial vector: angular part, linear part
+struct SV {
+  V3 a, l;
+};
+GP_HD SV svz() { return SV{v3z(), v3z()}; }
+
+// motion vector from predecessor to successor coordinates. E maps successor-frame vectors
+// to the predecessor frame, r is the successor origin in predecessor coordinates.
+GP_HD SV motion_to_child(const M3& E, V3 r, const SV& p) {
+  return SV{mulT(E, p.a), mulT(E, p.l + cross(p.a, r))};
+}
+// force vector from successor to predecessor coordinates
+GP_HD SV force_to_parent(const M3& E, V3 r, const SV& f) {
+  V3 fl = mul(E, f.l);
+  return SV{mul(E, f.a) + cross(r, fl), fl};
+}
+
+// rigid-body inertia about the frame origin: (J, c = m * com, m)
+struct RBI {
+  S3 J;
+  V3 c;
+  double m;
+};
+// I * (w; v) = (J w + c x v ; m v - c x w)        reference util.rs:18-28 mul_inertia
+GP_HD SV mul(const RBI& I, const SV& v) {
+  return SV{mul(I.J, v.a) + cross(I.c, v.l), v.l * I.m - cross(I.c, v.a)};
+}
+// express an inertia given in the successor frame in the predecessor frame
+// (same algebra as reference inertia.rs:106-134, with Y = w r^T + r w^T, w = c' + (m/2) r)
+GP_HD RBI inertia_to_parent(const M3& E, V3 r, const RBI& I) {
+  V3 c1 = mul(E, I.c);
+  S3 J1 = rotate_sym(E, I.J);
+  V3 w = c1 + r * (0.5 * I.m);
+  double tr = 2.0 * dot(w, r);
+  RBI R;
+  R.J.xx = J1.xx - 2.0 * w.x * r.x + tr;
+  R.J.yy = J1.yy - 2.0 * w.y * r.y + tr;
+  R.J.zz = J1.zz - 2.0 * w.z * r.z + tr;
+  R.J.xy = J1.xy - (w.x * r.y + r.x * w.y);
+  R.J.xz = J1.xz - (w.x * r.z + r.x * w.z);
+  R.J.yz = J1.yz - (w.y * r.z + r.y * w.z);
+  R.c = c1 + r * I.m;
+  R.m = I.m;
+  return R;
+}
+
+}  // namespace gp

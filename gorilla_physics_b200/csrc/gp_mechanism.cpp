@@ -1,0 +1,347 @@
+// gp_mechanism.cpp — mechanism handles of the C ABI: validation, flattening to device
+// constants, kernel-variant selection. Host only; needs no GPU.
+//
+// Replaces the bookkeeping half of MechanismState::new (reference src/mechanism.rs:62-148):
+// parents and supports become integer tables, joint transforms become the constant matrices
+// the kernels combine with sin/cos of the joint angle.
+#include <cmath>
+#include <cstring>
+
+#include "gp_host.h"
+#include "gp_topology.cuh"
+
+namespace gp {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+const std::string& last_error() { return g_last_error; }
+
+void quat_to_mat_host(const double q[4], double R[9]) {
+  const double i = q[0], j = q[1], k = q[2], w = q[3];
+  const double ww = w * w, ii = i * i, jj = j * j, kk = k * k;
+  const double ij = i * j * 2.0, wk = w * k * 2.0, wj = w * j * 2.0;
+  const double ik = i * k * 2.0, jk = j * k * 2.0, wi = w * i * 2.0;
+  R[0] = ww + ii - jj - kk; R[1] = ij - wk;           R[2] = wj + ik;
+  R[3] = wk + ij;           R[4] = ww - ii + jj - kk; R[5] = jk - wi;
+  R[6] = ik - wj;           R[7] = wi + jk;           R[8] = ww - ii - jj + kk;
+}
+
+static void mat_mul(const double A[9], const double B[9], double C[9]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) C[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+}
+
+int finalize_mechanism(gp_mechanism* m) {
+  MechParams& P = m->params;
+  std::memset(&P, 0, sizeof(P));
+  const int nb = m->nb;
+
+  TopoData td{};
+  td.nb = nb;
+  for (int i = 0; i < nb; ++i) {
+    td.parent[i] = m->parent[i] - 1;
+    td.jtype[i] = m->joint_type[i];
+    const double* a = &m->axis[3 * i];
+    const bool scalar = (td.jtype[i] == JRevolute || td.jtype[i] == JPrismatic);
+    td.axis[i] = (scalar && a[0] == 0.0 && a[1] == 0.0 && a[2] == 1.0) ? AxZ : AxAny;
+  }
+  const TopoTables t = make_tables(td);
+  if (t.nv > kMaxNV || t.nq > kMaxNQ) {
+    set_error("mechanism has n_v=%d n_q=%d, limits are %d / %d", t.nv, t.nq, kMaxNV, kMaxNQ);
+    return GP_ERR_LIMIT;
+  }
+  m->n_q = t.nq;
+  m->n_v = t.nv;
+  P.nb = nb;
+  P.n_q = t.nq;
+  P.n_v = t.nv;
+  P.n_cp = m->n_cp();
+  P.n_hs = m->n_hs();
+  for (int i = 0; i < kMaxBodies; ++i) {
+    P.parent[i] = t.parent[i];
+    P.jtype[i] = t.jtype[i];
+    P.qoff[i] = t.qoff[i];
+    P.voff[i] = t.voff[i];
+    P.depth[i] = t.depth[i];
+    P.anc_mask[i] = t.anc_mask[i];
+    P.has_children[i] = t.has_children[i];
+    for (int k = 0; k < kMaxBodies; ++k) P.anc_at[i][k] = t.anc_at[i][k];
+  }
+  for (int k = 0; k < kMaxNV; ++k) P.dof_body[k] = t.dof_body[k];
+
+  for (int i = 0; i < nb; ++i) {
+    const double* iso = &m->init_iso[7 * i];
+    double E0[9];
+    quat_to_mat_host(iso, E0);
+    const double* a = &m->axis[3 * i];
+    for (int k = 0; k < 4; ++k) P.iq[i][k] = iso[k];
+    for (int k = 0; k < 3; ++k) {
+      P.r0[i][k] = iso[4 + k];
+      P.axis[i][k] = a[k];
+      P.Ea[i][k] = E0[3 * k] * a[0] + E0[3 * k + 1] * a[1] + E0[3 * k + 2] * a[2];
+    }
+    if (td.jtype[i] == JRevolute) {
+      // E0 * Rot(a, q) = Cm + cos(q) A + sin(q) B,  Cm = E0 a a^T, A = E0 - Cm, B = E0 [a]x
+      const double aaT[9] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[0], a[1] * a[1],
+                             a[1] * a[2], a[2] * a[0], a[2] * a[1], a[2] * a[2]};
+      const double K[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+      double Cm[9], B[9];
+      mat_mul(E0, aaT, Cm);
+      mat_mul(E0, K, B);
+      for (int k = 0; k < 9; ++k) {
+        P.Cm[i][k] = Cm[k];
+        P.A[i][k] = E0[k] - Cm[k];
+        P.B[i][k] = B[k];
+      }
+    } else {
+      for (int k = 0; k < 9; ++k) P.Cm[i][k] = E0[k];
+    }
+    const double* J = &m->moment[9 * i];
+    P.J[i][0] = J[0]; P.J[i][1] = J[1]; P.J[i][2] = J[2];
+    P.J[i][3] = J[4]; P.J[i][4] = J[5]; P.J[i][5] = J[8];
+    for (int k = 0; k < 3; ++k) P.mc[i][k] = m->cross_part[3 * i + k];
+    P.mass[i] = m->mass[i];
+    P.has_spring[i] = m->has_spring[i];
+    P.spring_k[i] = m->spring_k[i];
+    P.spring_l[i] = m->spring_l[i];
+  }
+  // contact points are stored body-major already
+  int c = 0;
+  for (int b = 0; b < nb; ++b) {
+    P.cp_begin[b] = c;
+    while (c < m->n_cp() && m->cp_body[c] == b + 1) ++c;
+  }
+  for (int b = nb; b <= kMaxBodies; ++b) P.cp_begin[b] = c;
+  for (int k = 0; k < m->n_cp(); ++k) {
+    for (int d = 0; d < 3; ++d) P.cp_loc[k][d] = m->cp_location[3 * k + d];
+    const double k_A = m->cp_k[k], k_B = 50e3;  // reference contact.rs:328, :274
+    P.cp_k[k] = k_A * k_B / (k_A + k_B);
+  }
+  for (int h = 0; h < m->n_hs(); ++h) {
+    for (int d = 0; d < 3; ++d) {
+      P.hs_point[h][d] = m->hs_point[3 * h + d];
+      P.hs_normal[h][d] = m->hs_normal[3 * h + d];
+    }
+    P.hs_alpha[h] = m->hs_alpha[h];
+    P.hs_mu[h] = m->hs_mu[h];
+  }
+
+  // kernel variant: first compiled specialisation whose signature matches, else generic
+  int nvar = 0;
+  const KernelTable* const* vars = all_variants(&nvar);
+  m->table = vars[nvar - 1];
+  for (int k = 0; k < nvar - 1; ++k)
+    if (topo_matches(vars[k]->topo, td)) {
+      m->table = vars[k];
+      break;
+    }
+  m->revision++;
+  return GP_OK;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" {
+
+int gp_abi_version(void) { return GP_ABI_VERSION; }
+
+size_t gp_last_error(char* buf, size_t len) {
+  const std::string& e = last_error();
+  if (buf && len > 0) {
+    const size_t n = e.size() < len - 1 ? e.size() : len - 1;
+    std::memcpy(buf, e.data(), n);
+    buf[n] = '\0';
+  }
+  return e.size();
+}
+
+int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
+  if (!d || !out) {
+    set_error("gp_mechanism_create: null argument");
+    return GP_ERR_INVALID;
+  }
+  *out = nullptr;
+  const int nb = d->n_bodies;
+  if (nb < 1 || nb > kMaxBodies) {
+    set_error("n_bodies=%d outside [1, %d]", nb, kMaxBodies);
+    return nb > kMaxBodies ? GP_ERR_LIMIT : GP_ERR_INVALID;
+  }
+  if (d->n_contact_points < 0 || d->n_contact_points > kMaxCP || d->n_halfspaces < 0 ||
+      d->n_halfspaces > kMaxHS) {
+    set_error("n_contact_points=%d (max %d) / n_halfspaces=%d (max %d)", d->n_contact_points, kMaxCP,
+              d->n_halfspaces, kMaxHS);
+    return GP_ERR_LIMIT;
+  }
+  if (!d->parent || !d->joint_type || !d->axis || !d->init_iso || !d->moment || !d->cross_part || !d->mass) {
+    set_error("gp_mechanism_create: null array in description");
+    return GP_ERR_INVALID;
+  }
+  gp_mechanism* m = new gp_mechanism();
+  m->nb = nb;
+  for (int i = 0; i < nb; ++i) {
+    const int p = d->parent[i];
+    // reference mechanism.rs:98-125: the parent frame must be the world or an earlier body
+    if (p < 0 || p > i) {
+      set_error("joint %d has no parent body %d (parents must precede children)", i + 1, p);
+      delete m;
+      return GP_ERR_INVALID;
+    }
+    const int jt = d->joint_type[i];
+    if (jt < GP_JOINT_FIXED || jt > GP_JOINT_FLOATING) {
+      set_error("joint %d: unknown joint type %d", i + 1, jt);
+      delete m;
+      return GP_ERR_INVALID;
+    }
+    const double* a = d->axis + 3 * i;
+    if (jt == GP_JOINT_REVOLUTE || jt == GP_JOINT_PRISMATIC) {
+      const double n2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+      if (!(std::fabs(n2 - 1.0) < 1e-9)) {
+        set_error("joint %d: axis is not a unit vector (|a|^2 = %.17g)", i + 1, n2);
+        delete m;
+        return GP_ERR_INVALID;
+      }
+    }
+    const double* q = d->init_iso + 7 * i;
+    const double qn = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (!(std::fabs(qn - 1.0) < 1e-9)) {
+      set_error("joint %d: init_iso rotation is not a unit quaternion (|q|^2 = %.17g)", i + 1, qn);
+      delete m;
+      return GP_ERR_INVALID;
+    }
+    const double* J = d->moment + 9 * i;
+    double jmax = 0.0;
+    for (int k = 0; k < 9; ++k) jmax = std::fmax(jmax, std::fabs(J[k]));
+    if (std::fabs(J[1] - J[3]) > 1e-12 * jmax || std::fabs(J[2] - J[6]) > 1e-12 * jmax ||
+        std::fabs(J[5] - J[7]) > 1e-12 * jmax) {
+      set_error("body %d: moment of inertia is not symmetric", i + 1);
+      delete m;
+      return GP_ERR_INVALID;
+    }
+    m->parent.push_back(p);
+    m->joint_type.push_back(jt);
+    m->axis.insert(m->axis.end(), a, a + 3);
+    m->init_iso.insert(m->init_iso.end(), q, q + 7);
+    m->moment.insert(m->moment.end(), J, J + 9);
+    m->cross_part.insert(m->cross_part.end(), d->cross_part + 3 * i, d->cross_part + 3 * i + 3);
+    m->mass.push_back(d->mass[i]);
+    const bool sp = d->has_spring && d->has_spring[i] != 0;
+    m->has_spring.push_back(sp ? 1 : 0);
+    m->spring_k.push_back(sp && d->spring_k ? d->spring_k[i] : 0.0);
+    m->spring_l.push_back(sp && d->spring_l ? d->spring_l[i] : 0.0);
+  }
+  for (int h = 0; h < d->n_halfspaces; ++h) {
+    m->hs_point.insert(m->hs_point.end(), d->hs_point + 3 * h, d->hs_point + 3 * h + 3);
+    m->hs_normal.insert(m->hs_normal.end(), d->hs_normal + 3 * h, d->hs_normal + 3 * h + 3);
+    m->hs_alpha.push_back(d->hs_alpha[h]);
+    m->hs_mu.push_back(d->hs_mu[h]);
+  }
+  int rc = finalize_mechanism(m);
+  for (int c = 0; rc == GP_OK && c < d->n_contact_points; ++c)
+    rc = gp_mechanism_add_contact_point(m, d->cp_body[c], d->cp_location + 3 * c, d->cp_k[c]);
+  if (rc != GP_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return GP_OK;
+}
+
+void gp_mechanism_destroy(gp_mechanism* m) { delete m; }
+int gp_mechanism_n_bodies(const gp_mechanism* m) { return m ? m->nb : 0; }
+int gp_mechanism_n_q(const gp_mechanism* m) { return m ? m->n_q : 0; }
+int gp_mechanism_n_v(const gp_mechanism* m) { return m ? m->n_v : 0; }
+int gp_mechanism_n_contact_points(const gp_mechanism* m) { return m ? m->n_cp() : 0; }
+int gp_mechanism_n_halfspaces(const gp_mechanism* m) { return m ? m->n_hs() : 0; }
+
+int gp_mechanism_get_desc(const gp_mechanism* m, gp_mechanism_desc* o) {
+  if (!m || !o) {
+    set_error("gp_mechanism_get_desc: null argument");
+    return GP_ERR_INVALID;
+  }
+  o->n_bodies = m->nb;
+  o->parent = m->parent.data();
+  o->joint_type = m->joint_type.data();
+  o->axis = m->axis.data();
+  o->init_iso = m->init_iso.data();
+  o->moment = m->moment.data();
+  o->cross_part = m->cross_part.data();
+  o->mass = m->mass.data();
+  o->has_spring = m->has_spring.data();
+  o->spring_k = m->spring_k.data();
+  o->spring_l = m->spring_l.data();
+  o->n_contact_points = m->n_cp();
+  o->cp_body = m->cp_body.data();
+  o->cp_location = m->cp_location.data();
+  o->cp_k = m->cp_k.data();
+  o->n_halfspaces = m->n_hs();
+  o->hs_point = m->hs_point.data();
+  o->hs_normal = m->hs_normal.data();
+  o->hs_alpha = m->hs_alpha.data();
+  o->hs_mu = m->hs_mu.data();
+  return GP_OK;
+}
+
+int gp_mechanism_add_halfspace(gp_mechanism* m, const double point[3], const double normal[3], double alpha,
+                               double mu) {
+  if (!m || !point || !normal) {
+    set_error("gp_mechanism_add_halfspace: null argument");
+    return GP_ERR_INVALID;
+  }
+  if (m->n_hs() >= kMaxHS) {
+    set_error("more than %d halfspaces", kMaxHS);
+    return GP_ERR_LIMIT;
+  }
+  m->hs_point.insert(m->hs_point.end(), point, point + 3);
+  m->hs_normal.insert(m->hs_normal.end(), normal, normal + 3);
+  m->hs_alpha.push_back(alpha);
+  m->hs_mu.push_back(mu);
+  return finalize_mechanism(m);
+}
+
+int gp_mechanism_add_contact_point(gp_mechanism* m, int32_t body, const double location[3], double k) {
+  if (!m || !location) {
+    set_error("gp_mechanism_add_contact_point: null argument");
+    return GP_ERR_INVALID;
+  }
+  if (body < 1 || body > m->nb) {  // reference mechanism.rs:384-391 silently ignores unknown frames
+    set_error("contact point on unknown body %d", body);
+    return GP_ERR_INVALID;
+  }
+  if (m->n_cp() >= kMaxCP) {
+    set_error("more than %d contact points", kMaxCP);
+    return GP_ERR_LIMIT;
+  }
+  // keep body-major order, appended after the body's existing points
+  size_t pos = 0;
+  while (pos < m->cp_body.size() && m->cp_body[pos] <= body) ++pos;
+  m->cp_body.insert(m->cp_body.begin() + pos, body);
+  m->cp_location.insert(m->cp_location.begin() + 3 * pos, location, location + 3);
+  m->cp_k.insert(m->cp_k.begin() + pos, k);
+  return finalize_mechanism(m);
+}
+
+int gp_mechanism_supports(const gp_mechanism* m, int32_t* out) {
+  if (!m || !out) {
+    set_error("gp_mechanism_supports: null argument");
+    return GP_ERR_INVALID;
+  }
+  for (int j = 0; j < m->nb; ++j)
+    for (int i = 0; i < m->nb; ++i) out[j * m->nb + i] = (m->params.anc_mask[i] >> j) & 1u;
+  return GP_OK;
+}
+
+const char* gp_mechanism_kernel_variant(const gp_mechanism* m) {
+  return (m && m->table) ? m->table->name : "";
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// gp_params.h — mechanism constants as they travel to the device (one kernel parameter),
+// shared by host code and kernels.
+//
+// Built once on the host by gp_mechanism_create from a gp_mechanism_desc (the flat form of
+// what MechanismState::new receives, reference src/mechanism.rs:62-148). Bodies are
+// 0-based here (body b = reference body id b+1, parent -1 = world).
+#pragma once
+#include <cstdint>
+
+#include "../../include/gorilla_b200.h"
+
+namespace gp {
+
+constexpr int kMaxBodies = GP_MAX_BODIES;
+constexpr int kMaxNV = GP_MAX_NV;
+constexpr int kMaxNQ = 28;
+constexpr int kMaxCP = GP_MAX_CONTACT_POINTS;
+constexpr int kMaxHS = GP_MAX_HALFSPACES;
+
+constexpr double kGravity = 9.81;  // reference src/lib.rs:39
+
+enum JointType : int { JFixed = 0, JRevolute = 1, JPrismatic = 2, JFloating = 3 };
+
+// how a static kernel specialisation treats a joint axis
+enum AxisKind : int {
+  AxAny = 0,  // runtime axis from MechParams (matches every axis)
+  AxZ = 1     // exactly (0,0,1): SO-101 and navbot (builders/mod.rs:321-329, navbot_builder.rs:773-789)
+};
+
+// Topology signature: what a compile-time kernel specialisation is keyed on.
+struct TopoData {
+  int nb;
+  int parent[kMaxBodies];  // -1 = world
+  int jtype[kMaxBodies];
+  int axis[kMaxBodies];  // AxisKind
+};
+
+struct MechParams {
+  // ---- topology (used by the runtime-topology kernels; static ones fold their own tables)
+  int nb, n_q, n_v, n_cp, n_hs;
+  int parent[kMaxBodies];
+  int jtype[kMaxBodies];
+  int qoff[kMaxBodies];
+  int voff[kMaxBodies];
+  int depth[kMaxBodies];                // ancestors including self
+  int anc_at[kMaxBodies][kMaxBodies];   // anc_at[i][k] = k-th ancestor of i (k = 0 -> i)
+  unsigned anc_mask[kMaxBodies];        // bit j set: j is ancestor-or-self of i
+  int has_children[kMaxBodies];
+  int dof_body[kMaxNV];
+  int cp_begin[kMaxBodies + 1];  // contact points are body-major: [cp_begin[b], cp_begin[b+1])
+  int has_spring[kMaxBodies];
+
+  // ---- joints. successor->predecessor transform at joint position q:
+  //   revolute : E = Cm + cos(q) A + sin(q) B   (= E0 * Rot(axis, q), revolute.rs:97-102), r = r0
+  //   prismatic: E = Cm (= E0),  r = r0 + Ea * q   (prismatic.rs:82-87, Ea = E0 * axis)
+  //   floating : E = Cm * R(quat), r = r0 + Cm * t   (floating.rs:26-31)
+  //   fixed    : E = Cm, r = r0
+  // E maps successor-frame vectors to predecessor-frame vectors, row-major.
+  double A[kMaxBodies][9];
+  double B[kMaxBodies][9];
+  double Cm[kMaxBodies][9];
+  double r0[kMaxBodies][3];
+  double Ea[kMaxBodies][3];
+  double axis[kMaxBodies][3];
+  double iq[kMaxBodies][4];  // init_iso rotation as quaternion x,y,z,w (poses only)
+
+  // ---- body inertia about the body-frame origin (inertia.rs:32-37): J xx,xy,xz,yy,yz,zz
+  double J[kMaxBodies][6];
+  double mc[kMaxBodies][3];
+  double mass[kMaxBodies];
+  double spring_k[kMaxBodies];
+  double spring_l[kMaxBodies];
+
+  // ---- contact (contact.rs:17-38, halfspace.rs:6-11)
+  double cp_loc[kMaxCP][3];
+  double cp_k[kMaxCP];
+  double hs_point[kMaxHS][3];
+  double hs_normal[kMaxHS][3];
+  double hs_alpha[kMaxHS];
+  double hs_mu[kMaxHS];
+};
+
+}  // namespace gp

@@ -1,0 +1,309 @@
+// gp_topology.cuh — compile-time and run-time views of a mechanism's tree.
+//
+// The dynamics core is written once against a `Topo` policy. A StaticTopo<Spec> answers
+// every structural question (parent, joint type, offsets, ancestor sets) from tables the
+// front end evaluates at compile time, so that after full unrolling every body loop index,
+// every branch on joint type and every mass-matrix sparsity test is a literal and all
+// per-body arrays live in registers. DynTopo answers the same questions from MechParams at
+// run time (arrays land in local memory) and serves any tree the specialisations don't cover.
+//
+// Tables replace the reference's string-matched `parents` and HashSet `supports`
+// (src/mechanism.rs:98-125).
+#pragma once
+#include "gp_params.h"
+
+#if defined(__CUDACC__)
+#define GP_HD __host__ __device__ __forceinline__
+#define GP_D __device__ __forceinline__
+#else
+#define GP_HD inline
+#define GP_D inline
+#endif
+
+namespace gp {
+
+struct TopoTables {
+  int nb, nq, nv;
+  int parent[kMaxBodies];
+  int jtype[kMaxBodies];
+  int axis[kMaxBodies];
+  int qoff[kMaxBodies];
+  int voff[kMaxBodies];
+  int depth[kMaxBodies];
+  int anc_at[kMaxBodies][kMaxBodies];
+  unsigned anc_mask[kMaxBodies];
+  int has_children[kMaxBodies];
+  int dof_body[kMaxNV];
+};
+
+constexpr int joint_nq(int t) { return t == JFloating ? 7 : (t == JFixed ? 0 : 1); }
+constexpr int joint_nv(int t) { return t == JFloating ? 6 : (t == JFixed ? 0 : 1); }
+
+// derive every table from the signature (host + compile time)
+constexpr TopoTables make_tables(const TopoData& d) {
+  TopoTables t{};
+  t.nb = d.nb;
+  int qo = 0, vo = 0;
+  for (int i = 0; i < kMaxBodies; ++i) {
+    t.parent[i] = -1;
+    t.jtype[i] = JFixed;
+    t.axis[i] = AxAny;
+    t.depth[i] = 0;
+    t.anc_mask[i] = 0u;
+    t.has_children[i] = 0;
+    t.qoff[i] = 0;
+    t.voff[i] = 0;
+    for (int k = 0; k < kMaxBodies; ++k) t.anc_at[i][k] = -1;
+  }
+  for (int k = 0; k < kMaxNV; ++k) t.dof_body[k] = 0;
+  for (int i = 0; i < d.nb; ++i) {
+    t.parent[i] = d.parent[i];
+    t.jtype[i] = d.jtype[i];
+    t.axis[i] = d.axis[i];
+    t.qoff[i] = qo;
+    t.voff[i] = vo;
+    for (int k = 0; k < joint_nv(d.jtype[i]); ++k)
+      if (vo + k < kMaxNV) t.dof_body[vo + k] = i;
+    qo += joint_nq(d.jtype[i]);
+    vo += joint_nv(d.jtype[i]);
+    int c = i, k = 0;
+    while (c >= 0) {
+      t.anc_at[i][k++] = c;
+      t.anc_mask[i] |= (1u << c);
+      c = d.parent[c];
+    }
+    t.depth[i] = k;
+    if (d.parent[i] >= 0) t.has_children[d.parent[i]] = 1;
+  }
+  t.nq = qo;
+  t.nv = vo;
+  return t;
+}
+
+// Compile-time lookups. A run-time index i is resolved through a chain of selects over
+// template-constant K whose values are constant expressions, packed into integers where a
+// second index is needed. After full unrolling i is a literal and the chain folds away; there
+// is never a table object in device code (a local constexpr table per call site makes the
+// optimiser chew through thousands of allocas).
+template <class F, int K, int N>
+GP_HD constexpr unsigned long long select_chain(int i) {
+  if constexpr (K + 1 >= N) {
+    return F::template at<K>();
+  } else {
+    return (i == K) ? F::template at<K>() : select_chain<F, K + 1, N>(i);
+  }
+}
+
+// compile-time index + guaranteed unrolling: f(IC<0>{}), f(IC<1>{}), ... Each call instantiates
+// the (generic) lambda with a literal index, so topology lookups fold in the front end and the
+// per-body arrays are only ever indexed by constants. `#pragma unroll` alone is not reliable for
+// the large body loops (the 9-body trees were left rolled, with their arrays in local memory).
+template <int I>
+struct IC {
+  static constexpr int value = I;
+  GP_HD constexpr operator int() const { return I; }
+};
+template <int B, int E, class F>
+GP_HD void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(IC<B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+template <int B, int E, class F>
+GP_HD void static_rfor(F&& f) {  // E-1, E-2, ..., B
+  if constexpr (B < E) {
+    f(IC<E - 1>{});
+    static_rfor<B, E - 1>(f);
+  }
+}
+// body loops: unrolled at compile time for static topologies, run-time loops otherwise
+template <class Topo, class F>
+GP_HD void for_bodies(const MechParams& P, F&& f) {
+  if constexpr (Topo::kStatic) {
+    static_for<0, Topo::NB>(f);
+  } else {
+    for (int i = 0; i < P.nb; ++i) f(i);
+  }
+}
+template <class Topo, class F>
+GP_HD void for_bodies_reverse(const MechParams& P, F&& f) {
+  if constexpr (Topo::kStatic) {
+    static_rfor<0, Topo::NB>(f);
+  } else {
+    for (int i = P.nb - 1; i >= 0; --i) f(i);
+  }
+}
+template <class Topo, class F>
+GP_HD void for_dofs(const MechParams& P, F&& f) {
+  if constexpr (Topo::kStatic) {
+    static_for<0, Topo::kNVreal>(f);
+  } else {
+    for (int k = 0; k < P.n_v; ++k) f(k);
+  }
+}
+template <class Topo, class F>
+GP_HD void for_dofs_reverse(const MechParams& P, F&& f) {
+  if constexpr (Topo::kStatic) {
+    static_rfor<0, Topo::kNVreal>(f);
+  } else {
+    for (int k = P.n_v - 1; k >= 0; --k) f(k);
+  }
+}
+
+template <class Spec>
+struct StaticTopo {
+  static constexpr bool kStatic = true;
+  static constexpr TopoTables tables() { return make_tables(Spec::data()); }
+  static constexpr int NB = tables().nb;
+  static constexpr int NQ = tables().nq > 0 ? tables().nq : 1;
+  static constexpr int NV = tables().nv > 0 ? tables().nv : 1;
+  static constexpr int kNVreal = tables().nv;
+  static constexpr int kUnroll = 64;
+  static const char* name() { return Spec::name(); }
+
+  struct FParent { template <int K> static constexpr unsigned long long at() { return (unsigned long long)(tables().parent[K] + 1); } };
+  struct FJtype { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().jtype[K]; } };
+  struct FAxis { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().axis[K]; } };
+  struct FQoff { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().qoff[K]; } };
+  struct FVoff { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().voff[K]; } };
+  struct FDepth { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().depth[K]; } };
+  struct FChildren { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().has_children[K]; } };
+  // ancestors of body K packed 4 bits each (value + 1), k-th nibble = k-th ancestor
+  struct FAncRow {
+    template <int K> static constexpr unsigned long long at() {
+      unsigned long long w = 0;
+      for (int k = 0; k < kMaxBodies; ++k) w |= (unsigned long long)(tables().anc_at[K][k] + 1) << (4 * k);
+      return w;
+    }
+  };
+  struct FDofBody { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().dof_body[K]; } };
+  // bit a set: dof a's body is an ancestor-or-self of dof K's body
+  struct FDofAnc {
+    template <int K> static constexpr unsigned long long at() {
+      unsigned long long w = 0;
+      for (int a = 0; a < tables().nv; ++a)
+        if ((tables().anc_mask[tables().dof_body[K]] >> tables().dof_body[a]) & 1u) w |= 1ull << a;
+      return w;
+    }
+  };
+
+  // loop bound helper: static topologies always loop to the compile-time maximum (with a
+  // guard inside) so that every trip count is a literal when the unroller first sees the loop
+  GP_HD static constexpr int lim(int /*runtime_bound*/, int static_bound) { return static_bound; }
+  GP_HD static constexpr int nb(const MechParams&) { return NB; }
+  GP_HD static constexpr int nq(const MechParams&) { return tables().nq; }
+  GP_HD static constexpr int nv(const MechParams&) { return tables().nv; }
+  GP_HD static constexpr int parent(const MechParams&, int i) { return (int)select_chain<FParent, 0, NB>(i) - 1; }
+  GP_HD static constexpr int jtype(const MechParams&, int i) { return (int)select_chain<FJtype, 0, NB>(i); }
+  GP_HD static constexpr int axis_kind(const MechParams&, int i) { return (int)select_chain<FAxis, 0, NB>(i); }
+  GP_HD static constexpr int qoff(const MechParams&, int i) { return (int)select_chain<FQoff, 0, NB>(i); }
+  GP_HD static constexpr int voff(const MechParams&, int i) { return (int)select_chain<FVoff, 0, NB>(i); }
+  GP_HD static constexpr int depth(const MechParams&, int i) { return (int)select_chain<FDepth, 0, NB>(i); }
+  GP_HD static constexpr int anc_at(const MechParams&, int i, int k) {
+    return (int)((select_chain<FAncRow, 0, NB>(i) >> (4 * k)) & 15ull) - 1;
+  }
+  GP_HD static constexpr bool has_children(const MechParams&, int i) { return select_chain<FChildren, 0, NB>(i) != 0ull; }
+  GP_HD static constexpr int dof_body(const MechParams&, int k) { return (int)select_chain<FDofBody, 0, NV>(k); }
+  // dof a's body is an ancestor-or-self of dof b's body (mass-matrix entry (b,a) is structurally non-zero)
+  GP_HD static constexpr bool dof_anc(const MechParams&, int a, int b) {
+    return ((select_chain<FDofAnc, 0, NV>(b) >> a) & 1ull) != 0ull;
+  }
+};
+
+struct DynTopo {
+  static constexpr bool kStatic = false;
+  static constexpr int NB = kMaxBodies;
+  static constexpr int NQ = kMaxNQ;
+  static constexpr int NV = kMaxNV;
+  static constexpr int kNVreal = kMaxNV;
+  static constexpr int kUnroll = 1;
+  static const char* name() { return "generic"; }
+
+  GP_HD static int lim(int runtime_bound, int /*static_bound*/) { return runtime_bound; }
+  GP_HD static int nb(const MechParams& P) { return P.nb; }
+  GP_HD static int nq(const MechParams& P) { return P.n_q; }
+  GP_HD static int nv(const MechParams& P) { return P.n_v; }
+  GP_HD static int parent(const MechParams& P, int i) { return P.parent[i]; }
+  GP_HD static int jtype(const MechParams& P, int i) { return P.jtype[i]; }
+  GP_HD static int axis_kind(const MechParams&, int) { return AxAny; }
+  GP_HD static int qoff(const MechParams& P, int i) { return P.qoff[i]; }
+  GP_HD static int voff(const MechParams& P, int i) { return P.voff[i]; }
+  GP_HD static int depth(const MechParams& P, int i) { return P.depth[i]; }
+  GP_HD static int anc_at(const MechParams& P, int i, int k) { return P.anc_at[i][k]; }
+  GP_HD static bool has_children(const MechParams& P, int i) { return P.has_children[i] != 0; }
+  GP_HD static int dof_body(const MechParams& P, int k) { return P.dof_body[k]; }
+  GP_HD static bool dof_anc(const MechParams& P, int a, int b) {
+    return ((P.anc_mask[P.dof_body[b]] >> P.dof_body[a]) & 1u) != 0u;
+  }
+};
+
+// ---------------------------------------------------------------- shipped specialisations
+// One per tree the reference's configs use (BASELINE.json configs).
+#define GP_R JRevolute
+#define GP_P JPrismatic
+#define GP_F JFloating
+#define GP_X JFixed
+
+struct SpecPendulum {  // helpers.rs:24 build_pendulum
+  static constexpr TopoData data() { return {1, {-1}, {GP_R}, {AxAny}}; }
+  static const char* name() { return "pendulum_R"; }
+};
+struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
+  static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
+  static const char* name() { return "double_pendulum_RR"; }
+};
+struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
+  static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
+  static const char* name() { return "cart_pole_PR"; }
+};
+struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
+  static constexpr TopoData data() {
+    return {7, {-1, 0, 1, 2, 3, 4, 5}, {GP_X, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R},
+            {AxAny, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ}};
+  }
+  static const char* name() { return "so101_X6Rz"; }
+};
+struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
+  static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
+  static const char* name() { return "floating_F"; }
+};
+struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
+  static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
+  static const char* name() { return "hopper1d_FPP"; }
+};
+struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
+  static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
+  static const char* name() { return "hopper_FPR"; }
+};
+struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
+  static constexpr TopoData data() {
+    return {9, {-1, 0, 1, 0, 3, 0, 5, 0, 7}, {GP_F, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R},
+            {AxAny, AxAny, AxAny, AxAny, AxAny, AxAny, AxAny, AxAny, AxAny}};
+  }
+  static const char* name() { return "quadruped_F8R"; }
+};
+struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
+  static constexpr TopoData data() {
+    return {9, {-1, 0, 1, 0, 2, 0, 5, 0, 6}, {GP_F, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R, GP_R},
+            {AxAny, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ}};
+  }
+  static const char* name() { return "navbot_F8Rz"; }
+};
+
+#undef GP_R
+#undef GP_P
+#undef GP_F
+#undef GP_X
+
+// does a mechanism's signature match a specialisation? (AxAny in the spec matches any axis)
+constexpr bool topo_matches(const TopoData& spec, const TopoData& mech) {
+  if (spec.nb != mech.nb) return false;
+  for (int i = 0; i < spec.nb; ++i) {
+    if (spec.parent[i] != mech.parent[i] || spec.jtype[i] != mech.jtype[i]) return false;
+    if (spec.axis[i] != AxAny && spec.axis[i] != mech.axis[i]) return false;
+  }
+  return true;
+}
+
+}  // namespace gp

@@ -1,0 +1,10 @@
+// Kernel instantiations for the "double_pendulum" topology (see gp_topology.cuh). One translation unit
+// per topology so the variants compile in parallel.
+#include "../gp_kernels.cuh"
+
+namespace gp {
+const KernelTable* variant_double_pendulum() {
+  static const KernelTable t = make_static_table<StaticTopo<SpecDoublePendulum>, SpecDoublePendulum>();
+  return &t;
+}
+}  // namespace gp

@@ -1,0 +1,10 @@
+// Kernel instantiations for the "generic" topology (see gp_topology.cuh). One translation unit
+// per topology so the variants compile in parallel.
+#include "../gp_kernels.cuh"
+
+namespace gp {
+const KernelTable* variant_generic() {
+  static const KernelTable t = make_generic_table<DynTopo>();
+  return &t;
+}
+}  // namespace gp

@@ -1,0 +1,10 @@
+// Kernel instantiations for the "hopper" topology (see gp_topology.cuh). One translation unit
+// per topology so the variants compile in parallel.
+#include "../gp_kernels.cuh"
+
+namespace gp {
+const KernelTable* variant_hopper() {
+  static const KernelTable t = make_static_table<StaticTopo<SpecHopper>, SpecHopper>();
+  return &t;
+}
+}  // namespace gp

