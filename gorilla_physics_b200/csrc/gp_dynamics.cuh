@@ -349,11 +349,11 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
         if (col < 3) {
           F.a = (col == 0) ? V3{Ic.J.xx, Ic.J.xy, Ic.J.xz}
                            : ((col == 1) ? V3{Ic.J.xy, Ic.J.yy, Ic.J.yz} : V3{Ic.J.xz, Ic.J.yz, Ic.J.zz});
-          F.l = V3{col == 1 ? -Ic.c.z : (col == 2 ? Ic.c.y : 0.0), col == 0 ? Ic.c.z : (col == 2 ? -Ic.c.x : 0.0),
-                   col == 0 ? -Ic.c.y : (col == 1 ? Ic.c.x : 0.0)};  // e x c
+          F.l = V3{col == 1 ? Ic.c.z : (col == 2 ? -Ic.c.y : 0.0), col == 0 ? -Ic.c.z : (col == 2 ? Ic.c.x : 0.0),
+                   col == 0 ? Ic.c.y : (col == 1 ? -Ic.c.x : 0.0)};  // -(c x e) = e x c
         } else {
-          F.a = V3{col == 4 ? Ic.c.z : (col == 5 ? -Ic.c.y : 0.0), col == 3 ? -Ic.c.z : (col == 5 ? Ic.c.x : 0.0),
-                   col == 3 ? Ic.c.y : (col == 4 ? -Ic.c.x : 0.0)};  // c x e
+          F.a = V3{col == 4 ? -Ic.c.z : (col == 5 ? Ic.c.y : 0.0), col == 3 ? Ic.c.z : (col == 5 ? -Ic.c.x : 0.0),
+                   col == 3 ? -Ic.c.y : (col == 4 ? Ic.c.x : 0.0)};  // c x e
           F.l = e * Ic.m;
         }
         const double Fv[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};

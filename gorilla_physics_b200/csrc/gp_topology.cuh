@@ -14,7 +14,13 @@
 
 #if defined(__CUDACC__)
 #define GP_HD __host__ __device__ __forceinline__
+#if defined(GP_HOST_DEBUG)
+// tools/host_debug.cu only: lets the developer single-step the device functions on the CPU of a
+// machine without a GPU. Never defined when building libgorilla_b200.so.
+#define GP_D __host__ __device__ __forceinline__
+#else
 #define GP_D __device__ __forceinline__
+#endif
 #else
 #define GP_HD inline
 #define GP_D inline

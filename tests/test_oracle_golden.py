@@ -1,0 +1,345 @@
+"""Pins the CPU oracle against every known-answer vector the reference's own tests hold for the
+step path. Each test names the reference test it restates. CPU only.
+
+The reference is Rust and cannot be built here, so these golden vectors (closed forms, numbers from
+RigidBodyDynamics.jl quoted in the reference's tests, physical outcomes of its rollouts) are what
+anchors the oracle; the CUDA path is then compared with the oracle in test_parity_gpu.py.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from gorilla_physics_b200 import (FLOATING, PRISMATIC, REVOLUTE, Mechanism, MechanismDesc, iso, quat_from_euler,
+                                  quat_from_scaled_axis)
+from oracle.binding import (OracleMechanism, quat_from_euler as o_quat_from_euler, simple_double_pendulum,
+                            simulate_step_count, twist_transform)
+from tests import models
+from tests.models import GRAVITY, PI, oracle_of, pose_q
+
+SIE, RK2, RK4 = 0, 1, 2
+
+
+# ---------------------------------------------------------------- dynamics.rs known answers
+def test_dynamics_rod_pendulum_horizontal():  # dynamics.rs:883 (assert_eq!, exact)
+    o = oracle_of(models.rod_pendulum())
+    assert o.dynamics([0.0], [0.0], [0.0])[0] == 3.0 * GRAVITY / (2.0 * 7.0)
+
+
+def test_dynamics_rod_pendulum_horizontal_rotated_frame():  # dynamics.rs:916 (exact)
+    rot = iso((0, 0, 0), quat_from_scaled_axis((PI / 2.0, 0, 0)))
+    o = oracle_of(models.rod_pendulum(rod_to_world=rot, axis=(0, 0, 1)))
+    assert o.dynamics([0.0], [0.0], [0.0])[0] == -3.0 * GRAVITY / (2.0 * 7.0)
+
+
+def test_dynamics_rod_pendulum_horizontal_moved_frame():  # dynamics.rs:949 (1e-6)
+    rot = iso((11.0, 0, 0), quat_from_scaled_axis((PI / 2.0, 0, 0)))
+    o = oracle_of(models.rod_pendulum(rod_to_world=rot, axis=(0, 0, 1)))
+    assert abs(o.dynamics([0.0], [0.0], [0.0])[0] - (-3.0 * GRAVITY / (2.0 * 7.0))) < 1e-6
+
+
+def test_dynamics_hold_horizontal_rod_pendulum():  # dynamics.rs:979 (1e-6)
+    m, l = 5.0, 7.0
+    o = oracle_of(models.rod_pendulum(m, l))
+    assert abs(o.dynamics([0.0], [0.0], [-m * GRAVITY * l / 2.0])[0]) < 1e-6
+
+
+def test_dynamics_simple_pendulum_horizontal():  # dynamics.rs:1011 (exact)
+    o = oracle_of(models.rod_pendulum(point_mass=True))
+    assert o.dynamics([0.0], [0.0], [0.0])[0] == GRAVITY / 7.0
+
+
+def test_dynamics_double_pendulum_horizontal():  # dynamics.rs:1038 (1e-6)
+    o = oracle_of(models.double_pendulum_horizontal())
+    np.testing.assert_allclose(o.dynamics([0, 0], [0, 0], [0, 0]), [GRAVITY / 7.0, -GRAVITY / 7.0], atol=1e-6)
+
+
+def test_double_pendulum_dynamics_vs_closed_form():  # dynamics.rs:1091 (1e-5)
+    m, l = 3.0, 5.0
+    o = oracle_of(models.double_pendulum_hanging(m, l))
+    vdot = o.dynamics([3.0, 5.0], [3.0, 5.0], [0.0, 0.0])
+    np.testing.assert_allclose(vdot, simple_double_pendulum(m, m, l, l, 3.0, 5.0, 3.0, 5.0), atol=1e-5)
+
+
+def test_simple_double_pendulum_rbdjl_numbers():  # double_pendulum.rs:64-83 (1e-4)
+    np.testing.assert_allclose(simple_double_pendulum(1.0, 3.0, 2.0, 4.0, 1.0, 2.0, 3.0, 4.0), [68.8824, -58.9877],
+                               atol=1e-4)
+
+
+def test_ball_dynamics_rbdjl_numbers():  # joint/floating.rs:82-129 (1e-5): body-frame velocity convention
+    o = oracle_of(models.ball())
+    vdot = o.dynamics(pose_q((0.1, 0.2, 0.3), (1.0, 2.0, 3.0)), [1, 2, 3, 4, 5, 6])
+    np.testing.assert_allclose(vdot, [0.0, 0.0, 0.0, 4.948946, -6.959844, -6.566419], atol=1e-5)
+
+
+def test_motor_turning_mass():  # dynamics.rs:1194-1251 (1e-5)
+    o = oracle_of(models.motor_turning_mass())
+    q, v = models.motor_turning_mass().zero_state()
+    acc = o.dynamics(q, v, [0, 0, 0, 0, 0, 0, 1.0])
+    base_angular = -1.0 / (2.0 / 5.0)
+    base_linear_x = -1.0
+    np.testing.assert_allclose(acc[0:3], [0, 0, base_angular], atol=1e-5)
+    np.testing.assert_allclose(acc[3:6], [base_linear_x, 0, -GRAVITY], atol=1e-5)
+    assert abs(acc[6] - (-base_angular + 1.0 + -base_linear_x)) < 1e-5
+
+
+# ---------------------------------------------------------------- mechanism.rs / spatial tests
+def test_mass_matrix_structure():  # mechanism.rs:711-786
+    d = models.mass_matrix_fixture()
+    o = oracle_of(d)
+    q, v = d.zero_state()
+    M = o.dynamics(q, v, want="all")["mass_matrix"]
+    assert M.shape == (8, 8)
+    assert np.any(M[6, 0:6] != 0) and M[6, 6] != 0
+    assert np.any(M[7, 0:6] != 0) and M[7, 6] != 0 and M[7, 7] != 0
+    np.testing.assert_array_equal(M, M.T)
+
+
+def test_supports():  # mechanism.rs:793-832
+    S = oracle_of(models.supports_fixture()).supports()
+    sets = [set(int(i) + 1 for i in np.nonzero(row)[0]) for row in S]
+    assert sets == [{1, 2, 3, 4, 5}, {2, 3}, {3}, {4, 5}, {5}]
+    # the product's host code derives the same table
+    S2 = Mechanism.from_desc(models.supports_fixture()).supports()
+    np.testing.assert_array_equal(S, S2)
+
+
+def test_compute_bodies_to_root():  # spatial/transform.rs tests: same 5-body tree, translations compose
+    d = models.supports_fixture()
+    o = oracle_of(d)
+    q, _ = d.zero_state()
+    poses = o.poses(q)
+    np.testing.assert_array_equal(poses[:, 4:], [[0, 0, 0], [-1, 0, 0], [-1, 0, 1], [1, 0, 0], [1, 0, 1]])
+    np.testing.assert_array_equal(poses[:, :4], np.tile([0, 0, 0, 1.0], (5, 1)))
+
+
+def test_twist_transform():  # spatial/twist.rs:216-284 (1e-6): w' = R w, v' = R v + t x w'
+    t = twist_transform(iso((0, 0, 0), quat_from_scaled_axis((0, 0, PI / 2.0))), [1, 0, 0, 0, 0, 0])
+    np.testing.assert_allclose(t, [0, 1, 0, 0, 0, 0], atol=1e-6)
+    t = twist_transform(iso((1.0, 0, 0), (0, 0, 0, 1)), [0, 0, 1.0, 0, 0, 0])
+    np.testing.assert_allclose(t, [0, 0, 1, 0, -1, 0], atol=1e-6)  # (1,0,0) x (0,0,1) = (0,-1,0)
+
+
+def test_nalgebra_euler_convention():  # R = Rz(yaw) Ry(pitch) Rx(roll)
+    q = o_quat_from_euler(0.1, 0.2, 0.3)
+    np.testing.assert_allclose(q, quat_from_euler(0.1, 0.2, 0.3), atol=0)
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    def rx(a): return np.array([[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]])
+    def ry(a): return np.array([[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]])
+    def rz(a): return np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]])
+    np.testing.assert_allclose(R, rz(0.3) @ ry(0.2) @ rx(0.1), atol=1e-15)
+
+
+def test_simulate_step_count_follows_f64_loop():  # simulate.rs:97-109
+    assert simulate_step_count(1.0, 0.1) == 11  # 0.1 * 10 accumulates to 0.9999999999999999 < 1.0
+    assert simulate_step_count(2.0, 1e-3) in (2000, 2001)
+    assert simulate_step_count(0.0, 1e-3) == 0
+
+
+# ---------------------------------------------------------------- rollouts: simulate.rs / energy.rs
+def test_simulate_horizontal_right_rod():  # simulate.rs:129-174 (SemiImplicitEuler)
+    m, l = 5.0, 7.0
+    o = oracle_of(models.rod_pendulum(m, l))
+    q, v, hq, hv = o.simulate([0.0], [0.0], 10.0, 0.001, SIE, tau=[0.0])
+    assert abs(hq[:, 0].max() - PI) < 1e-2
+    pe = m * GRAVITY * l / 2.0 * (-math.sin(q[0]))
+    ke = 0.5 * (m * l * l / 3.0) * v[0] * v[0]
+    assert abs(pe + ke) < 1e-1
+
+
+def test_simulate_cart():  # simulate.rs:177-214 (RK4)
+    o = oracle_of(Mechanism.from_model("cart"))
+    q, v, hq, hv = o.simulate([2.0], [-1.0], 10.0, 0.02, RK4, tau=[0.0])
+    assert abs(q[0] - (2.0 - 1.0 * 10.0)) < 2e-2 and abs(v[0] + 1.0) < 1e-6
+
+
+def test_simulate_cart_pole_steady_state():  # simulate.rs:218-272 (RK4, 1e-5)
+    o = oracle_of(models.cart_pole(3.0, 1.0, 5.0, 7.0, (0, 1, 0)))
+    F = 1.0
+    acc = F / (3.0 + 5.0)
+    theta = math.atan2(acc, GRAVITY)
+    q, v = o.simulate([0.0, theta], [0.0, 0.0], 20.0, 1e-2, RK4, tau=[F, 0.0], history=False)
+    assert abs(v[0] - acc * 20.0) < 1e-4 + 1e-2 * acc  # step count follows the f64 loop
+    assert abs(q[1] - theta) < 1e-5
+
+
+def test_double_pendulum_energy():  # energy.rs:82-127 (SemiImplicitEuler, 1e-1)
+    m, l = 1.0, 1.0
+    o = oracle_of(models.double_pendulum_hanging(m, l))
+
+    def energy(q, v):
+        h1 = -l * math.cos(q[0])
+        h2 = -l * math.cos(q[0]) - l * math.cos(q[0] + q[1])
+        return o.kinetic_energy(q, v) + m * GRAVITY * (h1 + h2)
+    q0, v0 = [1.0, 1.0], [0.1, 0.1]
+    q, v = o.simulate(q0, v0, 2.0, 1e-3, SIE, tau=[0.0, 0.0], history=False)
+    assert abs(energy(q, v) - energy(q0, v0)) < 1e-1
+
+
+def test_cart_pole_energy():  # energy.rs:130-178 (RK4, 1e-1)
+    o = oracle_of(models.cart_pole(1.0, 1.0, 1.0, 1.0, (0, -1, 0)))
+
+    def energy(q, v):
+        return o.kinetic_energy(q, v) - 1.0 * GRAVITY * 1.0 * math.cos(q[1])
+    q0, v0 = [0.0, PI + 0.1], [0.0, 0.0]
+    q, v = o.simulate(q0, v0, 2.0, 0.001, RK4, tau=[0.0, 0.0], history=False)
+    assert abs(energy(q, v) - energy(q0, v0)) < 1e-1
+
+
+def test_spring_on_frictionless_ground():  # dynamics.rs:1133-1190 (RK4, midpoint conserved 1e-5)
+    d, l_init = models.spring_pair()
+    o = oracle_of(d)
+    q, v = d.zero_state()
+    q[7] = l_init
+    q, v = o.simulate(q, v, 1.1, 1e-3, RK4, history=False)
+    poses = o.poses(q)
+    x_a, x_b = poses[0, 4], poses[1, 4]
+    assert abs((x_a + x_b) / 2.0 - l_init / 2.0) < 1e-5
+    assert x_a > 0.0 and x_b < l_init
+
+
+# ---------------------------------------------------------------- contact.rs rollouts
+def test_pendulum_hit_ground():  # contact.rs:371-405 (RK4, rests at 30 degrees, 1e-3)
+    m, l = 1.5, 10.0
+    d = models.rod_pendulum(m, l, point_mass=True)
+    d.add_contact_point(1, (l, 0, 0))
+    d.add_halfspace((0, 0, 1), -5.0)
+    q, v = oracle_of(d).simulate([0.0], [0.0], 5.0, 1e-2, RK4, tau=[0.0], history=False)
+    assert abs(q[0] - 30.0 * PI / 180.0) < 1e-3
+
+
+def _cube_on(h_ground, alpha=0.9, mu=0.5):
+    m = Mechanism.from_model("cube")
+    m.add_halfspace((0, 0, 1), h_ground, alpha=alpha, mu=mu)
+    return oracle_of(m)
+
+
+def test_cube_fall_ground():  # contact.rs:408-441
+    o = _cube_on(-10.0)
+    q, v = o.simulate(pose_q(), [1, 1, 1, 1, 1, 1], 5.0, 1e-3, RK4, history=False)
+    assert abs(q[6] - (-10.0 + 0.5)) < 1e-2
+
+
+def test_cube_slide_ground():  # contact.rs:444-490: friction stopping distance
+    mu = 0.5
+    o = _cube_on(-0.5, alpha=1.0, mu=mu)
+    q, v = o.simulate(pose_q(), [0, 0, 0, 1.0, 0, 0], 2.0, 1e-3, RK4, history=False)
+    assert abs(q[6]) < 1e-2
+    assert np.linalg.norm(v[3:6]) < 5e-3 and np.linalg.norm(v[0:3]) < 1e-2
+    acc = -GRAVITY * mu
+    t_slide = 1.0 / -acc
+    assert abs(q[4] - (t_slide + acc * t_slide ** 2 / 2.0)) < 1e-2
+
+
+def test_cube_hit_ground():  # contact.rs:493-530
+    o = _cube_on(-10.0)
+    q, v = o.simulate(pose_q(), [0, 5.0, 0, 1.0, 0, 0], 5.0, 1e-3, RK4, history=False)
+    assert abs(q[6] - (-10.0 + 0.5)) < 1e-2
+    assert np.linalg.norm(v[3:6]) < 5e-3 and np.linalg.norm(v[0:3]) < 1e-2
+
+
+def test_two_cubes_hit_ground():  # contact.rs:533-604: two floating bodies on the world
+    m, l = 3.0, 1.0
+    d = MechanismDesc()
+    for _ in range(2):
+        d.add_body(0, FLOATING, moment=np.eye(3) * m * l * l / 6.0, mass=m)
+    h = l / 2.0
+    for body in (1, 2):
+        for sz in (-h, h):
+            for sx, sy in ((h, h), (h, -h), (-h, h), (-h, -h)):
+                d.add_contact_point(body, (sx, sy, sz))
+    d.add_halfspace((0, 0, 1), -10.0)
+    o = oracle_of(d)
+    q0 = np.concatenate([pose_q(t=(2.0 * l, 0, 0)), pose_q(t=(-2.0 * l, 0, 0))])
+    v0 = [0, 5.0, 0, 1.0, 0, 0, 0, -5.0, 0, -1.0, 0, 0]
+    q, v = o.simulate(q0, v0, 5.0, 1e-3, RK4, history=False)
+    for b in range(2):
+        assert abs(q[7 * b + 6] - (-10.0 + l / 2.0)) < 1e-2
+        assert np.linalg.norm(v[6 * b + 3:6 * b + 6]) < 5e-3 and np.linalg.norm(v[6 * b:6 * b + 3]) < 1e-2
+
+
+def test_mass_hit_ground():  # contact.rs:607-676: impact + sliding distance
+    m, r, vx, h_ground, mu = 1.0, 0.1, 2.0, -0.3, 0.5
+    d = models.ball(m, r)
+    d.add_contact_point(1, (0, 0, 0))
+    d.add_halfspace((0, 0, 1), h_ground, alpha=1.0, mu=mu)
+    q, v = oracle_of(d).simulate(pose_q(), [0, 0, 0, vx, 0, 0], 2.0, 1e-3, RK4, history=False)
+    assert abs(q[6] - h_ground) < 1e-2
+    assert np.linalg.norm(v[3:6]) < 1e-2 and np.linalg.norm(v[0:3]) < 1e-3
+    t_hit = math.sqrt(-h_ground * 2.0 / GRAVITY)
+    vx_after = vx - GRAVITY * t_hit * mu
+    assert vx_after > 0.0
+    acc = -GRAVITY * mu
+    t_slide = vx_after / -acc
+    x_expect = t_hit * vx + vx_after * t_slide + acc * t_slide ** 2 / 2.0
+    assert abs(q[4] - x_expect) < 1e-2
+
+
+def test_rimless_wheel_limit_cycle():  # contact.rs:679-729 (RK4, dt=1/600, 20 s)
+    o = oracle_of(models.rimless_wheel_on_slope())
+    q, v, hq, hv = o.simulate(pose_q(), [0, 0, 0, 1.0, 0, 0], 20.0, 1.0 / 600.0, RK4)
+    omega_y = hv[:, 1]
+    assert omega_y[-1] > 0.0
+    assert omega_y.max() < 0.75
+
+
+def test_ball_fall():  # joint/floating.rs ball_fall: free fall under gravity (SemiImplicitEuler)
+    o = oracle_of(models.ball())
+    q, v = o.simulate(pose_q(), np.zeros(6), 1.0, 1e-3, SIE, history=False)
+    n = simulate_step_count(1.0, 1e-3)
+    assert abs(v[5] + GRAVITY * n * 1e-3) < 1e-9  # world-aligned body frame: v_z = -g t exactly per step
+    assert abs(q[6] + 0.5 * GRAVITY * (n * 1e-3) ** 2) < 1e-2
+
+
+def test_acrobot_swingup():  # control/swingup.rs:129-188 (RK4, dt=1e-2, 50 s, "very relaxed check")
+    m, l = 1.0, 7.0
+    o = oracle_of(models.double_pendulum_horizontal(m, l, axis=(0, -1, 0)))
+    n = simulate_step_count(50.0, 1e-2)
+    q, v, hq, hv = o.rollout([-PI / 2.0 + 0.1, 0.0], [0.0, 0.0], 1e-2, n, RK4, controller=2, params=(m, l),
+                             history=True)
+    q1 = np.mod(hq[:, 0], 2 * PI)
+    q2 = np.mod(hq[:, 1], 2 * PI)
+    swungup = (np.abs(q1 - PI / 2.0) < 0.5) & (np.abs(q2) < 0.5) & (np.abs(hv[:, 0]) < 0.3) & (np.abs(hv[:, 1]) < 0.3)
+    assert swungup.any()
+
+
+def test_cart_pole_swingup():  # control/swingup.rs:190-261 (RK4, dt=1e-2, 30 s)
+    m_cart, m_pole, l_pole = 3.0, 5.0, 7.0
+    o = oracle_of(models.cart_pole(m_cart, 1.0, m_pole, l_pole, (0, -1, 0)))
+    n = simulate_step_count(30.0, 1e-2)
+    q, v, hq, hv = o.rollout([0.0, 0.1], [0.0, 0.0], 1e-2, n, RK4, controller=3, params=(m_cart, m_pole, l_pole),
+                             history=True)
+    q2 = np.mod(hq[:, 1], 2 * PI)
+    swungup = (np.abs(hq[:, 0]) < 1e-1) & (np.abs(q2 - PI) < 1e-1) & (np.abs(hv[:, 0]) < 1e-1) & (np.abs(hv[:, 1]) < 1e-1)
+    assert swungup.any()
+    assert abs(q[0]) < 1e-1 and abs(v[0]) < 1e-1
+    E = o.kinetic_energy(q, v) - m_pole * GRAVITY * l_pole * math.cos(q[1])  # energy.rs:34-41
+    assert abs(E - m_pole * l_pole * GRAVITY) < 2.0
+
+
+def test_acrobot_example_energy_trace():  # examples/acrobot.rs: config 1 (SemiImplicitEuler, dt=1e-3)
+    """The swing-up controller pumps the total energy towards m g (l + 2l) (swingup.rs:20)."""
+    m, l = 1.0, 7.0
+    o = oracle_of(Mechanism.from_model("double_pendulum"))  # defaults = examples/acrobot.rs:14-34
+    q, v, hq, hv = o.rollout([0.0, 0.0], [0.0, 0.0], 1e-3, 30000, SIE, controller=2, params=(m, l), history=True)
+
+    def energy(qq, vv):
+        pe = m * GRAVITY * (l * math.sin(qq[0]) + (l * math.sin(qq[0]) + l * math.sin(qq[0] + qq[1])))
+        return o.kinetic_energy(qq, vv) + pe
+    e0, e1 = energy(hq[0], hv[0]), energy(hq[-1], hv[-1])
+    target = m * GRAVITY * 3.0 * l
+    assert abs(e0) < 1e-12
+    assert abs(e1 - target) < abs(e0 - target)
+
+
+def test_so101_pd_controller_holds_zero_pose():  # control/so101_control.rs:12-34 (PD + clamp)
+    m = Mechanism.from_model("so101")
+    o = oracle_of(m)
+    tau = o.control(np.full(6, 0.02), np.zeros(6), 1, (1000.0, 0.1, 10.0))
+    np.testing.assert_allclose(tau, np.full(6, -10.0))  # 1000 * -0.02 = -20 clamped to -10
+    tau = o.control(np.full(6, 0.001), np.full(6, 1.0), 1, (1000.0, 0.1, 10.0))
+    np.testing.assert_allclose(tau, np.full(6, -1.1))
