@@ -7,10 +7,12 @@ if the shared library is missing this module raises instead of substituting anyt
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libgorilla_b200.so"
+# GP_LIB_PATH lets a developer point at an experimental build of the same library
+LIB_PATH = Path(os.environ.get("GP_LIB_PATH", _HERE / "lib" / "libgorilla_b200.so"))
 
 GP_OK, GP_ERR_INVALID, GP_ERR_UNSUPPORTED, GP_ERR_NO_DEVICE, GP_ERR_CUDA, GP_ERR_LIMIT = range(6)
 

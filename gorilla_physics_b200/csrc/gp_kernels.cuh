@@ -217,8 +217,11 @@ GP_D bool all_finite(const double* a, int n) {
 }
 
 // ---- step kernel: n_steps of step() per launch (reference simulate.rs:20-83) -----------------
+#ifndef GP_STEP_MIN_BLOCKS
+#define GP_STEP_MIN_BLOCKS 1
+#endif
 template <class Topo, bool CONTACT, int INTEG>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, GP_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
