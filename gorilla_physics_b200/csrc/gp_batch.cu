@@ -216,7 +216,12 @@ int check_batch(gp_batch* b, const char* fn) {
   return GP_OK;
 }
 
-bool has_contact(const gp_mechanism* m) { return m->n_cp() > 0 && m->n_hs() > 0; }
+// 0 = no contact work, 1 = exactly one halfspace, 2 = several (dynamics_core's CONTACT modes)
+int contact_mode(const gp_mechanism* m) {
+  if (m->n_cp() == 0 || m->n_hs() == 0) return 0;
+  return m->n_hs() == 1 ? 1 : 2;
+}
+bool has_contact(const gp_mechanism* m) { return contact_mode(m) != 0; }
 
 int64_t step_count(double final_time, double dt) {
   // reference simulate.rs:97-109: `let mut t = 0.0; while t < final_time { ...; t += dt; }`
@@ -284,7 +289,7 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   }
   if (n_steps == 0) return GP_OK;
   const int ic = integrator == GP_SEMI_IMPLICIT_EULER ? IntegSIE : IntegRK;
-  GP_CUDA(m->table->step(has_contact(m), ic, b->stream, m->params, A));
+  GP_CUDA(m->table->step(contact_mode(m), ic, b->stream, m->params, A));
   b->launches++;
   return GP_OK;
 }
@@ -451,7 +456,7 @@ int gp_batch_dynamics(gp_batch* b, double* vdot_host, double* contact_force_host
   A.status = b->status;
   A.n = b->n;
   A.ld = b->ld;
-  GP_CUDA(m->table->dynamics(has_contact(m), b->stream, m->params, A));
+  GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if ((rc = to_host_aos(b, A.vdot, vdot_host, nv))) return rc;
   if (contact_force_host && ncf) {
@@ -481,7 +486,7 @@ int gp_batch_mass_matrix(gp_batch* b, double* mass_matrix_host, double* bias_hos
   A.status = b->status;
   A.n = b->n;
   A.ld = b->ld;
-  GP_CUDA(m->table->dynamics(has_contact(m), b->stream, m->params, A));
+  GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if (mass_matrix_host) {
     // nv*nv planes can exceed one tile's shared memory: move them nv planes (one row) at a time

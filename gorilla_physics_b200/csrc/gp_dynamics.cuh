@@ -107,16 +107,17 @@ GP_D V3 contact_force(double z, V3 n, V3 vel, double k, double alpha, double mu)
   // f64::max(NaN, 0) = 0, i.e. no force
   if (!(z > 0.0)) return v3z();
   const double z_dot = -dot(vel, n);
-  const double zn = z * sqrt(z);
+  const double zn = z * sqrt(z);  // z^(3/2)
   const double lambda = 1.5 * alpha * k;
   const double pi_n = fmax(lambda * zn * z_dot + k * zn, 0.0);
   V3 f = n * pi_n;
   V3 v_t = vel + n * z_dot;
-  const double v_t_norm = sqrt(dot(v_t, v_t));
-  if (v_t_norm != 0.0) {
-    const double s = v_t_norm / 1e-3;
-    const double mu_eff = (s > 1.0) ? mu : mu * s;
-    const double g = -mu_eff * pi_n / v_t_norm;
+  const double vt2 = dot(v_t, v_t);
+  if (vt2 != 0.0) {
+    // -mu_eff * pi * v_t / |v_t| with mu_eff = mu * min(1, |v_t| / 1e-3):
+    //   |v_t| >  1e-3 : -mu pi / |v_t|        |v_t| <= 1e-3 : -mu pi / 1e-3
+    const double inv_norm = rsqrt(vt2);
+    const double g = -mu * pi_n * ((vt2 > 1e-6) ? inv_norm : 1e3);
     f += v_t * g;
   }
   return f;
@@ -156,7 +157,12 @@ GP_D void mass_matrix_walk(const MechParams& P, int i, int row, SV F, const M3& 
 
 // ---- dynamics_continuous for one environment ------------------------------------------------
 // q[NQ], v[NV], tau[NV] (caller passes zeros for "no torque"); writes vdot[NV]; returns status.
-template <class Topo, bool CONTACT, bool DUMP>
+// CONTACT: 0 = no contact points / halfspaces, 1 = exactly one halfspace, 2 = up to kMaxHS.
+// Contact is evaluated in BODY coordinates: each halfspace is carried down the tree as a plane
+// (n, o) with signed distance n.x - o, 21 flops per body and plane, instead of composing
+// body->world poses; the world pose chain is only built by the parity kernels (DUMP), which must
+// report world-frame forces.
+template <class Topo, int CONTACT, bool DUMP>
 GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* v, const double* tau,
                             double* vdot, const DynOut& out) {
   constexpr int NB = Topo::NB;
@@ -167,8 +173,11 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
 
   double sn[NB], cs[NB];  // cached sin/cos of revolute joints
   SV vel[NB], acc[NB], frc[NB];
-  M3 Rw[CONTACT ? NB : 1];
-  V3 tw[CONTACT ? NB : 1];
+  constexpr int NHS = (CONTACT == 2) ? kMaxHS : 1;
+  constexpr bool WORLD = (CONTACT != 0) && DUMP;
+  V3 hn[CONTACT ? NB : 1][NHS];     // halfspace normals in body coordinates
+  double ho[CONTACT ? NB : 1][NHS];  // plane offsets: signed distance of x is hn.x - ho
+  M3 Rw[WORLD ? NB : 1];
 
   // ------------------------------------------------------------------ pass 1: root -> leaf
   for_bodies<Topo>(P, [&](auto ii) {
@@ -235,41 +244,49 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     f.a += cross(vi.a, h.a) + cross(vi.l, h.l);
     f.l += cross(vi.a, h.l);
 
-    if (CONTACT) {
-      // body -> world pose (reference mechanism.rs:153-170)
+    if constexpr (CONTACT != 0) {
       M3 Rwi;
-      V3 twi;
-      if (p >= 0) {
-        Rwi = mul(Rw[p], E);
-        twi = tw[p] + mul(Rw[p], r);
-      } else {
-        Rwi = E;
-        twi = r;
+      if constexpr (WORLD) {  // body -> world rotation (reference mechanism.rs:153-170), parity output only
+        if (p >= 0) Rwi = mul(Rw[p], E);
+        else Rwi = E;
+        Rw[i] = Rwi;
       }
-      Rw[i] = Rwi;
-      tw[i] = twi;
-      // point-vs-halfspace contact (reference contact.rs:103-128), wrench subtracted from the
-      // body force (dynamics.rs:244-246)
+      // halfspaces in this body's coordinates: x_parent = E x + r  =>  n' = E^T n, o' = o - n.r
+#pragma unroll
+      for (int h = 0; h < NHS; ++h) {
+        if (CONTACT == 1 || h < P.n_hs) {
+          const V3 np_ = (p >= 0) ? hn[p][h] : ld3(P.hs_normal[h]);
+          const double op_ = (p >= 0) ? ho[p][h] : P.hs_off[h];
+          hn[i][h] = mulT(E, np_);
+          ho[i][h] = op_ - dot(np_, r);
+        }
+      }
+      // point-vs-halfspace contact (reference contact.rs:103-128); the wrench is subtracted from
+      // the body force (dynamics.rs:244-246)
       const int c0 = P.cp_begin[i], c1 = P.cp_begin[i + 1];
       for (int c = c0; c < c1; ++c) {
         const V3 loc = ld3(P.cp_loc[c]);
-        const V3 pw = mul(Rwi, loc) + twi;                   // contact.rs:41-58
-        const V3 vw = mul(Rwi, vi.l + cross(vi.a, loc));     // twist.rs:130-132
-        V3 fw = v3z();
-        for (int hsi = 0; hsi < P.n_hs; ++hsi) {
-          const V3 n = ld3(P.hs_normal[hsi]);
-          const double d = dot(pw - ld3(P.hs_point[hsi]), n);
-          if (d <= 1e-8)  // halfspace.rs:39-44 has_inside
-            fw += contact_force(-d, n, vw, P.cp_k[c], P.hs_alpha[hsi], P.hs_mu[hsi]);
+        V3 fb = v3z();
+#pragma unroll
+        for (int h = 0; h < NHS; ++h) {
+          if (CONTACT == 1 || h < P.n_hs) {
+            const double d = dot(hn[i][h], loc) - ho[i][h];  // contact.rs:64-68, halfspace.rs:39-44
+            if (d <= 1e-8) {
+              const V3 vpt = vi.l + cross(vi.a, loc);  // twist.rs:130-132, body coordinates
+              fb += contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
+            }
+          }
         }
-        const V3 fb = mulT(Rwi, fw);
         f.a -= cross(loc, fb);
         f.l -= fb;
-        if (DUMP && out.contact_force) {
-          double* o = out.contact_force + (long long)(3 * c) * out.ld + out.env;
-          o[0] = fw.x;
-          o[out.ld] = fw.y;
-          o[2 * out.ld] = fw.z;
+        if constexpr (WORLD) {
+          if (out.contact_force) {
+            const V3 fw = mul(Rwi, fb);
+            double* o = out.contact_force + (long long)(3 * c) * out.ld + out.env;
+            o[0] = fw.x;
+            o[out.ld] = fw.y;
+            o[2 * out.ld] = fw.z;
+          }
         }
       }
     }

@@ -220,7 +220,7 @@ GP_D bool all_finite(const double* a, int n) {
 #ifndef GP_STEP_MIN_BLOCKS
 #define GP_STEP_MIN_BLOCKS 1
 #endif
-template <class Topo, bool CONTACT, int INTEG>
+template <class Topo, int CONTACT, int INTEG>
 __global__ void __launch_bounds__(kBlock, GP_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
@@ -291,7 +291,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
 }
 
 // ---- dynamics kernel: dynamics_continuous once, with the parity outputs ----------------------
-template <class Topo, bool CONTACT>
+template <class Topo, int CONTACT>
 __global__ void __launch_bounds__(kBlock)
 dynamics_kernel(const __grid_constant__ MechParams P, const __grid_constant__ DynArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
@@ -341,22 +341,23 @@ energy_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Ener
 inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 template <class Topo>
-cudaError_t launch_step(bool contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
+cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
   const dim3 g(grid_for(A.n)), b(kBlock);
   if (integ_class == IntegSIE) {
-    if (contact) step_kernel<Topo, true, IntegSIE><<<g, b, 0, s>>>(P, A);
-    else step_kernel<Topo, false, IntegSIE><<<g, b, 0, s>>>(P, A);
+    if (contact == 0) step_kernel<Topo, 0, IntegSIE><<<g, b, 0, s>>>(P, A);
+    else if (contact == 1) step_kernel<Topo, 1, IntegSIE><<<g, b, 0, s>>>(P, A);
+    else step_kernel<Topo, 2, IntegSIE><<<g, b, 0, s>>>(P, A);
   } else {
-    if (contact) step_kernel<Topo, true, IntegRK><<<g, b, 0, s>>>(P, A);
-    else step_kernel<Topo, false, IntegRK><<<g, b, 0, s>>>(P, A);
+    // the Runge-Kutta kernels are instantiated for the general contact mode only
+    step_kernel<Topo, 2, IntegRK><<<g, b, 0, s>>>(P, A);
   }
   return cudaGetLastError();
 }
 template <class Topo>
-cudaError_t launch_dynamics(bool contact, cudaStream_t s, const MechParams& P, const DynArgs& A) {
+cudaError_t launch_dynamics(int contact, cudaStream_t s, const MechParams& P, const DynArgs& A) {
   const dim3 g(grid_for(A.n)), b(kBlock);
-  if (contact) dynamics_kernel<Topo, true><<<g, b, 0, s>>>(P, A);
-  else dynamics_kernel<Topo, false><<<g, b, 0, s>>>(P, A);
+  (void)contact;  // parity kernel: always the general contact mode
+  dynamics_kernel<Topo, 2><<<g, b, 0, s>>>(P, A);
   return cudaGetLastError();
 }
 template <class Topo>

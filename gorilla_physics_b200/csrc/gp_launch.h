@@ -50,8 +50,8 @@ struct KernelTable {
   const char* name;
   TopoData topo;
   bool is_static;
-  cudaError_t (*step)(bool contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
-  cudaError_t (*dynamics)(bool contact, cudaStream_t, const MechParams&, const DynArgs&);
+  cudaError_t (*step)(int contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
+  cudaError_t (*dynamics)(int contact, cudaStream_t, const MechParams&, const DynArgs&);
   cudaError_t (*energy)(cudaStream_t, const MechParams&, const EnergyArgs&);
 };
 

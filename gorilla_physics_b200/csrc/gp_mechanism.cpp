@@ -130,6 +130,8 @@ int finalize_mechanism(gp_mechanism* m) {
       P.hs_point[h][d] = m->hs_point[3 * h + d];
       P.hs_normal[h][d] = m->hs_normal[3 * h + d];
     }
+    P.hs_off[h] = P.hs_point[h][0] * P.hs_normal[h][0] + P.hs_point[h][1] * P.hs_normal[h][1] +
+                  P.hs_point[h][2] * P.hs_normal[h][2];
     P.hs_alpha[h] = m->hs_alpha[h];
     P.hs_mu[h] = m->hs_mu[h];
   }

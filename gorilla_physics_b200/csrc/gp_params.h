@@ -76,6 +76,7 @@ struct MechParams {
   double cp_k[kMaxCP];
   double hs_point[kMaxHS][3];
   double hs_normal[kMaxHS][3];
+  double hs_off[kMaxHS];  // point . normal
   double hs_alpha[kMaxHS];
   double hs_mu[kMaxHS];
 };

@@ -35,7 +35,7 @@ extern "C" int gpdbg_dynamics(const gp_mechanism* m, const double* q, const doub
   for (int k = 0; k < P.n_q; ++k) qq[k] = q[k];
   for (int k = 0; k < P.n_v; ++k) { vv[k] = v[k]; tt[k] = tau ? tau[k] : 0.0; }
   DynOut out{cf, H, bias, 1, 0};
-  unsigned st = dynamics_core<DynTopo, true, true>(P, qq, vv, tt, vd, out);
+  unsigned st = dynamics_core<DynTopo, 2, true>(P, qq, vv, tt, vd, out);
   for (int k = 0; k < P.n_v; ++k) vdot[k] = vd[k];
   return (int)st;
 }
