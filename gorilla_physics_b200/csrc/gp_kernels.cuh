@@ -217,11 +217,16 @@ GP_D bool all_finite(const double* a, int n) {
 }
 
 // ---- step kernel: n_steps of step() per launch (reference simulate.rs:20-83) -----------------
-#ifndef GP_STEP_MIN_BLOCKS
-#define GP_STEP_MIN_BLOCKS 1
-#endif
+// Resident blocks per SM the register allocator must leave room for. Tuned per topology and
+// contact mode on B200 (profiles/r1_tuning.md): e.g. the SO-101 contact kernel runs 15% faster
+// capped at 168 registers (3 blocks/SM) than at 242 (2 blocks/SM), the 9-body trees do not.
+template <class Topo, int CONTACT>
+constexpr int step_min_blocks() {
+  if constexpr (Topo::kStatic) return Topo::min_blocks(CONTACT);
+  return 1;
+}
 template <class Topo, int CONTACT, int INTEG>
-__global__ void __launch_bounds__(kBlock, GP_STEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, (step_min_blocks<Topo, CONTACT>()))
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
   constexpr int U = Topo::kUnroll;

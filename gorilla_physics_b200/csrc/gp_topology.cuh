@@ -167,6 +167,7 @@ struct StaticTopo {
   static constexpr int kNVreal = tables().nv;
   static constexpr int kUnroll = 64;
   static const char* name() { return Spec::name(); }
+  static constexpr int min_blocks(int contact) { return Spec::min_blocks(contact); }
 
   struct FParent { template <int K> static constexpr unsigned long long at() { return (unsigned long long)(tables().parent[K] + 1); } };
   struct FJtype { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().jtype[K]; } };
@@ -254,14 +255,17 @@ struct DynTopo {
 struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static constexpr TopoData data() { return {1, {-1}, {GP_R}, {AxAny}}; }
   static const char* name() { return "pendulum_R"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "double_pendulum_RR"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "cart_pole_PR"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
   static constexpr TopoData data() {
@@ -269,18 +273,22 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
             {AxAny, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ}};
   }
   static const char* name() { return "so101_X6Rz"; }
+  static constexpr int min_blocks(int contact) { return contact == 1 ? 3 : 1; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
   static const char* name() { return "floating_F"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper1d_FPP"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper_FPR"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
   static constexpr TopoData data() {
@@ -288,6 +296,7 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
             {AxAny, AxAny, AxAny, AxAny, AxAny, AxAny, AxAny, AxAny, AxAny}};
   }
   static const char* name() { return "quadruped_F8R"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
   static constexpr TopoData data() {
@@ -295,6 +304,7 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
             {AxAny, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ}};
   }
   static const char* name() { return "navbot_F8Rz"; }
+  static constexpr int min_blocks(int) { return 1; }
 };
 
 #undef GP_R

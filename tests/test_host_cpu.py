@@ -1,0 +1,202 @@
+"""CPU-only tests: the C ABI library loads and exports every declared symbol, host-side mechanism
+logic (validation, flattening, kernel-variant selection), model literals against the golden
+fixture extracted from the reference sources, sharding, and the multi-rank path under gloo."""
+import ctypes as C
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import gorilla_physics_b200 as gp
+from gorilla_physics_b200 import _abi
+from gorilla_physics_b200._abi import GorillaError
+from gorilla_physics_b200.sharding import shard_range, shard_sizes
+from tests import models
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _abi.lib()
+    header = (ROOT / "include" / "gorilla_b200.h").read_text()
+    declared = set(re.findall(r"\b(gp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gp_status_code"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in gorilla_b200.h but not exported"
+    assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
+    assert lib.gp_abi_version() == 1
+
+
+def test_library_does_not_link_torch_or_the_oracle():
+    out = subprocess.run(["ldd", str(_abi.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "torch" not in out and "gp_oracle" not in out and "libcudart" not in out  # cudart is static
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_abi.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "gpo_" not in nm
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    if _abi.lib().gp_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    mech = gp.Mechanism.from_model("so101")
+    with pytest.raises(GorillaError) as e:
+        gp.MechanismState(mech, 8)
+    assert e.value.code == _abi.GP_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    with pytest.raises(GorillaError):
+        gp.measure_fp64_peak()
+
+
+def test_mechanism_validation_mirrors_reference_panics():
+    d = gp.MechanismDesc()
+    with pytest.raises(ValueError):  # reference: "joint 1 has no parent body" (mechanism.rs:110-116)
+        d.add_body(3, gp.REVOLUTE)
+    d.add_body(0, gp.REVOLUTE, axis=(0, 0, 2.0), moment=np.eye(3), mass=1.0)
+    with pytest.raises(GorillaError) as e:  # UnitVector3 in the reference: axis must be unit
+        gp.Mechanism.from_desc(d)
+    assert e.value.code == _abi.GP_ERR_INVALID
+    d = gp.MechanismDesc()
+    d.add_body(0, gp.REVOLUTE, moment=[[1, 2, 0], [0, 1, 0], [0, 0, 1]], mass=1.0)
+    with pytest.raises(GorillaError):
+        gp.Mechanism.from_desc(d)
+    with pytest.raises(GorillaError):
+        gp.Mechanism.from_model("no_such_model")
+    with pytest.raises(GorillaError):
+        gp.Mechanism.from_model("cube", [1.0])  # wrong parameter count
+    m = gp.Mechanism.from_model("so101")
+    with pytest.raises(GorillaError):
+        m.add_contact_point(99, (0, 0, 0))
+    for _ in range(4):
+        m.add_halfspace((0, 0, 1), 0.0)
+    with pytest.raises(GorillaError) as e:
+        m.add_halfspace((0, 0, 1), 0.0)
+    assert e.value.code == _abi.GP_ERR_LIMIT
+
+
+def test_kernel_variant_selection():
+    expect = {"pendulum": "pendulum_R", "double_pendulum": "double_pendulum_RR", "cart_pole": "cart_pole_PR",
+              "so101": "so101_X6Rz", "cube": "floating_F", "ball": "floating_F", "rimless_wheel": "floating_F",
+              "hopper": "hopper_FPR", "hopper_1d": "hopper1d_FPP", "quadruped": "quadruped_F8R",
+              "navbot": "navbot_F8Rz", "cart": "generic"}
+    for name, variant in expect.items():
+        assert gp.Mechanism.from_model(name).kernel_variant == variant
+    # an SO-101-shaped chain whose axes are not +z falls back to the run-time topology kernel
+    d = gp.Mechanism.from_model("so101").desc()
+    d._axis[3] = np.array([0.0, 1.0, 0.0])
+    assert gp.Mechanism.from_desc(d).kernel_variant == "generic"
+
+
+def test_desc_roundtrip_and_contact_point_order():
+    m = gp.Mechanism.from_model("quadruped")
+    d = m.desc()
+    assert (d.n_bodies, d.n_q, d.n_v, d.n_contact_points) == (9, 15, 14, 12)
+    # body-major, insertion order within a body: knee bodies carry (knee origin, foot) in that order
+    assert list(d.cp_body) == [2, 3, 3, 4, 5, 5, 6, 7, 7, 8, 9, 9]
+    assert d.cp_k[1] == 50e3 and d.cp_k[2] == 10e3
+    m2 = gp.Mechanism.from_desc(d)
+    d2 = m2.desc()
+    for f in ("parent", "joint_type", "axis", "init_iso", "moment", "cross_part", "mass", "cp_body", "cp_location", "cp_k"):
+        np.testing.assert_array_equal(getattr(d, f), getattr(d2, f))
+    q, v = d.zero_state()
+    assert q[3] == 1.0 and q.sum() == 1.0 and not v.any()
+
+
+def test_supports_table():
+    S = gp.Mechanism.from_desc(models.supports_fixture()).supports()
+    sets = [set(int(i) + 1 for i in np.nonzero(r)[0]) for r in S]
+    assert sets == [{1, 2, 3, 4, 5}, {2, 3}, {3}, {4, 5}, {5}]  # reference mechanism.rs:793-832
+
+
+def test_simulate_step_count():
+    f = _abi.lib().gp_simulate_step_count
+    assert f(1.0, 0.1) == 11 and f(0.0, 1e-3) == 0
+    from oracle.binding import simulate_step_count
+    for ft, dt in ((2.0, 1e-3), (30.0, 1e-3), (20.0, 1.0 / 600.0), (0.01, 1.0 / 6000.0)):
+        assert f(ft, dt) == simulate_step_count(ft, dt)
+
+
+def test_model_literals_match_reference_sources():
+    """tests/golden/model_literals.json was extracted from the reference's Rust builders by
+    tools/extract_reference_literals.py; every mass / COM / inertia / joint origin must agree."""
+    gold = json.loads((ROOT / "tests" / "golden" / "model_literals.json").read_text())
+    for model in ("so101", "navbot"):
+        d = gp.Mechanism.from_model(model).desc()
+        g = gold[model]
+        assert d.n_bodies == len(g["bodies"])
+        for i, b in enumerate(g["bodies"]):
+            m, com = b["m"], np.array(b["com"])
+            mc = np.array([[b["ixx"], b["ixy"], b["ixz"]], [b["ixy"], b["iyy"], b["iyz"]], [b["ixz"], b["iyz"], b["izz"]]])
+            moment = mc + m * (com @ com * np.eye(3) - np.outer(com, com))
+            assert d.mass[i] == m
+            np.testing.assert_allclose(d.cross_part[i], m * com, rtol=1e-15, atol=0)
+            np.testing.assert_allclose(d.moment[i].reshape(3, 3), moment, rtol=1e-13, atol=1e-20)
+            assert int(d.parent[i]) == b["parent"]
+            assert int(d.joint_type[i]) == b["joint_type"]
+            if b["xyz"] is not None:
+                np.testing.assert_array_equal(d.init_iso[i][4:], b["xyz"])
+                np.testing.assert_allclose(d.init_iso[i][:4], gp.quat_from_euler(*b["rpy"]), rtol=0, atol=1e-16)
+            if b["joint_type"] != gp.FIXED and b["joint_type"] != gp.FLOATING:
+                np.testing.assert_array_equal(d.axis[i], b["axis"])
+
+
+def test_shard_ranges_cover_everything():
+    for n, w in ((65536, 8), (262144, 3), (7, 8), (1, 1), (1000003, 8)):
+        ranges = [shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = shard_sizes(n, w)
+        assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from gorilla_physics_b200 import Mechanism
+from gorilla_physics_b200.sharding import shard_range, reduce_diagnostics
+from oracle.binding import OracleMechanism
+from tests.test_parity_gpu import random_states
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+mech = Mechanism.from_model("double_pendulum"); desc = mech.desc(); orc = OracleMechanism(desc)
+n = 37
+q, v = random_states(desc, n, seed=5, q_range=3.0)
+lo, hi = shard_range(n, rank, world)
+# each rank advances only its own environments (no communication on the step path) ...
+q1, v1 = orc.batch_rollout(q[lo:hi], v[lo:hi], 1e-3, 50, n_threads=1)
+ke = sum(orc.kinetic_energy(q1[e], v1[e]) for e in range(hi - lo))
+pe = sum(orc.gravitational_energy(q1[e]) for e in range(hi - lo))
+sums = torch.tensor([ke, pe, 0.0, 0.0], dtype=torch.float64)
+reduce_diagnostics(sums)                      # ... and only the diagnostic sums are all-reduced
+if rank == 0:
+    qa, va = orc.batch_rollout(q, v, 1e-3, 50, n_threads=1)
+    ke_all = sum(orc.kinetic_energy(qa[e], va[e]) for e in range(n))
+    pe_all = sum(orc.gravitational_energy(qa[e]) for e in range(n))
+    assert abs(sums[0].item() - ke_all) < 1e-9 * max(1.0, abs(ke_all)), (sums, ke_all)
+    assert abs(sums[1].item() - pe_all) < 1e-9 * max(1.0, abs(pe_all)), (sums, pe_all)
+    print("gloo-ok")
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding_and_diagnostic_reduction(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "gloo-ok" in out.stdout
+
+
+def test_bench_reference_arm_non_zero_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
