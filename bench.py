@@ -31,19 +31,17 @@ sys.path.insert(0, str(ROOT))
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
-# FP64 work per environment time step of the kernel that runs each workload, counted as
-# 2*DFMA + DADD + DMUL thread-level instructions (ncu smsp__sass_thread_inst_executed_op_d{fma,add,mul}
-# _pred_on.sum / env-steps, see profiles/); DESIGN.md §4 has the derivation.
-FLOPS_PER_ENV_STEP = {
-    "so101_contact": 4467.0,
-    "so101": 4030.0,
-    "double_pendulum": 700.0,
-    "cart_pole": 600.0,
-    "rimless_wheel": 1100.0,
-    "hopper_1d": 2400.0,
-    "quadruped": 11000.0,
-    "navbot_contact": 12500.0,
-}
+# FP64 work per environment time step of the kernel that runs each workload: 2*DFMA + DADD + DMUL
+# thread-level instructions per env-step as counted by ncu
+# (smsp__sass_thread_inst_executed_op_d{fma,add,mul}_pred_on.sum of one step-kernel launch divided by
+# n_envs * inner steps). profiles/flop_counts.json holds the numbers with the capture they come
+# from; DESIGN.md §4 explains why this (executed, not reference-formulation) count is used.
+def load_flop_counts():
+    try:
+        return json.loads((ROOT / "profiles" / "flop_counts.json").read_text())["flop_per_env_step"]
+    except Exception:
+        return {}
+
 
 WORKLOADS = {
     # name: (n_envs per GPU, dt, randomize kwargs)
@@ -60,6 +58,14 @@ WORKLOADS = {
     "navbot_contact": (65536, 1.0 / 6000.0, dict(q_range=(-0.2, 0.2), v_range=(0.0, 0.0), base_t=(0.0, 0.0, 0.075),
                                                  t_jitter=(0.01, 0.01, 0.01), rpy_jitter=0.1)),
 }
+
+
+def load_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch (ncu --set full), or None"""
+    try:
+        return json.loads((ROOT / "profiles" / "flop_counts.json").read_text())["dram_bytes_per_launch"].get(workload)
+    except Exception:
+        return None
 
 
 def make_mechanism(name):
@@ -100,7 +106,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -180,11 +186,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="so101_contact", choices=list(WORKLOADS))
-    ap.add_argument("--inner", type=int, default=64, help="fused time steps per kernel launch")
+    ap.add_argument("--inner", type=int, default=128, help="fused time steps per kernel launch")
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -231,11 +237,11 @@ def main():
     barrier()
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = st.launch_count
     barrier()
+    sampler.start()
     for i in range(args.steps):
         with torch.cuda.stream(stream):
             flush.fill_(i & 0xFF)          # untimed L2 flush, ordered before the launch on the same stream
@@ -293,13 +299,14 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     per_gpu_rate = n_envs * inner * args.steps / (total_ms * 1e-3)
-    flops = FLOPS_PER_ENV_STEP.get(args.workload, 0.0)
+    flops = float(load_flop_counts().get(args.workload, 0.0))
     achieved_tf = per_gpu_rate * flops / 1e12
     alg_bytes_per_launch = n_envs * (nq + nv) * 8 * 2  # read + write q,v once per launch
     avg_launch_s = total_ms * 1e-3 / args.steps
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "frac": achieved_tf / fp64_peak if fp64_peak else None,
+        "traffic": load_traffic(args.workload),
         "peak_source": "gp_measure_fp64_peak: DFMA chain on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure)",
         "flop_per_env_step": flops,
         "hbm": {"achieved": alg_bytes_per_launch / avg_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -1,0 +1,21 @@
+"""Runs tests/cpp/test_reference_suite (built by __graft_entry__.build()): the reference's own
+known-answer tests restated against the C++ facade include/gorilla_b200.hpp, executed on the GPU
+through the C ABI with n_envs = 1."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "tests" / "cpp" / "test_reference_suite"
+
+
+@pytest.mark.gpu
+def test_cpp_reference_suite():
+    if not BIN.exists():
+        import __graft_entry__
+        __graft_entry__.build()
+    out = subprocess.run([str(BIN)], capture_output=True, text=True, timeout=600)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert "0 failed" in out.stdout
