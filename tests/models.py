@@ -167,3 +167,51 @@ def navbot_with_contact() -> Mechanism:
         m.add_contact_point(body, (0.0, 0.0, 0.0))
     m.add_halfspace((0, 0, 1), 0.0)
     return m
+
+
+def random_tree(seed: int, n_bodies: int, max_dof: int = 24, contact: bool = True):
+    """A random mechanism for the run-time-topology kernel: random parents (any earlier body or the
+    world), mixed joint types (floating joints may hang off other bodies, fixed joints may sit in
+    the middle of a chain), random unit axes, random joint origins, random positive-definite
+    inertias, prismatic joint springs, contact points and one or two halfspaces."""
+    rng = np.random.default_rng(seed)
+    d = MechanismDesc()
+    dof = 0
+    for i in range(n_bodies):
+        parent = int(rng.integers(0, i + 1))
+        choices = [REVOLUTE, REVOLUTE, PRISMATIC, FIXED]
+        if dof + 6 <= max_dof - (n_bodies - i - 1):
+            choices.append(FLOATING)
+        jt = int(rng.choice(choices))
+        if dof + (6 if jt == FLOATING else 1) > max_dof:
+            jt = FIXED
+        dof += {FIXED: 0, REVOLUTE: 1, PRISMATIC: 1, FLOATING: 6}[jt]
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        aa = rng.normal(size=3) * 0.7
+        origin = iso(rng.uniform(-0.3, 0.3, size=3), quat_from_scaled_axis(aa))
+        m = float(rng.uniform(0.2, 2.0))
+        com = rng.uniform(-0.1, 0.1, size=3)
+        a = rng.normal(size=(3, 3))
+        j_com = a @ a.T * 0.01 + np.eye(3) * 0.01
+        moment = j_com + m * (com @ com * np.eye(3) - np.outer(com, com))
+        spring = (float(rng.uniform(10, 100)), float(rng.uniform(-0.2, 0.2))) if (jt == PRISMATIC and rng.random() < 0.5) else None
+        d.add_body(parent, jt, axis=axis, init_iso=origin, moment=moment, cross_part=m * com, mass=m, spring=spring)
+    if contact:
+        for _ in range(int(rng.integers(1, 9))):
+            d.add_contact_point(int(rng.integers(1, n_bodies + 1)), rng.uniform(-0.2, 0.2, size=3),
+                                k=float(rng.choice([50e3, 10e3, 75e3])))
+        d.add_halfspace((0, 0, 1), -0.2, alpha=0.9, mu=0.5)
+        if rng.random() < 0.5:
+            n = np.array([0.3, 0.1, 1.0])
+            d.add_halfspace(n / np.linalg.norm(n), -0.4, alpha=1.0, mu=1.0)
+    return d
+
+
+def cube_in_corner() -> Mechanism:
+    """two halfspaces (ground + tilted wall): exercises the multi-halfspace contact mode"""
+    m = Mechanism.from_model("cube")
+    m.add_halfspace((0, 0, 1), -0.45, alpha=0.9, mu=0.5)
+    n = np.array([1.0, 0.0, 0.2])
+    m.add_halfspace(n / np.linalg.norm(n), -0.45, alpha=1.0, mu=0.3)
+    return m

@@ -303,3 +303,92 @@ def test_status_flags_nan_and_singular():
     st.step(1e-3)
     flags = st.status()
     assert flags[2] & 1 and not flags[0] and not flags[1] and not flags[3]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_trees_on_the_runtime_topology_kernel(seed):
+    """Random trees (floating joints hanging off bodies, fixed joints mid-chain, springs, one or two
+    halfspaces, up to 16 bodies / 24 dof) through the generic kernel: dynamics, forces, one step."""
+    nb = int(np.random.default_rng(1000 + seed).integers(1, 17))
+    desc = models.random_tree(1000 + seed, nb)
+    mech = Mechanism.from_desc(desc)
+    orc = oracle_of(mech.desc())
+    if desc.n_v == 0:
+        pytest.skip("no degrees of freedom drawn")
+    n = 96
+    q, v = random_states(desc, n, seed=seed, t_jitter=0.3, rpy_jitter=0.8)
+    tau = np.random.default_rng(seed).uniform(-1, 1, size=(n, desc.n_v))
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    vdot, cf = st.dynamics(tau=tau, contact_forces=True)
+    vdot_ref, cf_ref = orc.batch_dynamics(q, v, tau)
+    assert rel_err(vdot, vdot_ref) < TOL_DYN
+    assert rel_err(cf, cf_ref, floor=1e-6) < TOL_DYN
+    for integ in (Integrator.SemiImplicitEuler, Integrator.RungeKutta4):
+        st.update(q, v)
+        st.step(1e-4, tau=tau, integrator=integ)
+        q_ref, v_ref = orc.batch_rollout(q, v, 1e-4, 1, integrator=int(integ), tau=tau)
+        assert rel_err(st.q, q_ref) < TOL_STEP and rel_err(st.v, v_ref) < TOL_STEP
+
+
+def test_two_halfspaces_contact_mode():
+    """cube wedged between ground and a tilted wall: the multi-halfspace step kernels (static + generic)"""
+    for mech in (models.cube_in_corner(), generic_twin(models.cube_in_corner())):
+        desc = models.cube_in_corner().desc()
+        orc = oracle_of(desc)
+        n = 512
+        q, v = random_states(desc, n, seed=3, t_jitter=0.15, rpy_jitter=0.6)
+        st = MechanismState(mech, n)
+        st.update(q, v)
+        vdot, cf = st.dynamics(tau=None, contact_forces=True)
+        vdot_ref, cf_ref = orc.batch_dynamics(q, v)
+        touching_both = ((cf_ref != 0).any(axis=2).sum(axis=1) > 0).mean()
+        assert touching_both > 0.2
+        assert rel_err(vdot, vdot_ref) < TOL_DYN and rel_err(cf, cf_ref, floor=1e-6) < TOL_DYN
+        st.step(1e-3, n_steps=1)
+        q_ref, v_ref = orc.batch_rollout(q, v, 1e-3, 1)
+        assert rel_err(st.q, q_ref) < TOL_STEP and rel_err(st.v, v_ref) < TOL_STEP
+        st.update(q, v)
+        st.step(1e-3, n_steps=100)
+        assert_rollout_parity(orc, q, v, st.q, st.v, 1e-3, 100)
+
+
+def test_mechanism_without_degrees_of_freedom_and_per_env_tau():
+    from gorilla_physics_b200 import MechanismDesc, REVOLUTE
+    d = MechanismDesc()
+    d.add_body(0, FIXED, moment=np.eye(3), mass=1.0)
+    d.add_body(1, FIXED, moment=np.eye(3), mass=1.0)
+    st = MechanismState(Mechanism.from_desc(d), 5)
+    st.step(1e-3, n_steps=3)  # nothing to integrate, must not fault
+    q, v = st.state()
+    assert q.shape == (5, 0) and v.shape == (5, 0)
+    assert not st.status().any()
+    # distinct torques per environment reach the right environment
+    mech = Mechanism.from_model("pendulum")
+    orc = oracle_of(mech)
+    n = 77
+    tau = np.linspace(-50, 50, n).reshape(n, 1)
+    st = MechanismState(mech, n)
+    vdot = st.dynamics(tau=tau)
+    ref, _ = orc.batch_dynamics(np.zeros((n, 1)), np.zeros((n, 1)), tau)
+    assert rel_err(vdot, ref) < TOL_DYN and np.unique(np.round(vdot, 9)).size == n
+
+
+def test_simulate_history_matches_reference_layout():
+    """simulate() returns every state including the initial one (reference simulate.rs:99-108)"""
+    mech = Mechanism.from_model("double_pendulum")
+    orc = oracle_of(mech)
+    n = 9
+    q, v = random_states(mech.desc(), n, seed=8, q_range=1.0)
+    st = MechanismState(mech, n)
+    nsteps, hq, hv = st.simulate(0.02, 1e-3, q.copy(), v.copy(), history=True)
+    assert hq.shape == (nsteps + 1, n, 2) and hv.shape == (nsteps + 1, n, 2)
+    np.testing.assert_array_equal(hq[0], q)
+    for e in range(n):
+        _, _, rq, rv = orc.rollout(q[e], v[e], 1e-3, nsteps, history=True)
+        assert np.abs(hq[:, e] - rq).max() < 1e-10 and np.abs(hv[:, e] - rv).max() < 1e-9
+    # the python-level simulate() with a host closure (the reference's control_fn)
+    from gorilla_physics_b200 import simulate as py_simulate
+    st.update(q, v)
+    qs, vs = py_simulate(st, 0.005, 1e-3, control_fn=lambda s: np.zeros((n, 2)))
+    np.testing.assert_allclose(qs, hq[:qs.shape[0]], rtol=0, atol=1e-13)
