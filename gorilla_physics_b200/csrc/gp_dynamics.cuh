@@ -194,20 +194,26 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
 
     // parent twist / bias acceleration in parent coordinates. The world "accelerates upwards
     // at g" (reference dynamics.rs:200-224) which is how gravity enters.
+    // a parent that is rigidly attached to the world (fixed joints only, e.g. the SO-101 base)
+    // has zero twist and a constant acceleration (0; g'): treat its children like root joints
+    const bool moving_parent = (p >= 0) && !Topo::anchored(P, p);
     SV vi, ai;
-    if (p >= 0) {
+    if (moving_parent) {
       vi = motion_to_child(E, r, vel[p]);
       ai = motion_to_child(E, r, acc[p]);
+    } else if (p >= 0) {
+      vi = svz();
+      ai = SV{v3z(), mulT(E, acc[p].l)};
     } else {  // world: zero twist, acceleration (0; 0,0,g) -> E^T (0,0,g)
       vi = svz();
       ai = SV{v3z(), V3{E.m[6] * kGravity, E.m[7] * kGravity, E.m[8] * kGravity}};
     }
     // joint twist vJ = S qdot and Coriolis term c = v_i x vJ (reference dynamics.rs:105-139,
     // util.rs:44-53 se3_commutator; the joint bias S-dot term is zero for all joint types).
-    // For a joint on the world the parent-induced twist is zero, hence c = vJ x vJ = 0.
+    // Without a moving parent the parent-induced twist is zero, hence c = vJ x vJ = 0.
     if (jt == JRevolute) {
       const double qd = v[vo];
-      if (p >= 0) {
+      if (moving_parent) {
         ai.a += cross_axis<Topo>(P, i, vi.a, qd);  // w x (a qd)
         ai.l += cross_axis<Topo>(P, i, vi.l, qd);  // vl x (a qd)
         vi.a = axis_add<Topo>(P, i, vi.a, qd);
@@ -216,7 +222,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       }
     } else if (jt == JPrismatic) {
       const double qd = v[vo];
-      if (p >= 0) {
+      if (moving_parent) {
         ai.l += cross_axis<Topo>(P, i, vi.a, qd);  // w x (a qd)
         vi.l = axis_add<Topo>(P, i, vi.l, qd);
       } else {
@@ -225,7 +231,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     } else if (jt == JFloating) {
       const V3 wj = V3{v[vo], v[vo + 1], v[vo + 2]};
       const V3 vj = V3{v[vo + 3], v[vo + 4], v[vo + 5]};
-      if (p >= 0) {
+      if (moving_parent) {
         ai.a += cross(vi.a, wj);
         ai.l += cross(vi.a, vj) + cross(vi.l, wj);
         vi.a += wj;

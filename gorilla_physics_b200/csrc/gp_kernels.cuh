@@ -222,6 +222,9 @@ GP_D bool all_finite(const double* a, int n) {
 // capped at 168 registers (3 blocks/SM) than at 242 (2 blocks/SM), the 9-body trees do not.
 template <class Topo, int CONTACT>
 constexpr int step_min_blocks() {
+#ifdef GP_STEP_MIN_BLOCKS
+  return GP_STEP_MIN_BLOCKS;  // tuning builds only
+#endif
   if constexpr (Topo::kStatic) return Topo::min_blocks(CONTACT);
   return 1;
 }

@@ -6,7 +6,10 @@
 
 namespace gp {
 
-constexpr int kBlock = 128;
+#ifndef GP_BLOCK
+#define GP_BLOCK 128
+#endif
+constexpr int kBlock = GP_BLOCK;  // threads per block of the per-environment kernels
 
 enum IntegClass : int { IntegSIE = 0, IntegRK = 1 };
 

@@ -73,6 +73,7 @@ int finalize_mechanism(gp_mechanism* m) {
     P.depth[i] = t.depth[i];
     P.anc_mask[i] = t.anc_mask[i];
     P.has_children[i] = t.has_children[i];
+    P.anchored[i] = t.anchored[i];
     for (int k = 0; k < kMaxBodies; ++k) P.anc_at[i][k] = t.anc_at[i][k];
   }
   for (int k = 0; k < kMaxNV; ++k) P.dof_body[k] = t.dof_body[k];

@@ -46,6 +46,7 @@ struct MechParams {
   int anc_at[kMaxBodies][kMaxBodies];   // anc_at[i][k] = k-th ancestor of i (k = 0 -> i)
   unsigned anc_mask[kMaxBodies];        // bit j set: j is ancestor-or-self of i
   int has_children[kMaxBodies];
+  int anchored[kMaxBodies];  // fixed to the world through fixed joints only
   int dof_body[kMaxNV];
   int cp_begin[kMaxBodies + 1];  // contact points are body-major: [cp_begin[b], cp_begin[b+1])
   int has_spring[kMaxBodies];

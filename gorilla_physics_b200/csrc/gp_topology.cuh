@@ -39,6 +39,7 @@ struct TopoTables {
   int anc_at[kMaxBodies][kMaxBodies];
   unsigned anc_mask[kMaxBodies];
   int has_children[kMaxBodies];
+  int anchored[kMaxBodies];  // rigidly attached to the world through fixed joints only: zero twist
   int dof_body[kMaxNV];
 };
 
@@ -57,6 +58,7 @@ constexpr TopoTables make_tables(const TopoData& d) {
     t.depth[i] = 0;
     t.anc_mask[i] = 0u;
     t.has_children[i] = 0;
+    t.anchored[i] = 0;
     t.qoff[i] = 0;
     t.voff[i] = 0;
     for (int k = 0; k < kMaxBodies; ++k) t.anc_at[i][k] = -1;
@@ -80,6 +82,7 @@ constexpr TopoTables make_tables(const TopoData& d) {
     }
     t.depth[i] = k;
     if (d.parent[i] >= 0) t.has_children[d.parent[i]] = 1;
+    t.anchored[i] = (d.jtype[i] == JFixed && (d.parent[i] < 0 || t.anchored[d.parent[i]])) ? 1 : 0;
   }
   t.nq = qo;
   t.nv = vo;
@@ -176,6 +179,7 @@ struct StaticTopo {
   struct FVoff { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().voff[K]; } };
   struct FDepth { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().depth[K]; } };
   struct FChildren { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().has_children[K]; } };
+  struct FAnchored { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().anchored[K]; } };
   // ancestors of body K packed 4 bits each (value + 1), k-th nibble = k-th ancestor
   struct FAncRow {
     template <int K> static constexpr unsigned long long at() {
@@ -211,6 +215,7 @@ struct StaticTopo {
     return (int)((select_chain<FAncRow, 0, NB>(i) >> (4 * k)) & 15ull) - 1;
   }
   GP_HD static constexpr bool has_children(const MechParams&, int i) { return select_chain<FChildren, 0, NB>(i) != 0ull; }
+  GP_HD static constexpr bool anchored(const MechParams&, int i) { return select_chain<FAnchored, 0, NB>(i) != 0ull; }
   GP_HD static constexpr int dof_body(const MechParams&, int k) { return (int)select_chain<FDofBody, 0, NV>(k); }
   // dof a's body is an ancestor-or-self of dof b's body (mass-matrix entry (b,a) is structurally non-zero)
   GP_HD static constexpr bool dof_anc(const MechParams&, int a, int b) {
@@ -239,6 +244,7 @@ struct DynTopo {
   GP_HD static int depth(const MechParams& P, int i) { return P.depth[i]; }
   GP_HD static int anc_at(const MechParams& P, int i, int k) { return P.anc_at[i][k]; }
   GP_HD static bool has_children(const MechParams& P, int i) { return P.has_children[i] != 0; }
+  GP_HD static bool anchored(const MechParams& P, int i) { return P.anchored[i] != 0; }
   GP_HD static int dof_body(const MechParams& P, int k) { return P.dof_body[k]; }
   GP_HD static bool dof_anc(const MechParams& P, int a, int b) {
     return ((P.anc_mask[P.dof_body[b]] >> P.dof_body[a]) & 1u) != 0u;

@@ -49,9 +49,17 @@ def assert_rollout_parity(orc, q0, v0, q1, v1, dt, steps, tol=TOL_ROLLOUT, ampli
     environment."""
     q_ref, v_ref = orc.batch_rollout(q0, v0, dt, steps, **roll_kw)
     q_pert, v_pert = orc.batch_rollout(q0 * (1.0 + 1e-15), v0 * (1.0 - 1e-15), dt, steps, **roll_kw)
+    # environments in which the REFERENCE algorithm itself blows up (explicit integration of the
+    # Hunt-Crossley damping term can diverge from deep initial penetration) carry no parity
+    # information; they must be rare, and are left out of the comparison
+    sane = np.ones(len(q_ref), dtype=bool)
+    for arr in (q_ref, v_ref, q_pert, v_pert):
+        a = np.asarray(arr).reshape(len(arr), -1)
+        sane &= np.isfinite(a).all(axis=1) & (np.abs(np.nan_to_num(a)).max(axis=1, initial=0.0) < 1e8)
+    assert sane.mean() > 0.97, f"reference diverges in {100 * (1 - sane.mean()):.1f}% of the environments"
     for got, ref, pert in ((q1, q_ref, q_pert), (v1, v_ref, v_pert)):
-        err = rollout_errors(got, ref)
-        sens = rollout_errors(pert, ref)
+        err = rollout_errors(np.asarray(got)[sane], np.asarray(ref)[sane])
+        sens = rollout_errors(np.asarray(pert)[sane], np.asarray(ref)[sane])
         for quant in (0.5, 0.9, 1.0):
             bound = max(tol, amplification * float(np.quantile(sens, quant)))
             assert float(np.quantile(err, quant)) <= bound, (quant, float(np.quantile(err, quant)), bound)
