@@ -32,6 +32,12 @@ struct DynOut {
   long long env;
 };
 
+GP_D void gp_block_sync() {
+#if defined(__CUDA_ARCH__)
+  __syncthreads();
+#endif
+}
+
 GP_HD int hidx(int r, int c) { return r * (r + 1) / 2 + c; }  // packed lower triangle, c <= r
 
 // ---- joint axis helpers (AxZ folds the unit axis away) ------------------------------------
@@ -162,7 +168,9 @@ GP_D void mass_matrix_walk(const MechParams& P, int i, int row, SV F, const M3& 
 // (n, o) with signed distance n.x - o, 21 flops per body and plane, instead of composing
 // body->world poses; the world pose chain is only built by the parity kernels (DUMP), which must
 // report world-frame forces.
-template <class Topo, int CONTACT, bool DUMP>
+// SYNC (step kernels only, every thread of the block must call): block barriers between the
+// phases (1) or after every body (2) keep the block's warps on the same stretch of code.
+template <class Topo, int CONTACT, bool DUMP, int SYNC = 0>
 GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* v, const double* tau,
                             double* vdot, const DynOut& out) {
   constexpr int NB = Topo::NB;
@@ -297,7 +305,9 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       }
     }
     frc[i] = f;
+    if constexpr (SYNC >= 2) gp_block_sync();
   });
+  if constexpr (SYNC == 1) gp_block_sync();
 
   // ------------------------------------------------------------------ pass 2: leaf -> root
   double H[NV * (NV + 1) / 2];
@@ -347,6 +357,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       Iacc[p].m += Ip.m;
     }
 
+    if constexpr (SYNC >= 2) gp_block_sync();
     // mass-matrix rows of joint i: F = Ic S_i, H_ij = S_j^T F for every joint j supporting i
     // (reference mechanism.rs:637-696, momentum.rs:17-47)
     if (jt == JRevolute) {
@@ -388,6 +399,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     }
   });
 
+  if constexpr (SYNC >= 1) gp_block_sync();
   if (DUMP) {
     if (out.bias) {
 #pragma unroll U

@@ -228,13 +228,19 @@ constexpr int step_min_blocks() {
   if constexpr (Topo::kStatic) return Topo::min_blocks(CONTACT);
   return 1;
 }
+#ifndef GP_STEP_SYNC
+#define GP_STEP_SYNC 1
+#endif
 template <class Topo, int CONTACT, int INTEG>
 __global__ void __launch_bounds__(kBlock, (step_min_blocks<Topo, CONTACT>()))
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
-  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= A.n) return;
+  // threads past the end redo the last environment (and store nothing) so that the whole block
+  // can meet at the per-step barrier below
+  const long long env_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = env_raw < A.n;
+  const long long env = active ? env_raw : A.n - 1;
   const int nq = Topo::nq(P), nv = Topo::nv(P);
 
   double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
@@ -250,10 +256,15 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
 
 #pragma unroll 1
   for (int s = 0; s < A.n_steps; ++s) {
+#if GP_STEP_SYNC
+    // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
+    // then share instruction-cache lines instead of each streaming the whole body from L2
+    __syncthreads();
+#endif
     controller_tau<Topo>(P, A, q, v, tau_in, tau);
     if (INTEG == IntegSIE) {
       // semi_implicit_euler, reference integrators.rs:25-39, :276-319
-      status |= dynamics_core<Topo, CONTACT, false>(P, q, v, tau, vdot, none);
+      status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
 #pragma unroll U
       for (int k = 0; k < nv; ++k) v[k] = v[k] + vdot[k] * A.dt;
       advance_q<Topo>(P, q, v, A.dt, q);
@@ -268,7 +279,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
       for (int k = 0; k < nv; ++k) { v0[k] = v[k]; facc[k] = 0.0; }
 #pragma unroll 1
       for (int st = 0; st < n_stage; ++st) {
-        status |= dynamics_core<Topo, CONTACT, false>(P, q, v, tau, vdot, none);
+        status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
         if (st + 1 < n_stage) {
           // RK4: f1 + 2 f2 + 2 f3 (+ f4 below), stage steps dt/2, dt/2, dt ; RK2: stage step dt/2
           const double wgt = (st == 0) ? 1.0 : 2.0;
@@ -290,6 +301,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     }
   }
 
+  if (!active) return;
 #pragma unroll U
   for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
 #pragma unroll U
