@@ -278,6 +278,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       // point-vs-halfspace contact (reference contact.rs:103-128); the wrench is subtracted from
       // the body force (dynamics.rs:244-246)
       const int c0 = P.cp_begin[i], c1 = P.cp_begin[i + 1];
+#pragma unroll 1  // keep ONE copy of the force law per body: unrolling this loop x4 bloated the kernel by 27 KB
       for (int c = c0; c < c1; ++c) {
         const V3 loc = ld3(P.cp_loc[c]);
         V3 fb = v3z();
