@@ -232,7 +232,7 @@ constexpr int step_min_blocks() {
 #define GP_STEP_SYNC 1
 #endif
 template <class Topo, int CONTACT, int INTEG>
-__global__ void __launch_bounds__(kBlock, (step_min_blocks<Topo, CONTACT>()))
+__global__ void __launch_bounds__(Topo::kBlockSize, (step_min_blocks<Topo, CONTACT>()))
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
@@ -256,11 +256,12 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
 
 #pragma unroll 1
   for (int s = 0; s < A.n_steps; ++s) {
-#if GP_STEP_SYNC
+    if constexpr (GP_STEP_SYNC && Topo::kBlockSize >= 256) {
+    // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
     // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
     // then share instruction-cache lines instead of each streaming the whole body from L2
     __syncthreads();
-#endif
+    }
     controller_tau<Topo>(P, A, q, v, tau_in, tau);
     if (INTEG == IntegSIE) {
       // semi_implicit_euler, reference integrators.rs:25-39, :276-319
@@ -358,11 +359,11 @@ energy_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Ener
 }
 
 // ---- launchers (table type in gp_launch.h) ------------------------------------------------
-inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
 template <class Topo>
 cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
-  const dim3 g(grid_for(A.n)), b(kBlock);
+  const dim3 g(grid_for(A.n, Topo::kBlockSize)), b(Topo::kBlockSize);
   if (integ_class == IntegSIE) {
     if (contact == 0) step_kernel<Topo, 0, IntegSIE><<<g, b, 0, s>>>(P, A);
     else if (contact == 1) step_kernel<Topo, 1, IntegSIE><<<g, b, 0, s>>>(P, A);

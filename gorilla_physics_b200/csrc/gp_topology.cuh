@@ -171,6 +171,7 @@ struct StaticTopo {
   static constexpr int kUnroll = 64;
   static const char* name() { return Spec::name(); }
   static constexpr int min_blocks(int contact) { return Spec::min_blocks(contact); }
+  static constexpr int kBlockSize = Spec::block_size();
 
   struct FParent { template <int K> static constexpr unsigned long long at() { return (unsigned long long)(tables().parent[K] + 1); } };
   struct FJtype { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().jtype[K]; } };
@@ -229,6 +230,7 @@ struct DynTopo {
   static constexpr int NQ = kMaxNQ;
   static constexpr int NV = kMaxNV;
   static constexpr int kNVreal = kMaxNV;
+  static constexpr int kBlockSize = 128;
   static constexpr int kUnroll = 1;
   static const char* name() { return "generic"; }
 
@@ -262,16 +264,19 @@ struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static constexpr TopoData data() { return {1, {-1}, {GP_R}, {AxAny}}; }
   static const char* name() { return "pendulum_R"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 128; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "double_pendulum_RR"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 128; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "cart_pole_PR"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 128; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
   static constexpr TopoData data() {
@@ -279,22 +284,28 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
             {AxAny, AxZ, AxZ, AxZ, AxZ, AxZ, AxZ}};
   }
   static const char* name() { return "so101_X6Rz"; }
-  static constexpr int min_blocks(int contact) { return contact == 1 ? 3 : 1; }
+  // one 256-thread block per SM: its 8 warps walk the unrolled step body in lockstep (per-step
+  // barrier) and share instruction-cache lines; 246 registers, no spills (profiles/r1_tuning.md)
+  static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 256; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
   static const char* name() { return "floating_F"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 128; }
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper1d_FPP"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 128; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper_FPR"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 128; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
   static constexpr TopoData data() {
@@ -303,6 +314,7 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
   }
   static const char* name() { return "quadruped_F8R"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 256; }
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
   static constexpr TopoData data() {
@@ -311,6 +323,7 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   }
   static const char* name() { return "navbot_F8Rz"; }
   static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return 256; }
 };
 
 #undef GP_R
