@@ -86,6 +86,8 @@ SYMBOLS = {
     "gp_batch_set_state": (C.c_int, [vp, vp, vp]),
     "gp_batch_get_state": (C.c_int, [vp, vp, vp]),
     "gp_batch_set_tau": (C.c_int, [vp, vp]),
+    "gp_batch_set_controller_state": (C.c_int, [vp, vp]),
+    "gp_batch_get_controller_state": (C.c_int, [vp, vp]),
     "gp_batch_randomize": (C.c_int, [vp, C.c_uint64, C.POINTER(GpStateDist)]),
     "gp_batch_dynamics": (C.c_int, [vp, vp, vp]),
     "gp_batch_mass_matrix": (C.c_int, [vp, vp, vp]),

@@ -22,6 +22,7 @@ struct gp_batch {
   double* tau = nullptr;     // [n_v][ld]
   bool tau_set = false;
   unsigned* status = nullptr;  // [ld]
+  double* ctrl_state = nullptr;  // [2][ld] controller state (GP_CTRL_HOPPER_1D), allocated on first use
   double* stage = nullptr;     // staging for AoS<->SoA and outputs
   size_t stage_bytes = 0;
   double* scratch = nullptr;   // SoA outputs of dynamics / energy
@@ -283,6 +284,19 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
         return GP_ERR_INVALID;
       }
       break;
+    case GP_CTRL_HOPPER_1D:
+      if (!(m->table->is_static && td.nb == 3 && td.jtype[0] == JFloating && td.jtype[1] == JPrismatic &&
+            td.jtype[2] == JPrismatic) || n_cp < 4) {
+        set_error("GP_CTRL_HOPPER_1D needs a floating + prismatic + prismatic chain and "
+                  "[k_spring, h_setpoint, body_leg_length, leg_foot_length]");
+        return GP_ERR_INVALID;
+      }
+      if (!b->ctrl_state) {
+        GP_CUDA(cudaMalloc((void**)&b->ctrl_state, 2 * b->ld * sizeof(double)));
+        GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, 2 * b->ld * sizeof(double), b->stream));
+      }
+      A.ctrl_state = b->ctrl_state;
+      break;
     default:
       set_error("unknown controller %d", controller);
       return GP_ERR_INVALID;
@@ -366,6 +380,7 @@ void gp_batch_destroy(gp_batch* b) {
   cudaFree(b->v);
   cudaFree(b->tau);
   cudaFree(b->status);
+  cudaFree(b->ctrl_state);
   cudaFree(b->stage);
   cudaFree(b->scratch);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -421,6 +436,34 @@ int gp_batch_set_tau(gp_batch* b, const double* tau_host) {
   GP_CUDA(cudaStreamSynchronize(b->stream));
   b->tau_set = true;
   return GP_OK;
+}
+
+int gp_batch_set_controller_state(gp_batch* b, const double* state_host) {
+  int rc = check_batch(b, "gp_batch_set_controller_state");
+  if (rc) return rc;
+  if (!b->ctrl_state) GP_CUDA(cudaMalloc((void**)&b->ctrl_state, 2 * b->ld * sizeof(double)));
+  if (!state_host) {
+    GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, 2 * b->ld * sizeof(double), b->stream));
+    GP_CUDA(cudaStreamSynchronize(b->stream));
+    return GP_OK;
+  }
+  if ((rc = to_device_soa(b, state_host, b->ctrl_state, 2))) return rc;
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int gp_batch_get_controller_state(gp_batch* b, double* state_host) {
+  int rc = check_batch(b, "gp_batch_get_controller_state");
+  if (rc) return rc;
+  if (!state_host) {
+    set_error("gp_batch_get_controller_state: null output");
+    return GP_ERR_INVALID;
+  }
+  if (!b->ctrl_state) {
+    std::memset(state_host, 0, sizeof(double) * 2 * (size_t)b->n);
+    return GP_OK;
+  }
+  return to_host_aos(b, b->ctrl_state, state_host, 2);
 }
 
 int gp_batch_randomize(gp_batch* b, uint64_t seed, const gp_state_dist* dist) {

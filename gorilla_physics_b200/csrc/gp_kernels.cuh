@@ -136,7 +136,7 @@ GP_D void energy_core(const MechParams& P, const double* q, const double* v, dou
 // ---- in-kernel controllers (reference closures Fn(&MechanismState) -> Vec<JointTorque>) -----
 template <class Topo>
 GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q, const double* v,
-                         const double* tau_in, double* tau) {
+                         const double* tau_in, double* tau, double* cstate) {
   constexpr int NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
   if (A.controller == GP_CTRL_SO101_PD) {
@@ -204,6 +204,35 @@ GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q
       return;
     }
   }
+  if constexpr (Topo::NQ == 9 && Topo::NV == 8) {
+    if (A.controller == GP_CTRL_HOPPER_1D) {
+      // Hopper1DController, reference control/energy_control.rs:35-101 (floating body + 2 prismatic)
+      const double k_spring = A.cp[0], h_setpoint = A.cp[1], body_leg_length = A.cp[2], leg_foot_length = A.cp[3];
+      const double q1 = q[7], v1 = v[6], q_foot = q[8], v_foot = v[7];
+      const double v_vertical = v[5];  // state.v[0].spatial().linear.z (body-frame component)
+      if (cstate[1] < 0.0 && v_vertical > 0.0) {
+        // bottom of stance: choose the leg length that injects the missing energy
+        double KE, PE, SE;
+        energy_core<Topo>(P, q, v, KE, PE, SE, nullptr, 0, 0);
+        const double E = KE + PE + 0.5 * k_spring * (q_foot - 0.0) * (q_foot - 0.0);  // energy.rs:44-53
+        const double E_target = kGravity * (P.mass[0] * h_setpoint + P.mass[1] * (h_setpoint - body_leg_length) +
+                                            P.mass[2] * (h_setpoint - body_leg_length - leg_foot_length));
+        const double dE = E_target - E;
+        cstate[0] = q_foot + sqrt(q_foot * q_foot + 2.0 * dE / k_spring);
+      } else if (cstate[1] > 0.0 && v_vertical < 0.0) {
+        cstate[0] = 0.0;  // top of flight
+      }
+      const double tau1 = 2000.0 * (cstate[0] - q1) + 100.0 * (0.0 - v1);
+      const double tau_foot = (q_foot < 0.0) ? -k_spring * (q_foot - 0.0)                    // spring_force
+                                             : -1e5 * (q_foot - 0.0) - 125.0 * v_foot;      // mechanical_stop
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tau[k] = 0.0;
+      tau[6] = tau1 - tau_foot;
+      tau[7] = tau_foot;
+      cstate[1] = v_vertical;
+      return;
+    }
+  }
   // GP_CTRL_NONE: torques as loaded
 #pragma unroll U
   for (int k = 0; k < Topo::nv(P); ++k) tau[k] = tau_in[k];
@@ -252,6 +281,11 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
   }
   unsigned status = 0u;
+  double cstate[2] = {0.0, 0.0};
+  if (A.ctrl_state) {
+    cstate[0] = A.ctrl_state[env];
+    cstate[1] = A.ctrl_state[A.ld + env];
+  }
   DynOut none{nullptr, nullptr, nullptr, 0, 0};
 
 #pragma unroll 1
@@ -262,7 +296,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     // then share instruction-cache lines instead of each streaming the whole body from L2
     __syncthreads();
     }
-    controller_tau<Topo>(P, A, q, v, tau_in, tau);
+    controller_tau<Topo>(P, A, q, v, tau_in, tau, cstate);
     if (INTEG == IntegSIE) {
       // semi_implicit_euler, reference integrators.rs:25-39, :276-319
       status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
@@ -303,6 +337,10 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   }
 
   if (!active) return;
+  if (A.ctrl_state) {
+    A.ctrl_state[env] = cstate[0];
+    A.ctrl_state[A.ld + env] = cstate[1];
+  }
 #pragma unroll U
   for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
 #pragma unroll U

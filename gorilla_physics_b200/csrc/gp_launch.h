@@ -24,6 +24,7 @@ struct StepArgs {
   int integrator;  // gp_integrator
   int controller;  // gp_controller
   double cp[4];    // controller parameters
+  double* ctrl_state;  // [2][ld] per-environment controller state (GP_CTRL_HOPPER_1D) or nullptr
 };
 
 struct DynArgs {

@@ -41,6 +41,8 @@ class Controller(enum.IntEnum):
     SO101_PD = 1           # reference control/so101_control.rs:12-34, params [kp, kd, clamp]
     ACROBOT_SWINGUP = 2    # reference control/swingup.rs:9-69, params [m, l]
     CARTPOLE_SWINGUP = 3   # reference control/swingup.rs:76-110, params [m_c, m_p, l]
+    HOPPER_1D = 4          # reference control/energy_control.rs:24-101 (stateful), params
+    #                        [k_spring, h_setpoint, body_leg_length, leg_foot_length]
 
 
 def _f64(a, shape=None):
@@ -260,6 +262,16 @@ class MechanismState:
         """None -> zero torques (reference simulate.rs:27-48)."""
         ta = None if tau is None else self._rows(tau, self.n_v)
         check(lib().gp_batch_set_tau(self._h, _ptr(ta)))
+
+    def set_controller_state(self, state=None):
+        """(leg_length_setpoint, v_vertical_prev) per environment of Controller.HOPPER_1D; None resets to 0."""
+        sa = None if state is None else self._rows(state, 2)
+        check(lib().gp_batch_set_controller_state(self._h, _ptr(sa)))
+
+    def controller_state(self):
+        out = np.empty((self.n_envs, 2))
+        check(lib().gp_batch_get_controller_state(self._h, _ptr(out)))
+        return out
 
     def randomize(self, seed: int, q_range=(-1.0, 1.0), v_range=(-1.0, 1.0), base_t=(0.0, 0.0, 0.0),
                   t_jitter=(0.0, 0.0, 0.0), rpy_jitter=0.0, base_v=(0.0,) * 6, v_jitter=0.0):

@@ -89,7 +89,11 @@ enum gp_controller {
   GP_CTRL_SO101_PD = 1,        /* SO101PositionController, control/so101_control.rs:12-34;
                                   params: [kp, kd, clamp] (reference: 1000, 0.1, 10) */
   GP_CTRL_ACROBOT_SWINGUP = 2, /* swingup_acrobot, control/swingup.rs:9-69; params: [m, l] */
-  GP_CTRL_CARTPOLE_SWINGUP = 3 /* swingup_cart_pole, control/swingup.rs:76-110; params: [m_c, m_p, l] */
+  GP_CTRL_CARTPOLE_SWINGUP = 3, /* swingup_cart_pole, control/swingup.rs:76-110; params: [m_c, m_p, l] */
+  GP_CTRL_HOPPER_1D = 4        /* Hopper1DController, control/energy_control.rs:24-101; params:
+                                  [k_spring, h_setpoint, body_leg_length, leg_foot_length]. Stateful: two
+                                  f64 per environment (leg_length_setpoint, v_vertical_prev) live in the
+                                  batch, start at 0 and persist across gp_batch_step calls */
 };
 
 /* per-environment status bits (replace the reference's panics) */
@@ -232,6 +236,11 @@ int gp_batch_mass_matrix(gp_batch* batch, double* mass_matrix_host, double* bias
  * (simulate.rs:103). Asynchronous: returns after enqueueing on the batch stream. */
 int gp_batch_step(gp_batch* batch, double dt, int integrator, int n_steps, int controller,
                   const double* ctrl_params, int n_ctrl_params);
+
+/* controller state of GP_CTRL_HOPPER_1D: [n_envs][2] = (leg_length_setpoint, v_vertical_prev).
+ * set: NULL resets every environment to (0, 0), the values examples/1D_hopper.rs starts from. */
+int gp_batch_set_controller_state(gp_batch* batch, const double* state_host);
+int gp_batch_get_controller_state(gp_batch* batch, double* state_host);
 
 /* simulate(state, final_time, dt, control_fn, integrator) (simulate.rs:87-112) through
  * host buffers in one call: H2D of q/v (and tau when non-NULL), the rollout, D2H of the

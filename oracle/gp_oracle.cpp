@@ -756,16 +756,64 @@ int control_impl(const gpo_mechanism* m, const double* q, const double* v, int c
   }
 }
 
+// Hopper1DController::control, control/energy_control.rs:35-101. cstate = {leg_length_setpoint,
+// v_vertical_prev}; p = {k_spring, h_setpoint, body_leg_length, leg_foot_length}
+int control_hopper1d(const gpo_mechanism* m, const double* q, const double* v, const double* p, double* cstate,
+                     double* tau, Work& w) {
+  if (m->nb != 3 || m->bodies[0].jtype != J_FLOAT || m->bodies[1].jtype != J_PRIS || m->bodies[2].jtype != J_PRIS)
+    return 1;
+  const double k_spring = p[0], h_setpoint = p[1], body_leg_length = p[2], leg_foot_length = p[3];
+  for (int i = 0; i < 6; ++i) tau[i] = 0.0;  // first floating joint unactuated
+  double q1 = q[7], v1 = v[6], q_foot = q[8], v_foot = v[7];
+  double v_vertical = v[5];
+  double m_body = m->bodies[0].mass, m_leg = m->bodies[1].mass, m_foot = m->bodies[2].mass;
+  if (cstate[1] < 0.0 && v_vertical > 0.0) {
+    // hopper_energy, energy.rs:44-53
+    double KE = kinetic_energy_impl(m, q, v, w);
+    double PE = 0.0;
+    for (int i = 1; i <= m->nb; ++i) PE += m->bodies[i - 1].mass * GRAVITY * w.b2r[i].t.z;
+    double l_rest = 0.0;
+    double EPE = 0.5 * k_spring * (q_foot - l_rest) * (q_foot - l_rest);
+    double E = KE + PE + EPE;
+    double E_target = GRAVITY * (m_body * h_setpoint + m_leg * (h_setpoint - body_leg_length) +
+                                 m_foot * (h_setpoint - body_leg_length - leg_foot_length));
+    double dE = E_target - E;
+    cstate[0] = q_foot + std::sqrt(q_foot * q_foot + 2.0 * dE / k_spring);
+  } else if (cstate[1] > 0.0 && v_vertical < 0.0) {
+    cstate[0] = 0.0;
+  }
+  double kp = 2000.0, kd = 100.0;
+  double p_term = kp * (cstate[0] - q1);
+  double d_term = kd * (0.0 - v1);
+  double tau1 = p_term + d_term;
+  double l_rest = 0.0;
+  double tau_foot;
+  if (q_foot < l_rest) {
+    tau_foot = -k_spring * (q_foot - l_rest);  // spring_force
+  } else {
+    double k_stop = 1e5, b_stop = 125.0;
+    tau_foot = -k_stop * (q_foot - l_rest) - b_stop * v_foot;  // mechanical_stop
+  }
+  tau[6] = tau1 - tau_foot;
+  tau[7] = tau_foot;
+  cstate[1] = v_vertical;
+  return 0;
+}
+
 int rollout_impl(const gpo_mechanism* m, double* q, double* v, const double* tau, double dt,
                  int64_t n_steps, int integrator, int controller, const double* params,
                  double* hq, double* hv, Work& w) {
   int rc = 0;
   double tau_c[GPO_MAX_NV];
+  double cstate[2] = {0.0, 0.0};  // Hopper1DController starts from (0, 0), examples/1D_hopper.rs:105-113
   if (hq) std::memcpy(hq, q, sizeof(double) * m->n_q);
   if (hv) std::memcpy(hv, v, sizeof(double) * m->n_v);
   for (int64_t s = 0; s < n_steps; ++s) {
     const double* t = tau;
-    if (controller != 0) {
+    if (controller == 4) {
+      rc |= control_hopper1d(m, q, v, params, cstate, tau_c, w);
+      t = tau_c;
+    } else if (controller != 0) {
       rc |= control_impl(m, q, v, controller, params, tau_c, w);
       t = tau_c;
     }

@@ -343,3 +343,17 @@ def test_so101_pd_controller_holds_zero_pose():  # control/so101_control.rs:12-3
     np.testing.assert_allclose(tau, np.full(6, -10.0))  # 1000 * -0.02 = -20 clamped to -10
     tau = o.control(np.full(6, 0.001), np.full(6, 1.0), 1, (1000.0, 0.1, 10.0))
     np.testing.assert_allclose(tau, np.full(6, -1.1))
+
+
+def test_hopper_1d_example_hops_to_setpoint():  # examples/1D_hopper.rs + control/energy_control.rs:24-101
+    """Hopper1DController (stateful, Raibert-style energy control): the body keeps hopping and its
+    apex height settles near h_setpoint = 0 (ground at -20, leg lengths 2 + 10)."""
+    m = models.hopper1d_on_ground()
+    o = oracle_of(m)
+    q, v = m.desc().zero_state()
+    _, _, hq, _ = o.rollout(q, v, 1.0 / 500.0, 15000, SIE, controller=4, params=(200.0, 0.0, 2.0, 10.0), history=True)
+    z = hq[:, 6]
+    apex = [z[i] for i in range(1, len(z) - 1) if z[i] > z[i - 1] and z[i] >= z[i + 1]]
+    assert len(apex) >= 6 and np.isfinite(hq).all()
+    assert abs(apex[-1] - 0.0) < 0.5 and abs(apex[-1] - apex[-2]) < 0.05
+    assert z.min() > -12.5  # never collapses through the ground (-20 + 2 + 10 = -8 at rest)

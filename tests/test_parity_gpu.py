@@ -400,3 +400,31 @@ def test_simulate_history_matches_reference_layout():
     st.update(q, v)
     qs, vs = py_simulate(st, 0.005, 1e-3, control_fn=lambda s: np.zeros((n, 2)))
     np.testing.assert_allclose(qs, hq[:qs.shape[0]], rtol=0, atol=1e-13)
+
+
+def test_stateful_hopper_controller_matches_oracle():
+    """Hopper1DController in-kernel (reference control/energy_control.rs:24-101): per-environment
+    controller state persists across launches; parity over several hops."""
+    mech = models.hopper1d_on_ground()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 200
+    q, v = random_states(desc, n, seed=21, base_t=(0, 0, -2.0), t_jitter=2.0, rpy_jitter=0.0, q_range=0.0, v_range=0.0)
+    q[:, 0:3] = 0.0
+    q[:, 3] = 1.0
+    params = (200.0, 0.0, 2.0, 10.0)
+    dt = 1.0 / 500.0
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    # 3000 steps split over several launches: the controller state must carry over
+    for chunk in (1, 499, 1000, 1500):
+        st.step(dt, n_steps=chunk, controller=Controller.HOPPER_1D, ctrl_params=params)
+    assert_rollout_parity(orc, q, v, st.q, st.v, dt, 3000, controller=4, params=params)
+    cs = st.controller_state()
+    assert cs.shape == (n, 2) and np.isfinite(cs).all() and np.abs(cs[:, 1]).max() > 0
+    st.set_controller_state(None)
+    assert not st.controller_state().any()
+    # a mechanism that is not floating + prismatic + prismatic is refused
+    other = MechanismState(Mechanism.from_model("so101"), 4)
+    with pytest.raises(Exception):
+        other.step(dt, controller=Controller.HOPPER_1D, ctrl_params=params)
