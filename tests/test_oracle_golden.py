@@ -357,3 +357,70 @@ def test_hopper_1d_example_hops_to_setpoint():  # examples/1D_hopper.rs + contro
     assert len(apex) >= 6 and np.isfinite(hq).all()
     assert abs(apex[-1] - 0.0) < 0.5 and abs(apex[-1] - apex[-2]) < 0.05
     assert z.min() > -12.5  # never collapses through the ground (-20 + 2 + 10 = -8 at rest)
+
+
+def _two_mass_spring(mu):
+    """contact.rs:908-955 / :991-1033 fixture: floating body + prismatic(-z) foot with a joint spring"""
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=models.sphere_moment(1.0, 1.0), mass=1.0)
+    d.add_body(1, PRISMATIC, axis=(0, 0, -1), init_iso=iso((0, 0, -1.0)), moment=models.sphere_moment(1.0, 1.0),
+               mass=1.0, spring=(100.0, 0.0))
+    d.add_contact_point(2, (0, 0, 0))
+    d.add_halfspace((0, 0, 1), -2.0, alpha=1.0, mu=mu)
+    return d
+
+
+def test_spring_drop():  # contact.rs:908-985 (RK4, 4 s): exact zeros + energy
+    d = _two_mass_spring(mu=0.0)
+    o = oracle_of(d)
+    q, v = d.zero_state()
+    q, v = o.simulate(q, v, 4.0, 1e-3, RK4, history=False)
+    poses = o.poses(q)
+    foot, body = poses[1], poses[0]
+    assert foot[4] == 0.0 and foot[5] == 0.0  # assert_eq! in the reference
+    z_tol = ((1.0 + 1.0) * GRAVITY / 50e3) ** (2.0 / 3.0)
+    assert abs(foot[6] - (-2.0)) < 2.0 * z_tol
+    np.testing.assert_array_equal(body[:4], [0.0, 0.0, 0.0, 1.0])  # body upright, exactly
+    total = o.kinetic_energy(q, v) + o.gravitational_energy(q) + o.spring_energy(q)
+    assert abs(total - (1.0 * GRAVITY * -2.0 + 1.0 * GRAVITY * (-2.0 + 1.0))) < 1.5
+
+
+def test_spring_forward_drop():  # contact.rs:991-1074 (RK4): body leans forward at the first bottom
+    d = _two_mass_spring(mu=0.5)
+    o = oracle_of(d)
+    q, v = d.zero_state()
+    v[3] = 0.5
+    prev, had_bottom = 0.0, False
+    for _ in range(1500):
+        q, v = o.step(q, v, None, 1e-3, RK4)
+        v_spring = v[6]
+        if prev < 0.0 and v_spring >= 0.0:
+            had_bottom = True
+            quat = q[0:4]
+            assert quat[0] == 0.0 and quat[2] == 0.0 and quat[1] > 0.0 and quat[3] > 0.0  # rotation about +y
+            assert q[4] > o.poses(q)[1][4]  # body in front of the foot
+            break
+        prev = v_spring
+    assert had_bottom
+
+
+def test_compass_gait_standing():  # contact.rs:735-832 (RK4, 2 s): stands still on a 5 degree slope
+    m_hip, r_hip, m_leg, l_leg = 10.0, 0.3, 5.0, 1.0
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=np.eye(3) * (m_hip * r_hip * r_hip * 2.0 / 5.0), mass=m_hip)
+    mx = m_leg * (l_leg / 2.0) * (l_leg / 2.0)
+    for _ in range(2):
+        d.add_body(1, REVOLUTE, axis=(0, -1, 0), moment=np.diag([mx, mx, 0.0]), cross_part=(0, 0, -m_leg * l_leg / 2.0),
+                   mass=m_leg)
+    d.add_contact_point(2, (0, 0, -l_leg))
+    d.add_contact_point(3, (0, 0, -l_leg))
+    ang = math.radians(5.0)
+    n = np.array([math.sin(ang), 0.0, math.cos(ang)])
+    d.add_halfspace(n / np.linalg.norm(n), 0.0, alpha=1.0, mu=1.0)
+    q, v = d.zero_state()
+    q[6] = l_leg
+    q[7], q[8] = math.radians(30.0), math.radians(-30.0)
+    q, v = oracle_of(d).simulate(q, v, 2.0, 1e-3, RK4, history=False)
+    assert q[4] > 0.0 and q[6] > 0.0
+    assert v[0] == 0.0 and v[2] == 0.0 and v[4] == 0.0  # assert_eq! in the reference: planar motion stays planar
+    assert abs(v[1]) < 1e-3 and abs(v[3]) < 6e-3 and abs(v[5]) < 3e-2
