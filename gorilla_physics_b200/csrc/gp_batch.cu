@@ -28,6 +28,10 @@ struct gp_batch {
   double* scratch = nullptr;   // SoA outputs of dynamics / energy
   size_t scratch_bytes = 0;
   long long launches = 0;
+  // simulate() through host buffers is pipelined over chunks of environments on two extra streams
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  double* pipe_stage[2] = {nullptr, nullptr};
+  size_t pipe_stage_bytes[2] = {0, 0};
 };
 
 namespace {
@@ -236,7 +240,9 @@ int64_t step_count(double final_time, double dt) {
 }
 
 int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
-                 int n_cp) {
+                 int n_cp, long long env0 = 0, long long n_sub = -1, cudaStream_t stream = nullptr) {
+  if (n_sub < 0) n_sub = b->n;
+  if (!stream) stream = b->stream;
   const gp_mechanism* m = b->mech;
   if (integrator == GP_VELOCITY_STEPPING || integrator == GP_CCD_VELOCITY_STEPPING) {
     set_error("VelocityStepping / CCDVelocityStepping need the SOCP contact solver (out of scope)");
@@ -251,11 +257,11 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
     return GP_ERR_INVALID;
   }
   StepArgs A{};
-  A.q = b->q;
-  A.v = b->v;
-  A.tau = b->tau_set ? b->tau : nullptr;
-  A.status = b->status;
-  A.n = b->n;
+  A.q = b->q + env0;  // planes keep their stride ld: a sub-range is just an offset
+  A.v = b->v + env0;
+  A.tau = b->tau_set ? b->tau + env0 : nullptr;
+  A.status = b->status + env0;
+  A.n = n_sub;
   A.ld = b->ld;
   A.dt = dt;
   A.n_steps = n_steps;
@@ -294,8 +300,9 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
       if (!b->ctrl_state) {
         GP_CUDA(cudaMalloc((void**)&b->ctrl_state, 2 * b->ld * sizeof(double)));
         GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, 2 * b->ld * sizeof(double), b->stream));
+        GP_CUDA(cudaStreamSynchronize(b->stream));  // the first user may be a pipeline stream
       }
-      A.ctrl_state = b->ctrl_state;
+      A.ctrl_state = b->ctrl_state + env0;
       break;
     default:
       set_error("unknown controller %d", controller);
@@ -303,8 +310,73 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   }
   if (n_steps == 0) return GP_OK;
   const int ic = integrator == GP_SEMI_IMPLICIT_EULER ? IntegSIE : IntegRK;
-  GP_CUDA(m->table->step(contact_mode(m), ic, b->stream, m->params, A));
+  GP_CUDA(m->table->step(contact_mode(m), ic, stream, m->params, A));
   b->launches++;
+  return GP_OK;
+}
+
+// simulate() without history, pipelined: the environments are cut into chunks; chunk c's host->device
+// copy + layout change, rollout, and device->host copy run on stream c&1, so copies of one chunk
+// overlap the rollout of the other (PCIe is full duplex). Results are identical to the one-shot path.
+int simulate_pipelined(gp_batch* b, double* q_host, double* v_host, const double* tau_host, double dt,
+                       int integrator, int n_steps, int controller, const double* cp, int n_cp) {
+  const gp_mechanism* m = b->mech;
+  const int nq = m->n_q, nv = m->n_v;
+  // chunks are whole waves of the step kernel (SMs x block size environments) so that cutting the
+  // batch does not add partially filled waves; about four chunks
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->device);
+  const long long wave = (long long)n_sm * m->table->block_size;
+  const long long n_waves = (b->n + wave - 1) / wave;
+  const long long chunk = wave * ((n_waves + 3) / 4);
+  const size_t per_env = (size_t)(nq + nv + (tau_host ? nv : 0));
+  for (int s = 0; s < 2; ++s) {
+    if (!b->pipe_stream[s]) GP_CUDA(cudaStreamCreateWithFlags(&b->pipe_stream[s], cudaStreamNonBlocking));
+    int rc = ensure(&b->pipe_stage[s], &b->pipe_stage_bytes[s], (size_t)chunk * per_env * sizeof(double));
+    if (rc) return rc;
+  }
+  b->tau_set = tau_host != nullptr;
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  int slot = 0;
+  for (long long env0 = 0; env0 < b->n; env0 += chunk, slot ^= 1) {
+    const long long nc = (env0 + chunk <= b->n) ? chunk : b->n - env0;
+    cudaStream_t st = b->pipe_stream[slot];
+    double* sq = b->pipe_stage[slot];
+    double* sv = sq + (size_t)chunk * nq;
+    double* stau = sv + (size_t)chunk * nv;
+    const unsigned grid = (unsigned)((nc + kTile - 1) / kTile);
+    if (nq) {
+      GP_CUDA(cudaMemcpyAsync(sq, q_host + (size_t)env0 * nq, (size_t)nc * nq * sizeof(double), cudaMemcpyHostToDevice, st));
+      aos_to_soa_kernel<<<grid, 256, (size_t)kTile * nq * sizeof(double), st>>>(sq, b->q + env0, nc, b->ld, nq);
+      b->launches++;
+    }
+    if (nv) {
+      GP_CUDA(cudaMemcpyAsync(sv, v_host + (size_t)env0 * nv, (size_t)nc * nv * sizeof(double), cudaMemcpyHostToDevice, st));
+      aos_to_soa_kernel<<<grid, 256, (size_t)kTile * nv * sizeof(double), st>>>(sv, b->v + env0, nc, b->ld, nv);
+      b->launches++;
+      if (tau_host) {
+        GP_CUDA(cudaMemcpyAsync(stau, tau_host + (size_t)env0 * nv, (size_t)nc * nv * sizeof(double), cudaMemcpyHostToDevice, st));
+        aos_to_soa_kernel<<<grid, 256, (size_t)kTile * nv * sizeof(double), st>>>(stau, b->tau + env0, nc, b->ld, nv);
+        b->launches++;
+      }
+    }
+    GP_CUDA(cudaGetLastError());
+    int rc = launch_steps(b, dt, integrator, n_steps, controller, cp, n_cp, env0, nc, st);
+    if (rc) return rc;
+    if (nq) {
+      soa_to_aos_kernel<<<grid, 256, (size_t)kTile * nq * sizeof(double), st>>>(b->q + env0, sq, nc, b->ld, nq);
+      GP_CUDA(cudaMemcpyAsync(q_host + (size_t)env0 * nq, sq, (size_t)nc * nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+      b->launches++;
+    }
+    if (nv) {
+      soa_to_aos_kernel<<<grid, 256, (size_t)kTile * nv * sizeof(double), st>>>(b->v + env0, sv, nc, b->ld, nv);
+      GP_CUDA(cudaMemcpyAsync(v_host + (size_t)env0 * nv, sv, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+      b->launches++;
+    }
+    GP_CUDA(cudaGetLastError());
+  }
+  GP_CUDA(cudaStreamSynchronize(b->pipe_stream[0]));
+  GP_CUDA(cudaStreamSynchronize(b->pipe_stream[1]));
   return GP_OK;
 }
 
@@ -381,6 +453,13 @@ void gp_batch_destroy(gp_batch* b) {
   cudaFree(b->tau);
   cudaFree(b->status);
   cudaFree(b->ctrl_state);
+  for (int s = 0; s < 2; ++s) {
+    if (b->pipe_stream[s]) {
+      cudaStreamSynchronize(b->pipe_stream[s]);
+      cudaStreamDestroy(b->pipe_stream[s]);
+    }
+    cudaFree(b->pipe_stage[s]);
+  }
   cudaFree(b->stage);
   cudaFree(b->scratch);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -573,6 +652,8 @@ int gp_batch_simulate(gp_batch* b, double* q_host, double* v_host, const double*
     return GP_ERR_INVALID;
   }
   const gp_mechanism* m = b->mech;
+  if (!history_q && !history_v && b->n >= 65536 && n_steps > 0)
+    return simulate_pipelined(b, q_host, v_host, tau_host, dt, integrator, (int)n_steps, controller, cp, n_cp);
   if ((rc = gp_batch_set_state(b, q_host, v_host))) return rc;
   if ((rc = gp_batch_set_tau(b, tau_host))) return rc;
   if (!history_q && !history_v) {

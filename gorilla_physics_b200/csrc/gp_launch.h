@@ -54,6 +54,7 @@ struct KernelTable {
   const char* name;
   TopoData topo;
   bool is_static;
+  int block_size;  // threads per block of the step kernels
   cudaError_t (*step)(int contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
   cudaError_t (*dynamics)(int contact, cudaStream_t, const MechParams&, const DynArgs&);
   cudaError_t (*energy)(cudaStream_t, const MechParams&, const EnergyArgs&);

@@ -428,3 +428,31 @@ def test_stateful_hopper_controller_matches_oracle():
     other = MechanismState(Mechanism.from_model("so101"), 4)
     with pytest.raises(Exception):
         other.step(dt, controller=Controller.HOPPER_1D, ctrl_params=params)
+
+
+def test_pipelined_simulate_matches_resident_stepping():
+    """gp_batch_simulate cuts big batches into chunks and overlaps copies with rollouts on two streams;
+    the result must be bitwise what stepping the resident state gives (ragged last chunk included)."""
+    mech = models.so101_with_contact()
+    desc = mech.desc()
+    n = 70001
+    q, v = random_states(desc, n, seed=5)
+    tau = np.random.default_rng(5).uniform(-0.05, 0.05, size=(n, desc.n_v))
+    dt = 1.0 / 6000.0
+    ref = MechanismState(mech, n)
+    ref.update(q, v)
+    ref.step(dt, tau=tau, n_steps=16)
+    q_ref, v_ref = ref.state()
+    st = MechanismState(mech, n)
+    n_steps, q_out, v_out = st.simulate(15.5 * dt, dt, q.copy(), v.copy(), tau=tau)
+    assert n_steps == 16
+    np.testing.assert_array_equal(q_out, q_ref)
+    np.testing.assert_array_equal(v_out, v_ref)
+    # device state after the call is the final state too
+    q_dev, v_dev = st.state()
+    np.testing.assert_array_equal(q_dev, q_ref)
+    # and without torques
+    ref.update(q, v)
+    ref.step(dt, tau=None, n_steps=8)
+    n_steps, q_out, v_out = st.simulate(7.5 * dt, dt, q.copy(), v.copy())
+    np.testing.assert_array_equal(q_out, ref.q)
