@@ -43,6 +43,7 @@ class GpMechanismDesc(C.Structure):
         ("hs_normal", dp),
         ("hs_alpha", dp),
         ("hs_mu", dp),
+        ("armature", dp),
     ]
 
 
@@ -90,6 +91,7 @@ SYMBOLS = {
     "gp_batch_get_controller_state": (C.c_int, [vp, vp]),
     "gp_batch_randomize": (C.c_int, [vp, C.c_uint64, C.POINTER(GpStateDist)]),
     "gp_batch_dynamics": (C.c_int, [vp, vp, vp]),
+    "gp_batch_free_velocity": (C.c_int, [vp, C.c_double, C.c_int, vp]),
     "gp_batch_mass_matrix": (C.c_int, [vp, vp, vp]),
     "gp_batch_step": (C.c_int, [vp, C.c_double, C.c_int, C.c_int, C.c_int, dp, C.c_int]),
     "gp_batch_simulate": (C.c_int, [vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, dp, C.c_int,

@@ -578,6 +578,7 @@ int gp_batch_dynamics(gp_batch* b, double* vdot_host, double* contact_force_host
   A.status = b->status;
   A.n = b->n;
   A.ld = b->ld;
+  A.gravity = kGravity;
   GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if ((rc = to_host_aos(b, A.vdot, vdot_host, nv))) return rc;
@@ -589,6 +590,35 @@ int gp_batch_dynamics(gp_batch* b, double* vdot_host, double* contact_force_host
     }
   }
   return GP_OK;
+}
+
+int gp_batch_free_velocity(gp_batch* b, double dt, int gravity_enabled, double* v_free_host) {
+  int rc = check_batch(b, "gp_batch_free_velocity");
+  if (rc) return rc;
+  if (!v_free_host || !(dt == dt)) {
+    set_error("gp_batch_free_velocity: bad argument");
+    return GP_ERR_INVALID;
+  }
+  const gp_mechanism* m = b->mech;
+  const int nv = m->n_v;
+  if ((rc = ensure(&b->scratch, &b->scratch_bytes, (size_t)(nv + 1) * b->ld * sizeof(double)))) return rc;
+  DynArgs A{};
+  A.q = b->q;
+  A.v = b->v;
+  A.tau = b->tau_set ? b->tau : nullptr;
+  A.vdot = b->scratch;
+  A.status = b->status;
+  A.n = b->n;
+  A.ld = b->ld;
+  A.gravity = gravity_enabled ? kGravity : 0.0;
+  A.free_dt = dt;
+  A.no_contact = 1;
+  if (dt == 0.0) {  // v + vdot * 0 = v: read the velocities back
+    return to_host_aos(b, b->v, v_free_host, nv);
+  }
+  GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
+  b->launches++;
+  return to_host_aos(b, A.vdot, v_free_host, nv);
 }
 
 int gp_batch_mass_matrix(gp_batch* b, double* mass_matrix_host, double* bias_host) {
@@ -608,6 +638,7 @@ int gp_batch_mass_matrix(gp_batch* b, double* mass_matrix_host, double* bias_hos
   A.status = b->status;
   A.n = b->n;
   A.ld = b->ld;
+  A.gravity = kGravity;
   GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if (mass_matrix_host) {

@@ -172,7 +172,7 @@ GP_D void mass_matrix_walk(const MechParams& P, int i, int row, SV F, const M3& 
 // phases (1) or after every body (2) keep the block's warps on the same stretch of code.
 template <class Topo, int CONTACT, bool DUMP, int SYNC = 0>
 GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* v, const double* tau,
-                            double* vdot, const DynOut& out) {
+                            double* vdot, const DynOut& out, const double gravity = kGravity) {
   constexpr int NB = Topo::NB;
   constexpr int NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
@@ -214,7 +214,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       ai = SV{v3z(), mulT(E, acc[p].l)};
     } else {  // world: zero twist, acceleration (0; 0,0,g) -> E^T (0,0,g)
       vi = svz();
-      ai = SV{v3z(), V3{E.m[6] * kGravity, E.m[7] * kGravity, E.m[8] * kGravity}};
+      ai = SV{v3z(), V3{E.m[6] * gravity, E.m[7] * gravity, E.m[8] * gravity}};
     }
     // joint twist vJ = S qdot and Coriolis term c = v_i x vJ (reference dynamics.rs:105-139,
     // util.rs:44-53 se3_commutator; the joint bias S-dot term is zero for all joint types).
@@ -365,13 +365,13 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       SV F;
       F.a = sym_mul_axis<Topo>(P, i, Ic.J);
       F.l = cross_axis<Topo>(P, i, Ic.c, -1.0);  // m*0 - c x a
-      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a);
+      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a) + P.armature[i];  // hybrid/articulated/mod.rs:247
       mass_matrix_walk<Topo>(P, i, vo, F, E, r, q, sn, cs, H);
     } else if (jt == JPrismatic) {
       SV F;
       F.a = cross_axis<Topo>(P, i, Ic.c, 1.0);  // J*0 + c x a
       F.l = axis_scaled<Topo>(P, i, Ic.m);
-      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.l);
+      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.l) + P.armature[i];
       mass_matrix_walk<Topo>(P, i, vo, F, E, r, q, sn, cs, H);
     } else if (jt == JFloating) {
       // S = identity: the F columns are the columns of the 6x6 composite inertia

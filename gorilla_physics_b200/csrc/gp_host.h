@@ -11,7 +11,7 @@ struct gp_mechanism {
   // flat description, owned (what MechanismState::new receives; reference mechanism.rs:62-148)
   int nb = 0, n_q = 0, n_v = 0;
   std::vector<int32_t> parent, joint_type, has_spring;
-  std::vector<double> axis, init_iso, moment, cross_part, mass, spring_k, spring_l;
+  std::vector<double> axis, init_iso, moment, cross_part, mass, spring_k, spring_l, armature;
   // contact points kept body-major, insertion order within a body (reference contact.rs:103-128)
   std::vector<int32_t> cp_body;
   std::vector<double> cp_location, cp_k;

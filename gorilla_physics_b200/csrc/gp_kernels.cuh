@@ -369,7 +369,12 @@ dynamics_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Dy
   DynOut out{A.contact_force, A.mass_matrix, A.bias, A.ld, env};
   if (A.contact_force)
     for (int c = 0; c < 3 * P.n_cp; ++c) A.contact_force[(long long)c * A.ld + env] = 0.0;
-  unsigned status = dynamics_core<Topo, CONTACT, true>(P, q, v, tau, vdot, out);
+  unsigned status = A.no_contact ? dynamics_core<Topo, 0, true>(P, q, v, tau, vdot, out, A.gravity)
+                                 : dynamics_core<Topo, CONTACT, true>(P, q, v, tau, vdot, out, A.gravity);
+  if (A.free_dt != 0.0) {
+#pragma unroll U
+    for (int k = 0; k < nv; ++k) vdot[k] = v[k] + vdot[k] * A.free_dt;
+  }
 #pragma unroll U
   for (int k = 0; k < nv; ++k) A.vdot[(long long)k * A.ld + env] = vdot[k];
   if (!all_finite(vdot, nv)) status |= kEnvNaN;

@@ -37,6 +37,9 @@ struct DynArgs {
   double* bias;           // [n_v][ld] or nullptr
   unsigned* status;
   long long n, ld;
+  double gravity;       // 9.81, or 0 with gravity disabled (free_velocity)
+  double free_dt;       // != 0: vdot receives v + vdot * free_dt (Articulated::free_velocity)
+  int no_contact;       // free_velocity ignores contact forces
 };
 
 struct EnergyArgs {

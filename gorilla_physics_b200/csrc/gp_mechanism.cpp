@@ -113,6 +113,7 @@ int finalize_mechanism(gp_mechanism* m) {
     P.has_spring[i] = m->has_spring[i];
     P.spring_k[i] = m->spring_k[i];
     P.spring_l[i] = m->spring_l[i];
+    P.armature[i] = m->armature[i];
   }
   // contact points are stored body-major already
   int c = 0;
@@ -241,6 +242,13 @@ int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
     m->has_spring.push_back(sp ? 1 : 0);
     m->spring_k.push_back(sp && d->spring_k ? d->spring_k[i] : 0.0);
     m->spring_l.push_back(sp && d->spring_l ? d->spring_l[i] : 0.0);
+    const double arm = d->armature ? d->armature[i] : 0.0;
+    if (!(arm >= 0.0) || (arm != 0.0 && jt != GP_JOINT_REVOLUTE && jt != GP_JOINT_PRISMATIC)) {
+      set_error("joint %d: armature must be >= 0 and only applies to revolute / prismatic joints", i + 1);
+      delete m;
+      return GP_ERR_INVALID;
+    }
+    m->armature.push_back(arm);
   }
   for (int h = 0; h < d->n_halfspaces; ++h) {
     m->hs_point.insert(m->hs_point.end(), d->hs_point + 3 * h, d->hs_point + 3 * h + 3);
@@ -291,6 +299,7 @@ int gp_mechanism_get_desc(const gp_mechanism* m, gp_mechanism_desc* o) {
   o->hs_normal = m->hs_normal.data();
   o->hs_alpha = m->hs_alpha.data();
   o->hs_mu = m->hs_mu.data();
+  o->armature = m->armature.data();
   return GP_OK;
 }
 

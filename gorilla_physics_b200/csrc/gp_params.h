@@ -71,6 +71,7 @@ struct MechParams {
   double mass[kMaxBodies];
   double spring_k[kMaxBodies];
   double spring_l[kMaxBodies];
+  double armature[kMaxBodies];  // added to the joint's own diagonal entry of H
 
   // ---- contact (contact.rs:17-38, halfspace.rs:6-11)
   double cp_loc[kMaxCP][3];

@@ -74,6 +74,7 @@ class MechanismDesc:
         self._parent, self._jtype, self._axis, self._iso = [], [], [], []
         self._moment, self._cross, self._mass = [], [], []
         self._has_spring, self._spring_k, self._spring_l = [], [], []
+        self._armature = []
         self._cp_body, self._cp_loc, self._cp_k = [], [], []
         self._hs_point, self._hs_normal, self._hs_alpha, self._hs_mu = [], [], [], []
         self.names: list[str] = []
@@ -81,7 +82,7 @@ class MechanismDesc:
     # ---- construction ------------------------------------------------------
     def add_body(self, parent: int, joint_type: int, *, axis=(0.0, 0.0, 1.0), init_iso=IDENTITY_ISO,
                  moment=None, cross_part=(0.0, 0.0, 0.0), mass=0.0,
-                 spring: Optional[Sequence[float]] = None, name: str = "") -> int:
+                 spring: Optional[Sequence[float]] = None, armature: float = 0.0, name: str = "") -> int:
         """Append joint+body; returns the new 1-based body id. `parent` must already exist
         (the reference resolves parents by frame name and panics otherwise, mechanism.rs:98-116)."""
         body_id = len(self._parent) + 1
@@ -100,6 +101,7 @@ class MechanismDesc:
         self._has_spring.append(0 if spring is None else 1)
         self._spring_k.append(0.0 if spring is None else float(spring[0]))
         self._spring_l.append(0.0 if spring is None else float(spring[1]))
+        self._armature.append(float(armature))
         self.names.append(name or f"body{body_id}")
         return body_id
 
@@ -171,6 +173,11 @@ class MechanismDesc:
     @property
     def spring_l(self):
         return np.asarray(self._spring_l, dtype=np.float64)
+
+    @property
+    def armature(self):
+        """reflected drivetrain inertia on the joint's own diagonal of M (reference revolute.rs:29)"""
+        return np.asarray(self._armature, dtype=np.float64)
 
     @property
     def cp_body(self):
@@ -247,7 +254,7 @@ class MechanismDesc:
                        init_iso=np.asarray(kw["init_iso"]).reshape(-1, 7)[i],
                        moment=np.asarray(kw["moment"]).reshape(-1, 9)[i],
                        cross_part=np.asarray(kw["cross_part"]).reshape(-1, 3)[i], mass=float(kw["mass"][i]),
-                       spring=spring)
+                       spring=spring, armature=float(kw["armature"][i]) if kw.get("armature") is not None else 0.0)
         for c in range(int(kw.get("n_contact_points", 0))):
             d.add_contact_point(int(kw["cp_body"][c]), np.asarray(kw["cp_location"]).reshape(-1, 3)[c],
                                 float(kw["cp_k"][c]))

@@ -80,6 +80,7 @@ class Mechanism:
             "cp_location": _f64(desc.cp_location), "cp_k": _f64(desc.cp_k),
             "hs_point": _f64(desc.hs_point), "hs_normal": _f64(desc.hs_normal),
             "hs_alpha": _f64(desc.hs_alpha), "hs_mu": _f64(desc.hs_mu),
+            "armature": _f64(desc.armature),
         }
         d = GpMechanismDesc()
         d.n_bodies = desc.n_bodies
@@ -155,7 +156,7 @@ class Mechanism:
             cp_location=arr(d.cp_location, 3 * nc, np.float64), cp_k=arr(d.cp_k, nc, np.float64),
             n_halfspaces=nh, hs_point=arr(d.hs_point, 3 * nh, np.float64),
             hs_normal=arr(d.hs_normal, 3 * nh, np.float64), hs_alpha=arr(d.hs_alpha, nh, np.float64),
-            hs_mu=arr(d.hs_mu, nh, np.float64))
+            hs_mu=arr(d.hs_mu, nh, np.float64), armature=arr(d.armature, nb, np.float64))
 
     def supports(self) -> np.ndarray:
         """supports[j-1][i-1] == 1 iff joint j supports body i (reference mechanism.rs:118-125)."""
@@ -296,6 +297,15 @@ class MechanismState:
         cf = np.zeros((self.n_envs, nc, 3)) if contact_forces else None
         check(lib().gp_batch_dynamics(self._h, _ptr(vdot), _ptr(cf) if (cf is not None and nc) else None))
         return (vdot, cf) if contact_forces else vdot
+
+    def free_velocity(self, dt: float, gravity_enabled: bool = True, tau="keep"):
+        """Articulated::free_velocity (reference hybrid/articulated/mod.rs:124-197): v + M^-1 (tau - c) dt,
+        armature on the diagonal of M, no contact forces. Does not advance the state."""
+        if not (isinstance(tau, str) and tau == "keep"):
+            self.set_tau(tau)
+        out = np.empty((self.n_envs, self.n_v))
+        check(lib().gp_batch_free_velocity(self._h, dt, 1 if gravity_enabled else 0, _ptr(out)))
+        return out
 
     def mass_matrix(self):
         """mass_matrix (reference mechanism.rs:637-696) and dynamics_bias (dynamics.rs:233-251)."""

@@ -127,6 +127,9 @@ typedef struct gp_mechanism_desc {
   const double* hs_normal;   /* [NH][3] unit outward normal */
   const double* hs_alpha;    /* [NH] */
   const double* hs_mu;       /* [NH] */
+  const double* armature;    /* [NB] reflected drivetrain inertia added to the joint's own mass-matrix
+                                diagonal (revolute.rs:29; used by hybrid/articulated/mod.rs:247); may be
+                                NULL = zeros. Revolute / prismatic joints only. */
 } gp_mechanism_desc;
 
 typedef struct gp_mechanism gp_mechanism; /* opaque */
@@ -225,6 +228,12 @@ int gp_batch_randomize(gp_batch* batch, uint64_t seed, const gp_state_dist* dist
  * world-frame force of calculate_contact_force_halfspace (contact.rs:321-338) summed
  * over halfspaces per contact point, points in the mechanism's body-major order. */
 int gp_batch_dynamics(gp_batch* batch, double* vdot_host, double* contact_force_host);
+/* Articulated::free_velocity(dt, tau, gravity_enabled) of the reference's second engine
+ * (hybrid/articulated/mod.rs:124-197): v + M^-1 (tau - c) dt with the armature on M's diagonal,
+ * no contact forces, gravity optional. v_free_host: [n_envs][n_v]. Uses the batch's tau buffer
+ * (zeros when none was set). The state is not advanced. */
+int gp_batch_free_velocity(gp_batch* batch, double dt, int gravity_enabled, double* v_free_host);
+
 /* mass_matrix(state), mechanism.rs:637-696: [n_envs][n_v][n_v] dense symmetric, and
  * dynamics_bias (dynamics.rs:233-251): [n_envs][n_v]. Either may be NULL. */
 int gp_batch_mass_matrix(gp_batch* batch, double* mass_matrix_host, double* bias_host);

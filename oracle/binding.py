@@ -45,6 +45,7 @@ class _Desc(C.Structure):
         ("hs_normal", _dp),
         ("hs_alpha", _dp),
         ("hs_mu", _dp),
+        ("armature", _dp),
     ]
 
 
@@ -84,6 +85,7 @@ def lib() -> C.CDLL:
         L.gpo_batch_rollout.argtypes = [vp, _dp, _dp, _dp, C.c_int64, C.c_double, C.c_int64, C.c_int,
                                         C.c_int, _dp, C.c_int]
         L.gpo_batch_dynamics.argtypes = [vp, _dp, _dp, _dp, C.c_int64, _dp, _dp, C.c_int]
+        L.gpo_free_velocity.argtypes = [vp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]
         L.gpo_kinetic_energy.argtypes = [vp, _dp, _dp]
         L.gpo_kinetic_energy.restype = C.c_double
         L.gpo_gravitational_energy.argtypes = [vp, _dp]
@@ -152,6 +154,8 @@ class OracleMechanism:
         keep["hs_normal"] = _f64(desc.hs_normal if nh else np.zeros((0, 3)), (nh, 3))
         keep["hs_alpha"] = _f64(desc.hs_alpha if nh else np.zeros(0), (nh,))
         keep["hs_mu"] = _f64(desc.hs_mu if nh else np.zeros(0), (nh,))
+        arm = getattr(desc, "armature", None)
+        keep["armature"] = _f64(arm if arm is not None and len(arm) == nb else np.zeros(nb), (nb,))
         d = _Desc()
         d.n_bodies = nb
         d.n_contact_points = nc
@@ -232,6 +236,17 @@ class OracleMechanism:
         """simulate() (simulate.rs:87): the step count follows the reference's f64 loop."""
         n = int(lib().gpo_simulate_step_count(final_time, dt))
         return self.rollout(q, v, dt, n, integrator, tau, controller, params, history)
+
+    def free_velocity(self, q, v, dt, tau=None, gravity_enabled=True):
+        """Articulated::free_velocity (hybrid/articulated/mod.rs:124-197)"""
+        q = _f64(q, (self.n_q,))
+        v = _f64(v, (self.n_v,))
+        tau = None if tau is None else _f64(tau, (self.n_v,))
+        out = np.zeros(self.n_v)
+        rc = lib().gpo_free_velocity(self._h, _d(q), _d(v), _d(tau), dt, 1 if gravity_enabled else 0, _d(out))
+        if rc != 0:
+            raise ArithmeticError("oracle: mass matrix not positive definite")
+        return out
 
     def kinetic_energy(self, q, v):
         q = _f64(q, (self.n_q,))

@@ -163,6 +163,7 @@ struct Body {
   double mass;
   bool has_spring;
   double spring_k, spring_l;
+  double armature;  // revolute.rs:29; only hybrid/articulated/mod.rs:247 reads it in the reference
   int qoff, voff, nq, nv;
   std::vector<ContactPoint> contact_points;  // rigid_body.rs:65
   int cp_index0;                             // index of this body's first point in the flat output
@@ -379,6 +380,12 @@ void mass_matrix(const gpo_mechanism* m, Work& w) {
         for (int c = 0; c < Sj.k; ++c)
           w.M[(bi.voff + r) * n_v + (bj.voff + c)] = dot(Fang[r], Sj.ang[c]) + dot(Flin[r], Sj.lin[c]);
     }
+  }
+  // armature on the joint's own diagonal entry (hybrid/articulated/mod.rs:247; zero by default, in which
+  // case this is exactly the reference's MechanismState mass matrix)
+  for (int i = 1; i <= nb; ++i) {
+    const Body& bi = m->bodies[i - 1];
+    if ((bi.jtype == J_REV || bi.jtype == J_PRIS) && bi.armature != 0.0) w.M[bi.voff * n_v + bi.voff] += bi.armature;
   }
   // mirror the lower triangle (mechanism.rs:688-693)
   for (int i = 0; i < n_v; ++i)
@@ -849,6 +856,7 @@ int gpo_mechanism_create(const gpo_mechanism_desc* d, gpo_mechanism** out) {
     b.has_spring = d->has_spring ? d->has_spring[i] != 0 : false;
     b.spring_k = (b.has_spring && d->spring_k) ? d->spring_k[i] : 0.0;
     b.spring_l = (b.has_spring && d->spring_l) ? d->spring_l[i] : 0.0;
+    b.armature = d->armature ? d->armature[i] : 0.0;
     switch (b.jtype) {
       case J_REV: case J_PRIS: b.nq = 1; b.nv = 1; break;
       case J_FLOAT: b.nq = 7; b.nv = 6; break;
@@ -973,6 +981,77 @@ int gpo_batch_dynamics(const gpo_mechanism* m, const double* q, const double* v,
   int rc = 0;
   for (int r : rcs) rc |= r;
   return rc;
+}
+
+// hybrid/articulated/mod.rs:124-197 (+ update_mass_matrix :199-269, nalgebra Cholesky)
+int gpo_free_velocity(const gpo_mechanism* m, const double* q, const double* v, const double* tau, double dt,
+                      int gravity_enabled, double* v_free) {
+  Work w;
+  bodies_to_root(m, q, w);
+  body_twists(m, v, w);
+  mass_matrix(m, w);
+  const int nb = m->nb, n = m->n_v;
+  // bias accelerations: world-frame commutator of body twist and joint twist, summed down the tree
+  SV bias[GPO_MAX_BODIES + 1];
+  for (int i = 1; i <= nb; ++i) {
+    const Body& b = m->bodies[i - 1];
+    SV jt = twist_transform(w.joint_twist[i - 1], w.b2r[i]);
+    const SV& bt = w.twist[i];
+    SV cor{cross(bt.ang, jt.ang), cross(bt.ang, jt.lin) + cross(bt.lin, jt.ang)};  // spatial_motion_cross
+    if (b.parent == 0) {
+      V3 g{0.0, 0.0, gravity_enabled ? GRAVITY : 0.0};
+      bias[i] = {cor.ang, g + cor.lin};
+    } else {
+      bias[i] = {bias[b.parent].ang + cor.ang, bias[b.parent].lin + cor.lin};
+    }
+  }
+  SV wr[GPO_MAX_BODIES + 1];
+  for (int i = 1; i <= nb; ++i) {
+    SpatialInertia I = inertia_transform(m->bodies[i - 1], w.b2r[i]);
+    V3 ia, il, ha, hl;
+    mul_inertia(I.moment, I.cross_part, I.mass, bias[i].ang, bias[i].lin, ia, il);
+    mul_inertia(I.moment, I.cross_part, I.mass, w.twist[i].ang, w.twist[i].lin, ha, hl);
+    // spatial_force_cross(v, Iv), util.rs:62-66
+    V3 fa = cross(w.twist[i].ang, ha) + cross(w.twist[i].lin, hl);
+    V3 fl = cross(w.twist[i].ang, hl);
+    wr[i] = {ia + fa, il + fl};
+  }
+  for (int i = nb; i >= 1; --i) {
+    int p = m->bodies[i - 1].parent;
+    if (p != 0) wr[p] = {wr[p].ang + wr[i].ang, wr[p].lin + wr[i].lin};
+  }
+  double c[GPO_MAX_NV];
+  for (int i = 1; i <= nb; ++i) {
+    const Body& b = m->bodies[i - 1];
+    Jac S = motion_subspace_world(b, w.b2r[i]);
+    for (int k = 0; k < S.k; ++k) c[b.voff + k] = dot(S.ang[k], wr[i].ang) + dot(S.lin[k], wr[i].lin);
+  }
+  // Cholesky (nalgebra: lower L, column by column), then two triangular solves
+  double L[GPO_MAX_NV * GPO_MAX_NV];
+  std::memcpy(L, w.M, sizeof(double) * n * n);
+  for (int j = 0; j < n; ++j) {
+    for (int k = 0; k < j; ++k) {
+      double f = L[j * n + k];
+      for (int r = j; r < n; ++r) L[r * n + j] -= f * L[r * n + k];
+    }
+    double d = L[j * n + j];
+    if (!(d > 0.0)) return 1;
+    d = std::sqrt(d);
+    L[j * n + j] = d;
+    for (int r = j + 1; r < n; ++r) L[r * n + j] /= d;
+  }
+  double x[GPO_MAX_NV];
+  for (int i = 0; i < n; ++i) x[i] = (tau ? tau[i] : 0.0) - c[i];
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < i; ++k) x[i] -= L[i * n + k] * x[k];
+    x[i] /= L[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    for (int k = i + 1; k < n; ++k) x[i] -= L[k * n + i] * x[k];
+    x[i] /= L[i * n + i];
+  }
+  for (int i = 0; i < n; ++i) v_free[i] = v[i] + x[i] * dt;
+  return 0;
 }
 
 double gpo_kinetic_energy(const gpo_mechanism* m, const double* q, const double* v) {

@@ -57,6 +57,7 @@ typedef struct gpo_mechanism_desc {
   const double* hs_normal;
   const double* hs_alpha;
   const double* hs_mu;
+  const double* armature; /* [NB] or NULL; hybrid/articulated/mod.rs:247 semantics */
 } gpo_mechanism_desc;
 
 typedef struct gpo_mechanism gpo_mechanism;
@@ -99,6 +100,11 @@ int gpo_batch_rollout(const gpo_mechanism* m, double* q, double* v, const double
                       const double* params, int n_threads);
 int gpo_batch_dynamics(const gpo_mechanism* m, const double* q, const double* v, const double* tau,
                        int64_t n_envs, double* vdot, double* contact_forces, int n_threads);
+
+/* Articulated::free_velocity (hybrid/articulated/mod.rs:124-197) with update_mass_matrix (:199-269):
+ * world-frame Coriolis commutator, armature on the diagonal, Cholesky solve, no contact. */
+int gpo_free_velocity(const gpo_mechanism* m, const double* q, const double* v, const double* tau, double dt,
+                      int gravity_enabled, double* v_free);
 
 /* energies (mechanism.rs:334-377) and poses (mechanism.rs:403) */
 double gpo_kinetic_energy(const gpo_mechanism* m, const double* q, const double* v);

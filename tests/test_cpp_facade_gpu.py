@@ -12,7 +12,9 @@ BIN = ROOT / "tests" / "cpp" / "test_reference_suite"
 
 @pytest.mark.gpu
 def test_cpp_reference_suite():
-    if not BIN.exists():
+    deps = [ROOT / "include" / "gorilla_b200.h", ROOT / "include" / "gorilla_b200.hpp",
+            ROOT / "tests" / "cpp" / "test_reference_suite.cpp"]
+    if not BIN.exists() or any(d.stat().st_mtime > BIN.stat().st_mtime for d in deps):
         import __graft_entry__
         __graft_entry__.build()
     out = subprocess.run([str(BIN)], capture_output=True, text=True, timeout=600)

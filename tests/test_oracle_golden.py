@@ -424,3 +424,45 @@ def test_compass_gait_standing():  # contact.rs:735-832 (RK4, 2 s): stands still
     assert q[4] > 0.0 and q[6] > 0.0
     assert v[0] == 0.0 and v[2] == 0.0 and v[4] == 0.0  # assert_eq! in the reference: planar motion stays planar
     assert abs(v[1]) < 1e-3 and abs(v[3]) < 6e-3 and abs(v[5]) < 3e-2
+
+
+# ---------------------------------------------------------------- hybrid::Articulated
+def test_articulated_step_tests_of_the_second_engine():
+    """hybrid/articulated/mod.rs:474-577: Articulated::step = free_velocity + integrate is this path's
+    semi-implicit Euler step without contact. cart: v stays; pendulum: swings to pi, energy kept."""
+    # cart (:474-501)
+    d = MechanismDesc()
+    d.add_body(0, PRISMATIC, axis=(1, 0, 0), moment=np.diag([0.01 + 0.01, 1.01, 1.01]) / 12.0, mass=1.0)
+    o = oracle_of(d)
+    q, v = o.rollout([0.0], [1.0], 1e-3, 2000, SIE)
+    assert abs(v[0] - 1.0) < 1e-3 and abs(q[0] - 2.0) < 1e-3
+    # pendulum (:504-534): sphere of mass 1, radius 1 at (l, 0, 0), revolute about y
+    l = 1.0
+    com = np.array([l, 0.0, 0.0])
+    moment = np.eye(3) * (2.0 / 5.0) + 1.0 * (com @ com * np.eye(3) - np.outer(com, com))
+    d = MechanismDesc()
+    d.add_body(0, REVOLUTE, axis=(0, 1, 0), moment=moment, cross_part=com, mass=1.0)
+    o = oracle_of(d)
+    e0 = o.kinetic_energy([0.0], [0.0]) + 1.0 * GRAVITY * 0.0
+    q, v, hq, hv = o.rollout([0.0], [0.0], 1e-3, 2000, SIE, history=True)
+    assert abs(hq[:, 0].max() - PI) < 1e-3
+    e1 = o.kinetic_energy(q, v) + 1.0 * GRAVITY * (-l * math.sin(q[0]))  # COM height
+    assert abs(e1 - e0) < 1e-2
+    # free_velocity == v + vdot dt of the MechanismState engine when armature = 0 and gravity is on
+    q0, v0 = [0.3], [0.7]
+    np.testing.assert_allclose(o.free_velocity(q0, v0, 1e-3), np.asarray(v0) + o.dynamics(q0, v0) * 1e-3, rtol=1e-14)
+
+
+def test_armature_adds_to_the_joint_diagonal():  # hybrid/articulated/mod.rs:243-247
+    m, l, arm = 5.0, 7.0, 3.5
+    d = models.rod_pendulum(m, l)
+    d._armature[0] = arm
+    o = oracle_of(d)
+    inertia = m * l * l / 3.0
+    torque_g = m * GRAVITY * l / 2.0
+    assert abs(o.dynamics([0.0], [0.0])[0] - torque_g / (inertia + arm)) < 1e-12
+    assert abs(o.free_velocity([0.0], [0.0], 0.01)[0] - 0.01 * torque_g / (inertia + arm)) < 1e-12
+    assert abs(o.free_velocity([0.0], [0.0], 0.01, gravity_enabled=False)[0]) < 1e-15
+    # the product's host code carries the armature through the flat description
+    from gorilla_physics_b200 import Mechanism
+    assert Mechanism.from_desc(d).desc().armature[0] == arm
