@@ -44,6 +44,11 @@ class GpMechanismDesc(C.Structure):
         ("hs_alpha", dp),
         ("hs_mu", dp),
         ("armature", dp),
+        ("n_spring_contacts", C.c_int32),
+        ("sc_body", ip),
+        ("sc_l_rest", dp),
+        ("sc_direction", dp),
+        ("sc_k", dp),
     ]
 
 
@@ -70,6 +75,8 @@ SYMBOLS = {
     "gp_mechanism_get_desc": (C.c_int, [vp, C.POINTER(GpMechanismDesc)]),
     "gp_mechanism_add_halfspace": (C.c_int, [vp, dp, dp, C.c_double, C.c_double]),
     "gp_mechanism_add_contact_point": (C.c_int, [vp, C.c_int32, dp, C.c_double]),
+    "gp_mechanism_add_spring_contact": (C.c_int, [vp, C.c_int32, C.c_double, dp, C.c_double]),
+    "gp_mechanism_n_spring_contacts": (C.c_int, [vp]),
     "gp_mechanism_supports": (C.c_int, [vp, ip]),
     "gp_mechanism_kernel_variant": (C.c_char_p, [vp]),
     "gp_model_create": (C.c_int, [C.c_char_p, dp, C.c_int, C.POINTER(vp)]),
@@ -87,6 +94,8 @@ SYMBOLS = {
     "gp_batch_set_state": (C.c_int, [vp, vp, vp]),
     "gp_batch_get_state": (C.c_int, [vp, vp, vp]),
     "gp_batch_set_tau": (C.c_int, [vp, vp]),
+    "gp_batch_set_spring_contact_state": (C.c_int, [vp, vp]),
+    "gp_batch_get_spring_contact_state": (C.c_int, [vp, vp]),
     "gp_batch_set_controller_state": (C.c_int, [vp, vp]),
     "gp_batch_get_controller_state": (C.c_int, [vp, vp]),
     "gp_batch_randomize": (C.c_int, [vp, C.c_uint64, C.POINTER(GpStateDist)]),

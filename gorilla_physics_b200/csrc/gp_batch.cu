@@ -23,6 +23,7 @@ struct gp_batch {
   bool tau_set = false;
   unsigned* status = nullptr;  // [ld]
   double* ctrl_state = nullptr;  // [2][ld] controller state (GP_CTRL_HOPPER_1D), allocated on first use
+  double* sc_state = nullptr;    // [n_sc*8][ld] spring-contact state (mechanisms with spring contacts)
   double* stage = nullptr;     // staging for AoS<->SoA and outputs
   size_t stage_bytes = 0;
   double* scratch = nullptr;   // SoA outputs of dynamics / energy
@@ -86,6 +87,18 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __rest
   __syncthreads();
   double* dst = aos + e0 * K;
   for (int idx = threadIdx.x; idx < ne * K; idx += blockDim.x) dst[idx] = tile[idx];
+}
+
+// unregistered spring contacts: MechanismState::new / SpringContact::new (contact.rs:83-94)
+__global__ void init_spring_state_kernel(double* st, long long ld, MechParams P) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ld) return;
+  for (int s = 0; s < P.n_sc; ++s) {
+    double* o = st + (long long)(kSpringState * s) * ld + e;
+    o[0] = 0.0; o[ld] = 0.0; o[2 * ld] = 0.0; o[3 * ld] = 0.0;
+    o[4 * ld] = P.sc_dir[s][0]; o[5 * ld] = P.sc_dir[s][1]; o[6 * ld] = P.sc_dir[s][2];
+    o[7 * ld] = P.sc_l_rest[s];
+  }
 }
 
 __global__ void init_state_kernel(double* q, double* v, long long n, long long ld, MechParams P) {
@@ -223,6 +236,7 @@ int check_batch(gp_batch* b, const char* fn) {
 
 // 0 = no contact work, 1 = exactly one halfspace, 2 = several (dynamics_core's CONTACT modes)
 int contact_mode(const gp_mechanism* m) {
+  if (m->n_sc() > 0) return 2;  // spring contacts live in the general mode of the run-time-topology kernels
   if (m->n_cp() == 0 || m->n_hs() == 0) return 0;
   return m->n_hs() == 1 ? 1 : 2;
 }
@@ -252,6 +266,11 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
     set_error("unknown integrator %d", integrator);
     return GP_ERR_INVALID;
   }
+  if (m->n_sc() > 0 && integrator != GP_SEMI_IMPLICIT_EULER) {
+    // reference simulate.rs:57-69: "Cannot use Runge-Kutta on state with spring contacts"
+    set_error("Cannot use Runge-Kutta on state with spring contacts");
+    return GP_ERR_INVALID;
+  }
   if (n_steps < 0 || !(dt == dt)) {
     set_error("bad n_steps / dt");
     return GP_ERR_INVALID;
@@ -261,6 +280,7 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   A.v = b->v + env0;
   A.tau = b->tau_set ? b->tau + env0 : nullptr;
   A.status = b->status + env0;
+  A.sc_state = b->sc_state ? b->sc_state + env0 : nullptr;
   A.n = n_sub;
   A.ld = b->ld;
   A.dt = dt;
@@ -432,6 +452,13 @@ int gp_batch_create(const gp_mechanism* mech, int64_t n_envs, int device, gp_bat
               cudaGetErrorString(cudaGetLastError()));
     return fail(GP_ERR_CUDA);
   }
+  if (mech->n_sc() > 0) {
+    if (cudaMalloc((void**)&b->sc_state, (size_t)kSpringState * mech->n_sc() * b->ld * sizeof(double)) != cudaSuccess) {
+      set_error("cudaMalloc failed for the spring-contact state");
+      return fail(GP_ERR_CUDA);
+    }
+    init_spring_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->sc_state, b->ld, mech->params);
+  }
   cudaMemsetAsync(b->tau, 0, nv * b->ld * sizeof(double), b->stream);
   cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream);
   init_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->q, b->v, b->n, b->ld, mech->params);
@@ -453,6 +480,7 @@ void gp_batch_destroy(gp_batch* b) {
   cudaFree(b->tau);
   cudaFree(b->status);
   cudaFree(b->ctrl_state);
+  cudaFree(b->sc_state);
   for (int s = 0; s < 2; ++s) {
     if (b->pipe_stream[s]) {
       cudaStreamSynchronize(b->pipe_stream[s]);
@@ -517,6 +545,35 @@ int gp_batch_set_tau(gp_batch* b, const double* tau_host) {
   return GP_OK;
 }
 
+int gp_batch_set_spring_contact_state(gp_batch* b, const double* state_host) {
+  int rc = check_batch(b, "gp_batch_set_spring_contact_state");
+  if (rc) return rc;
+  const int ns = b->mech->n_sc();
+  if (ns == 0) return GP_OK;
+  if (!state_host) {
+    init_spring_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->sc_state, b->ld, b->mech->params);
+    GP_CUDA(cudaGetLastError());
+    GP_CUDA(cudaStreamSynchronize(b->stream));
+    b->launches++;
+    return GP_OK;
+  }
+  if ((rc = to_device_soa(b, state_host, b->sc_state, kSpringState * ns))) return rc;
+  GP_CUDA(cudaStreamSynchronize(b->stream));
+  return GP_OK;
+}
+
+int gp_batch_get_spring_contact_state(gp_batch* b, double* state_host) {
+  int rc = check_batch(b, "gp_batch_get_spring_contact_state");
+  if (rc) return rc;
+  if (!state_host) {
+    set_error("gp_batch_get_spring_contact_state: null output");
+    return GP_ERR_INVALID;
+  }
+  const int ns = b->mech->n_sc();
+  if (ns == 0) return GP_OK;
+  return to_host_aos(b, b->sc_state, state_host, kSpringState * ns);
+}
+
 int gp_batch_set_controller_state(gp_batch* b, const double* state_host) {
   int rc = check_batch(b, "gp_batch_set_controller_state");
   if (rc) return rc;
@@ -579,6 +636,7 @@ int gp_batch_dynamics(gp_batch* b, double* vdot_host, double* contact_force_host
   A.n = b->n;
   A.ld = b->ld;
   A.gravity = kGravity;
+  A.sc_state = b->sc_state;  // dynamics_continuous advances the spring-contact state like the reference does
   GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if ((rc = to_host_aos(b, A.vdot, vdot_host, nv))) return rc;
@@ -639,6 +697,7 @@ int gp_batch_mass_matrix(gp_batch* b, double* mass_matrix_host, double* bias_hos
   A.n = b->n;
   A.ld = b->ld;
   A.gravity = kGravity;
+  A.sc_state = b->sc_state;  // dynamics_continuous advances the spring-contact state like the reference does
   GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if (mass_matrix_host) {

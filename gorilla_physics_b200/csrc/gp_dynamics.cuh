@@ -30,6 +30,7 @@ struct DynOut {
   double* bias;           // [n_v][ld], or nullptr
   long long ld;
   long long env;
+  double* sc_state;  // spring-contact state planes [(s*8 + k)*ld + env] of the batch, or nullptr
 };
 
 GP_D void gp_block_sync() {
@@ -182,10 +183,14 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
   double sn[NB], cs[NB];  // cached sin/cos of revolute joints
   SV vel[NB], acc[NB], frc[NB];
   constexpr int NHS = (CONTACT == 2) ? kMaxHS : 1;
-  constexpr bool WORLD = (CONTACT != 0) && DUMP;
+  // spring contacts (contact.rs:133-186) need world poses and carry state; only the run-time-topology
+  // kernels in the general contact mode implement them (gp_mechanism picks those kernels)
+  constexpr bool SPRINGS = !Topo::kStatic && CONTACT == 2;
+  constexpr bool WORLD = ((CONTACT != 0) && DUMP) || SPRINGS;
   V3 hn[CONTACT ? NB : 1][NHS];     // halfspace normals in body coordinates
   double ho[CONTACT ? NB : 1][NHS];  // plane offsets: signed distance of x is hn.x - ho
   M3 Rw[WORLD ? NB : 1];
+  V3 tw[SPRINGS ? NB : 1];
 
   // ------------------------------------------------------------------ pass 1: root -> leaf
   for_bodies<Topo>(P, [&](auto ii) {
@@ -264,6 +269,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
         if (p >= 0) Rwi = mul(Rw[p], E);
         else Rwi = E;
         Rw[i] = Rwi;
+        if constexpr (SPRINGS) tw[i] = (p >= 0) ? tw[p] + mul(Rw[p], r) : r;
       }
       // halfspaces in this body's coordinates: x_parent = E x + r  =>  n' = E^T n, o' = o - n.r
 #pragma unroll
@@ -301,6 +307,45 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
             o[0] = fw.x;
             o[out.ld] = fw.y;
             o[2 * out.ld] = fw.z;
+          }
+        }
+      }
+    }
+    if constexpr (SPRINGS) {
+      if (out.sc_state) {
+        for (int s = 0; s < P.n_sc; ++s) {
+          if (P.sc_body[s] != i) continue;
+          double* st = out.sc_state + (long long)(kSpringState * s) * out.ld + out.env;
+          const V3 body_location = tw[i];
+          const double reg = st[0];
+          const double l_rest = st[7 * out.ld];
+          if (reg == 0.0) {
+            // not registered: does the tip of the leg at rest length touch a halfspace?
+            const V3 dir = V3{st[4 * out.ld], st[5 * out.ld], st[6 * out.ld]};
+            const V3 tip = body_location + mul(Rw[i], dir) * l_rest;
+            for (int h = 0; h < P.n_hs; ++h) {
+              if (dot(tip - ld3(P.hs_point[h]), ld3(P.hs_normal[h])) <= 1e-8) {
+                st[0] = (double)(h + 1);
+                st[out.ld] = tip.x; st[2 * out.ld] = tip.y; st[3 * out.ld] = tip.z;
+                break;  // a spring contact registers to one halfspace at a time
+              }
+            }
+          } else {
+            const V3 d = V3{st[out.ld], st[2 * out.ld], st[3 * out.ld]} - body_location;
+            const double dist = sqrt(dot(d, d));
+            const V3 sdir = d * (1.0 / dist);
+            const int h = (int)reg - 1;
+            if (dot(sdir, ld3(P.hs_normal[h])) > 0.0) status |= GP_ENV_SPRING_INTO_HALFSPACE;
+            if (dist < l_rest) {
+              const double spring_force = -P.sc_k[s] * (dist - l_rest);
+              const V3 force_w = sdir * (-spring_force);  // acts at the body origin: no moment about it
+              f.l -= mulT(Rw[i], force_w);
+            } else {
+              // no longer under load: detach, the leg keeps the direction it left the surface with
+              const double inv = 1.0 / sqrt(dot(sdir, sdir));
+              st[0] = 0.0;
+              st[4 * out.ld] = sdir.x * inv; st[5 * out.ld] = sdir.y * inv; st[6 * out.ld] = sdir.z * inv;
+            }
           }
         }
       }

@@ -16,6 +16,8 @@ struct gp_mechanism {
   std::vector<int32_t> cp_body;
   std::vector<double> cp_location, cp_k;
   std::vector<double> hs_point, hs_normal, hs_alpha, hs_mu;
+  std::vector<int32_t> sc_body;
+  std::vector<double> sc_l_rest, sc_direction, sc_k;
 
   // derived: device constants + kernel variant; rebuilt after add_halfspace/add_contact_point
   gp::MechParams params;
@@ -24,6 +26,7 @@ struct gp_mechanism {
 
   int n_cp() const { return (int)cp_body.size(); }
   int n_hs() const { return (int)hs_alpha.size(); }
+  int n_sc() const { return (int)sc_body.size(); }
 };
 
 namespace gp {

@@ -286,7 +286,8 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     cstate[0] = A.ctrl_state[env];
     cstate[1] = A.ctrl_state[A.ld + env];
   }
-  DynOut none{nullptr, nullptr, nullptr, 0, 0};
+  // (clones of the last environment in a partially filled block must not touch its spring-contact state)
+  DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
 
 #pragma unroll 1
   for (int s = 0; s < A.n_steps; ++s) {
@@ -366,7 +367,7 @@ dynamics_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Dy
     v[k] = A.v[(long long)k * A.ld + env];
     tau[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
   }
-  DynOut out{A.contact_force, A.mass_matrix, A.bias, A.ld, env};
+  DynOut out{A.contact_force, A.mass_matrix, A.bias, A.ld, env, A.sc_state};
   if (A.contact_force)
     for (int c = 0; c < 3 * P.n_cp; ++c) A.contact_force[(long long)c * A.ld + env] = 0.0;
   unsigned status = A.no_contact ? dynamics_core<Topo, 0, true>(P, q, v, tau, vdot, out, A.gravity)

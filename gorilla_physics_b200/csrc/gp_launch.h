@@ -25,6 +25,7 @@ struct StepArgs {
   int controller;  // gp_controller
   double cp[4];    // controller parameters
   double* ctrl_state;  // [2][ld] per-environment controller state (GP_CTRL_HOPPER_1D) or nullptr
+  double* sc_state;    // [n_sc*8][ld] spring-contact state or nullptr
 };
 
 struct DynArgs {
@@ -40,6 +41,7 @@ struct DynArgs {
   double gravity;       // 9.81, or 0 with gravity disabled (free_velocity)
   double free_dt;       // != 0: vdot receives v + vdot * free_dt (Articulated::free_velocity)
   int no_contact;       // free_velocity ignores contact forces
+  double* sc_state;     // [n_sc*8][ld] spring-contact state or nullptr
 };
 
 struct EnergyArgs {

@@ -138,11 +138,20 @@ int finalize_mechanism(gp_mechanism* m) {
     P.hs_mu[h] = m->hs_mu[h];
   }
 
+  P.n_sc = m->n_sc();
+  for (int s = 0; s < m->n_sc(); ++s) {
+    P.sc_body[s] = m->sc_body[s] - 1;
+    P.sc_l_rest[s] = m->sc_l_rest[s];
+    P.sc_k[s] = m->sc_k[s];
+    for (int d = 0; d < 3; ++d) P.sc_dir[s][d] = m->sc_direction[3 * s + d];
+  }
+
   // kernel variant: first compiled specialisation whose signature matches, else generic
+  // (spring contacts are only implemented by the run-time-topology kernels)
   int nvar = 0;
   const KernelTable* const* vars = all_variants(&nvar);
   m->table = vars[nvar - 1];
-  for (int k = 0; k < nvar - 1; ++k)
+  for (int k = 0; k < nvar - 1 && m->n_sc() == 0; ++k)
     if (topo_matches(vars[k]->topo, td)) {
       m->table = vars[k];
       break;
@@ -257,6 +266,8 @@ int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
     m->hs_mu.push_back(d->hs_mu[h]);
   }
   int rc = finalize_mechanism(m);
+  for (int s = 0; rc == GP_OK && s < d->n_spring_contacts; ++s)
+    rc = gp_mechanism_add_spring_contact(m, d->sc_body[s], d->sc_l_rest[s], d->sc_direction + 3 * s, d->sc_k[s]);
   for (int c = 0; rc == GP_OK && c < d->n_contact_points; ++c)
     rc = gp_mechanism_add_contact_point(m, d->cp_body[c], d->cp_location + 3 * c, d->cp_k[c]);
   if (rc != GP_OK) {
@@ -300,6 +311,11 @@ int gp_mechanism_get_desc(const gp_mechanism* m, gp_mechanism_desc* o) {
   o->hs_alpha = m->hs_alpha.data();
   o->hs_mu = m->hs_mu.data();
   o->armature = m->armature.data();
+  o->n_spring_contacts = m->n_sc();
+  o->sc_body = m->sc_body.data();
+  o->sc_l_rest = m->sc_l_rest.data();
+  o->sc_direction = m->sc_direction.data();
+  o->sc_k = m->sc_k.data();
   return GP_OK;
 }
 
@@ -341,6 +357,33 @@ int gp_mechanism_add_contact_point(gp_mechanism* m, int32_t body, const double l
   m->cp_k.insert(m->cp_k.begin() + pos, k);
   return finalize_mechanism(m);
 }
+
+int gp_mechanism_add_spring_contact(gp_mechanism* m, int32_t body, double l_rest, const double direction[3], double k) {
+  if (!m || !direction) {
+    set_error("gp_mechanism_add_spring_contact: null argument");
+    return GP_ERR_INVALID;
+  }
+  if (body < 1 || body > m->nb) {
+    set_error("spring contact on unknown body %d", body);
+    return GP_ERR_INVALID;
+  }
+  const double n2 = direction[0] * direction[0] + direction[1] * direction[1] + direction[2] * direction[2];
+  if (!(std::fabs(n2 - 1.0) < 1e-9)) {
+    set_error("spring contact direction is not a unit vector");
+    return GP_ERR_INVALID;
+  }
+  if (m->n_sc() >= kMaxSC) {
+    set_error("more than %d spring contacts", kMaxSC);
+    return GP_ERR_LIMIT;
+  }
+  m->sc_body.push_back(body);
+  m->sc_l_rest.push_back(l_rest);
+  m->sc_direction.insert(m->sc_direction.end(), direction, direction + 3);
+  m->sc_k.push_back(k);
+  return finalize_mechanism(m);
+}
+
+int gp_mechanism_n_spring_contacts(const gp_mechanism* m) { return m ? m->n_sc() : 0; }
 
 int gp_mechanism_supports(const gp_mechanism* m, int32_t* out) {
   if (!m || !out) {

@@ -239,6 +239,18 @@ extern "C" int gp_model_create(const char* name_c, const double* p, int np, gp_m
     b.add(0, FLOAT, Z, iso_identity(), sphere_inertia(m, r));
     return b.create(out);
   }
+  if (name == "slip") {  // helpers.rs:308-337 build_SLIP; defaults: contact.rs:839-846 SLIP_hopping
+    if (np != 0 && np != 5) return bad_params(name_c, np, 5);
+    const double m = np ? p[0] : 0.54, r = np ? p[1] : 0.1, l_rest = np ? p[2] : 0.2,
+                 angle = np ? p[3] : 45.0 * PI / 180.0, k_spring = np ? p[4] : 500.0;
+    b.add(0, FLOAT, Z, iso_identity(), sphere_inertia(m, r));
+    int rc = b.create(out);
+    if (rc != GP_OK) return rc;
+    double dir[3] = {std::sin(angle), 0.0, -std::cos(angle)};
+    const double n = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    for (double& x : dir) x /= n;  // UnitVector3::new_normalize
+    return gp_mechanism_add_spring_contact(*out, 1, l_rest, dir, k_spring);
+  }
   if (name == "rimless_wheel") {  // helpers.rs:168-201; defaults: examples/rimless_wheel.rs:14-21
     if (np != 0 && np != 4) return bad_params(name_c, np, 4);
     const double m_body = np ? p[0] : 10.0, r_body = np ? p[1] : 5.0, l = np ? p[2] : 10.0;

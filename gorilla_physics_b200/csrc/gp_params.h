@@ -16,6 +16,8 @@ constexpr int kMaxNV = GP_MAX_NV;
 constexpr int kMaxNQ = 28;
 constexpr int kMaxCP = GP_MAX_CONTACT_POINTS;
 constexpr int kMaxHS = GP_MAX_HALFSPACES;
+constexpr int kMaxSC = GP_MAX_SPRING_CONTACTS;
+constexpr int kSpringState = 8;  // doubles of state per spring contact and environment
 
 constexpr double kGravity = 9.81;  // reference src/lib.rs:39
 
@@ -81,6 +83,13 @@ struct MechParams {
   double hs_off[kMaxHS];  // point . normal
   double hs_alpha[kMaxHS];
   double hs_mu[kMaxHS];
+
+  // ---- spring contacts (contact.rs:74-94); run-time-topology kernels only
+  int n_sc;
+  int sc_body[kMaxSC];  // 0-based
+  double sc_l_rest[kMaxSC];
+  double sc_k[kMaxSC];
+  double sc_dir[kMaxSC][3];
 };
 
 }  // namespace gp

@@ -75,6 +75,7 @@ class MechanismDesc:
         self._moment, self._cross, self._mass = [], [], []
         self._has_spring, self._spring_k, self._spring_l = [], [], []
         self._armature = []
+        self._sc_body, self._sc_l_rest, self._sc_dir, self._sc_k = [], [], [], []
         self._cp_body, self._cp_loc, self._cp_k = [], [], []
         self._hs_point, self._hs_normal, self._hs_alpha, self._hs_mu = [], [], [], []
         self.names: list[str] = []
@@ -112,6 +113,16 @@ class MechanismDesc:
         self._cp_body.append(int(body))
         self._cp_loc.append(np.asarray(location, dtype=np.float64).reshape(3))
         self._cp_k.append(float(k))
+
+    def add_spring_contact(self, body: int, l_rest: float, direction, k: float):
+        """SpringContact::new + add_spring_contact (src/contact.rs:83-94, mechanism.rs:394-401): an ideal spring
+        leg attached at the body origin, pointing along `direction` (unit, body frame)."""
+        if not (1 <= body <= len(self._parent)):
+            raise ValueError("spring contact frame does not match a body")
+        self._sc_body.append(int(body))
+        self._sc_l_rest.append(float(l_rest))
+        self._sc_dir.append(np.asarray(direction, dtype=np.float64).reshape(3))
+        self._sc_k.append(float(k))
 
     def add_halfspace(self, normal, distance: float, alpha: float = 0.9, mu: float = 0.5):
         """HalfSpace::new / new_with_params (src/collision/halfspace.rs:15-37): point = normal * distance."""
@@ -178,6 +189,26 @@ class MechanismDesc:
     def armature(self):
         """reflected drivetrain inertia on the joint's own diagonal of M (reference revolute.rs:29)"""
         return np.asarray(self._armature, dtype=np.float64)
+
+    @property
+    def n_spring_contacts(self):
+        return len(self._sc_body)
+
+    @property
+    def sc_body(self):
+        return np.asarray(self._sc_body, dtype=np.int32)
+
+    @property
+    def sc_l_rest(self):
+        return np.asarray(self._sc_l_rest, dtype=np.float64)
+
+    @property
+    def sc_direction(self):
+        return np.asarray(self._sc_dir, dtype=np.float64).reshape(-1, 3)
+
+    @property
+    def sc_k(self):
+        return np.asarray(self._sc_k, dtype=np.float64)
 
     @property
     def cp_body(self):

@@ -81,11 +81,14 @@ class Mechanism:
             "hs_point": _f64(desc.hs_point), "hs_normal": _f64(desc.hs_normal),
             "hs_alpha": _f64(desc.hs_alpha), "hs_mu": _f64(desc.hs_mu),
             "armature": _f64(desc.armature),
+            "sc_body": np.ascontiguousarray(desc.sc_body, dtype=np.int32),
+            "sc_l_rest": _f64(desc.sc_l_rest), "sc_direction": _f64(desc.sc_direction), "sc_k": _f64(desc.sc_k),
         }
         d = GpMechanismDesc()
         d.n_bodies = desc.n_bodies
         d.n_contact_points = desc.n_contact_points
         d.n_halfspaces = desc.n_halfspaces
+        d.n_spring_contacts = desc.n_spring_contacts
         for name, arr in keep.items():
             setattr(d, name, arr.ctypes.data_as(ip if arr.dtype == np.int32 else dp))
         h = C.c_void_p()
@@ -146,7 +149,8 @@ class Mechanism:
                 return np.zeros(0, dtype=dtype)
             return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
 
-        return MechanismDesc.from_arrays(
+        ns = d.n_spring_contacts
+        md = MechanismDesc.from_arrays(
             n_bodies=nb, parent=arr(d.parent, nb, np.int32), joint_type=arr(d.joint_type, nb, np.int32),
             axis=arr(d.axis, 3 * nb, np.float64), init_iso=arr(d.init_iso, 7 * nb, np.float64),
             moment=arr(d.moment, 9 * nb, np.float64), cross_part=arr(d.cross_part, 3 * nb, np.float64),
@@ -157,6 +161,10 @@ class Mechanism:
             n_halfspaces=nh, hs_point=arr(d.hs_point, 3 * nh, np.float64),
             hs_normal=arr(d.hs_normal, 3 * nh, np.float64), hs_alpha=arr(d.hs_alpha, nh, np.float64),
             hs_mu=arr(d.hs_mu, nh, np.float64), armature=arr(d.armature, nb, np.float64))
+        for k in range(ns):
+            md.add_spring_contact(int(d.sc_body[k]), float(d.sc_l_rest[k]),
+                                  [d.sc_direction[3 * k], d.sc_direction[3 * k + 1], d.sc_direction[3 * k + 2]], float(d.sc_k[k]))
+        return md
 
     def supports(self) -> np.ndarray:
         """supports[j-1][i-1] == 1 iff joint j supports body i (reference mechanism.rs:118-125)."""
@@ -171,6 +179,15 @@ class Mechanism:
         n = _f64(normal, (3,))
         point = _f64(n * distance)
         check(lib().gp_mechanism_add_halfspace(self._h, point.ctypes.data_as(dp), n.ctypes.data_as(dp), alpha, mu))
+
+    def add_spring_contact(self, body: int, l_rest: float, direction, k: float):
+        """SpringContact::new + add_spring_contact (reference contact.rs:83-94, mechanism.rs:394-401)"""
+        d = _f64(direction, (3,))
+        check(lib().gp_mechanism_add_spring_contact(self._h, body, l_rest, d.ctypes.data_as(dp), k))
+
+    @property
+    def n_spring_contacts(self):
+        return lib().gp_mechanism_n_spring_contacts(self._h)
 
     def add_contact_point(self, body: int, location, k: float = 50e3):
         loc = _f64(location, (3,))
@@ -263,6 +280,18 @@ class MechanismState:
         """None -> zero torques (reference simulate.rs:27-48)."""
         ta = None if tau is None else self._rows(tau, self.n_v)
         check(lib().gp_batch_set_tau(self._h, _ptr(ta)))
+
+    def spring_contact_state(self):
+        """[n_envs, NS, 8] = (registered halfspace, contact xyz, direction xyz, l_rest) per spring contact"""
+        ns = self.mechanism.n_spring_contacts
+        out = np.zeros((self.n_envs, ns, 8))
+        if ns:
+            check(lib().gp_batch_get_spring_contact_state(self._h, _ptr(out)))
+        return out
+
+    def set_spring_contact_state(self, state=None):
+        sa = None if state is None else np.ascontiguousarray(np.asarray(state, dtype=np.float64).reshape(self.n_envs, -1))
+        check(lib().gp_batch_set_spring_contact_state(self._h, _ptr(sa)))
 
     def set_controller_state(self, state=None):
         """(leg_length_setpoint, v_vertical_prev) per environment of Controller.HOPPER_1D; None resets to 0."""

@@ -55,6 +55,7 @@ extern "C" {
 #define GP_MAX_NV 24
 #define GP_MAX_CONTACT_POINTS 32
 #define GP_MAX_HALFSPACES 4
+#define GP_MAX_SPRING_CONTACTS 4
 
 enum gp_status_code {
   GP_OK = 0,
@@ -98,6 +99,7 @@ enum gp_controller {
 
 /* per-environment status bits (replace the reference's panics) */
 #define GP_ENV_NAN 1u         /* non-finite q, v or vdot */
+#define GP_ENV_SPRING_INTO_HALFSPACE 4u /* reference panic "Spring force is into the halfspace!" (contact.rs:161-163) */
 #define GP_ENV_NOT_SPD 2u     /* a pivot of the mass-matrix factorisation was <= 0 (dynamics.rs:267 "Failed to solve") */
 
 /*
@@ -130,6 +132,11 @@ typedef struct gp_mechanism_desc {
   const double* armature;    /* [NB] reflected drivetrain inertia added to the joint's own mass-matrix
                                 diagonal (revolute.rs:29; used by hybrid/articulated/mod.rs:247); may be
                                 NULL = zeros. Revolute / prismatic joints only. */
+  int32_t n_spring_contacts;   /* SpringContact (contact.rs:74-94): ideal spring legs acting against halfspaces */
+  const int32_t* sc_body;      /* [NS] body id (1-based) the leg is attached to (at the body-frame origin) */
+  const double* sc_l_rest;     /* [NS] rest length */
+  const double* sc_direction;  /* [NS][3] unit direction in the body frame */
+  const double* sc_k;          /* [NS] spring constant */
 } gp_mechanism_desc;
 
 typedef struct gp_mechanism gp_mechanism; /* opaque */
@@ -159,6 +166,11 @@ int gp_mechanism_get_desc(const gp_mechanism* mech, gp_mechanism_desc* out);
 int gp_mechanism_add_halfspace(gp_mechanism* mech, const double point[3], const double normal[3],
                                double alpha, double mu);
 int gp_mechanism_add_contact_point(gp_mechanism* mech, int32_t body, const double location[3], double k);
+/* add_spring_contact (mechanism.rs:394-401). Mechanisms with spring contacts run on the run-time-topology
+ * kernels; Runge-Kutta integrators are refused for them like in the reference (simulate.rs:57-69). */
+int gp_mechanism_add_spring_contact(gp_mechanism* mech, int32_t body, double l_rest, const double direction[3],
+                                    double k);
+int gp_mechanism_n_spring_contacts(const gp_mechanism* mech);
 /* supports[j-1] as a 0/1 row of length NB (mechanism.rs:118-125); out[(j-1)*NB + (i-1)] */
 int gp_mechanism_supports(const gp_mechanism* mech, int32_t* out);
 /* name of the device kernel specialisation this topology maps to ("generic" if none) */
@@ -176,6 +188,7 @@ const char* gp_mechanism_kernel_variant(const gp_mechanism* mech);
  *   "hopper_1d"         []  (examples/1D_hopper.rs:20-98 literals)
  *   "hopper_2d"         [12 params]                                       helpers.rs:203
  *   "quadruped"         []                                                helpers.rs:423
+ *   "slip"              [m, r, l_rest, angle, k_spring]                   helpers.rs:308
  *   "so101"             []                                                builders/mod.rs:252
  *   "navbot"            []                                                builders/navbot_builder.rs:682
  * Pass n_params == 0 to get the parameter values used by the reference's own
@@ -245,6 +258,12 @@ int gp_batch_mass_matrix(gp_batch* batch, double* mass_matrix_host, double* bias
  * (simulate.rs:103). Asynchronous: returns after enqueueing on the batch stream. */
 int gp_batch_step(gp_batch* batch, double dt, int integrator, int n_steps, int controller,
                   const double* ctrl_params, int n_ctrl_params);
+
+/* SpringContact state, which lives outside (q, v) (contact.rs:79-80): [n_envs][NS][8] =
+ * (registered halfspace: 0 none / h+1, contact x,y,z (world), direction x,y,z, l_rest).
+ * set: NULL restores the unregistered state of MechanismState::new. */
+int gp_batch_set_spring_contact_state(gp_batch* batch, const double* state_host);
+int gp_batch_get_spring_contact_state(gp_batch* batch, double* state_host);
 
 /* controller state of GP_CTRL_HOPPER_1D: [n_envs][2] = (leg_length_setpoint, v_vertical_prev).
  * set: NULL resets every environment to (0, 0), the values examples/1D_hopper.rs starts from. */

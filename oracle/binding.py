@@ -46,6 +46,11 @@ class _Desc(C.Structure):
         ("hs_alpha", _dp),
         ("hs_mu", _dp),
         ("armature", _dp),
+        ("n_spring_contacts", C.c_int32),
+        ("sc_body", _ip),
+        ("sc_l_rest", _dp),
+        ("sc_direction", _dp),
+        ("sc_k", _dp),
     ]
 
 
@@ -85,6 +90,11 @@ def lib() -> C.CDLL:
         L.gpo_batch_rollout.argtypes = [vp, _dp, _dp, _dp, C.c_int64, C.c_double, C.c_int64, C.c_int,
                                         C.c_int, _dp, C.c_int]
         L.gpo_batch_dynamics.argtypes = [vp, _dp, _dp, _dp, C.c_int64, _dp, _dp, C.c_int]
+        L.gpo_n_spring_contacts.argtypes = [vp]
+        L.gpo_spring_state_init.argtypes = [vp, _dp]
+        L.gpo_spring_state_init.restype = None
+        L.gpo_step_sc.argtypes = [vp, _dp, _dp, _dp, C.c_double, _dp]
+        L.gpo_dynamics_sc.argtypes = [vp, _dp, _dp, _dp, _dp, _dp]
         L.gpo_free_velocity.argtypes = [vp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]
         L.gpo_kinetic_energy.argtypes = [vp, _dp, _dp]
         L.gpo_kinetic_energy.restype = C.c_double
@@ -156,10 +166,17 @@ class OracleMechanism:
         keep["hs_mu"] = _f64(desc.hs_mu if nh else np.zeros(0), (nh,))
         arm = getattr(desc, "armature", None)
         keep["armature"] = _f64(arm if arm is not None and len(arm) == nb else np.zeros(nb), (nb,))
+        ns = int(getattr(desc, "n_spring_contacts", 0))
+        keep["sc_body"] = _i32(desc.sc_body if ns else np.zeros(0))
+        keep["sc_l_rest"] = _f64(desc.sc_l_rest if ns else np.zeros(0), (ns,))
+        keep["sc_direction"] = _f64(desc.sc_direction if ns else np.zeros((0, 3)), (ns, 3))
+        keep["sc_k"] = _f64(desc.sc_k if ns else np.zeros(0), (ns,))
         d = _Desc()
         d.n_bodies = nb
         d.n_contact_points = nc
         d.n_halfspaces = nh
+        d.n_spring_contacts = ns
+        self.n_sc = ns
         for name, arr in keep.items():
             ptr_t = _ip if arr.dtype == np.int32 else _dp
             setattr(d, name, arr.ctypes.data_as(ptr_t))
@@ -236,6 +253,21 @@ class OracleMechanism:
         """simulate() (simulate.rs:87): the step count follows the reference's f64 loop."""
         n = int(lib().gpo_simulate_step_count(final_time, dt))
         return self.rollout(q, v, dt, n, integrator, tau, controller, params, history)
+
+    def spring_state_init(self):
+        """unregistered SpringContact state, [n_sc, 8] = (registered halfspace, contact xyz, direction xyz, l_rest)"""
+        st = np.zeros((self.n_sc, 8))
+        lib().gpo_spring_state_init(self._h, _d(st))
+        return st
+
+    def step_sc(self, q, v, sc_state, dt, tau=None):
+        """step() with SemiImplicitEuler on a mechanism with spring contacts; returns (q, v, sc_state, flags)"""
+        q = _f64(q, (self.n_q,)).copy()
+        v = _f64(v, (self.n_v,)).copy()
+        st = _f64(sc_state, (self.n_sc, 8)).copy()
+        tau = None if tau is None else _f64(tau, (self.n_v,))
+        flags = lib().gpo_step_sc(self._h, _d(q), _d(v), _d(tau), dt, _d(st))
+        return q, v, st, flags
 
     def free_velocity(self, q, v, dt, tau=None, gravity_enabled=True):
         """Articulated::free_velocity (hybrid/articulated/mod.rs:124-197)"""

@@ -171,7 +171,17 @@ struct Body {
 
 }  // namespace
 
+namespace {
+struct SpringContactDef {  // contact.rs:74-81
+  int body;  // 1-based
+  double l_rest;
+  V3 direction;
+  double k;
+};
+}  // namespace
+
 struct gpo_mechanism {
+  std::vector<SpringContactDef> spring_contacts;
   int nb, n_q, n_v, n_cp;
   std::vector<Body> bodies;  // bodies[i-1] = body i
   std::vector<HalfSpace> halfspaces;
@@ -207,6 +217,8 @@ struct Work {
   SV wrench[GPO_MAX_BODIES + 1];
   double M[GPO_MAX_NV * GPO_MAX_NV];
   double c[GPO_MAX_NV];
+  double* sc_state = nullptr;  // spring contact state of this environment (8 doubles each), or null
+  int sc_flags = 0;
 };
 
 // joint/revolute.rs:97-102, prismatic.rs:82-87, floating.rs:26-31 + pose.rs:30-33, fixed.rs
@@ -445,6 +457,44 @@ void contact_dynamics(const gpo_mechanism* m, Work& w, double* contact_forces) {
       if (contact_forces) {
         double* o = contact_forces + 3 * (b.cp_index0 + (int)c);
         o[0] = total.x; o[1] = total.y; o[2] = total.z;
+      }
+    }
+    // spring contacts with halfspaces (contact.rs:133-186); state lives in w.sc_state
+    if (w.sc_state) {
+      for (size_t s = 0; s < m->spring_contacts.size(); ++s) {
+        const SpringContactDef& sc = m->spring_contacts[s];
+        if (sc.body != i) continue;
+        double* st = w.sc_state + 8 * s;
+        V3 body_location = trans;
+        if (st[0] == 0.0) {
+          V3 direction{st[4], st[5], st[6]};
+          V3 spring_direction = rot * direction;
+          V3 contact_location = body_location + spring_direction * st[7];
+          for (size_t h = 0; h < m->halfspaces.size(); ++h) {
+            const HalfSpace& hs = m->halfspaces[h];
+            if (!(dot(contact_location - hs.point, hs.normal) <= 1e-8)) continue;
+            st[0] = (double)(h + 1);
+            st[1] = contact_location.x; st[2] = contact_location.y; st[3] = contact_location.z;
+            break;
+          }
+        } else {
+          V3 contact_location{st[1], st[2], st[3]};
+          V3 dvec = contact_location - body_location;
+          V3 spring_direction = dvec / norm(dvec);
+          const HalfSpace& hs = m->halfspaces[(size_t)st[0] - 1];
+          if (dot(spring_direction, hs.normal) > 0.0) w.sc_flags |= 4;  // panic!("Spring force is into the halfspace!")
+          double direction_distance = norm(dvec);
+          if (direction_distance < st[7]) {
+            double spring_force = -sc.k * (direction_distance - st[7]);
+            V3 force = -spring_direction * spring_force;
+            wrench.ang = wrench.ang + cross(body_location, force);
+            wrench.lin = wrench.lin + force;
+          } else {
+            st[0] = 0.0;
+            V3 nd = spring_direction / norm(spring_direction);
+            st[4] = nd.x; st[5] = nd.y; st[6] = nd.z;
+          }
+        }
       }
     }
     w.contact_wrench[i] = wrench;
@@ -880,6 +930,12 @@ int gpo_mechanism_create(const gpo_mechanism_desc* d, gpo_mechanism** out) {
   int idx = 0;
   for (Body& b : m->bodies) { b.cp_index0 = idx; idx += (int)b.contact_points.size(); }
   m->n_cp = idx;
+  for (int s = 0; s < d->n_spring_contacts; ++s) {
+    if (d->sc_body[s] < 1 || d->sc_body[s] > m->nb) { delete m; return 1; }
+    m->spring_contacts.push_back({d->sc_body[s], d->sc_l_rest[s],
+                                  {d->sc_direction[3 * s], d->sc_direction[3 * s + 1], d->sc_direction[3 * s + 2]},
+                                  d->sc_k[s]});
+  }
   for (int h = 0; h < d->n_halfspaces; ++h)
     m->halfspaces.push_back({{d->hs_point[3 * h], d->hs_point[3 * h + 1], d->hs_point[3 * h + 2]},
                              {d->hs_normal[3 * h], d->hs_normal[3 * h + 1], d->hs_normal[3 * h + 2]},
@@ -914,6 +970,33 @@ int gpo_dynamics(const gpo_mechanism* m, const double* q, const double* v, const
   if (mass_matrix_out) std::memcpy(mass_matrix_out, w.M, sizeof(double) * m->n_v * m->n_v);
   if (bias) std::memcpy(bias, w.c, sizeof(double) * m->n_v);
   return rc;
+}
+
+int gpo_n_spring_contacts(const gpo_mechanism* m) { return (int)m->spring_contacts.size(); }
+
+void gpo_spring_state_init(const gpo_mechanism* m, double* st) {
+  for (size_t s = 0; s < m->spring_contacts.size(); ++s) {
+    const SpringContactDef& sc = m->spring_contacts[s];
+    double* o = st + 8 * s;
+    o[0] = 0.0; o[1] = o[2] = o[3] = 0.0;
+    o[4] = sc.direction.x; o[5] = sc.direction.y; o[6] = sc.direction.z;
+    o[7] = sc.l_rest;
+  }
+}
+
+int gpo_step_sc(const gpo_mechanism* m, double* q, double* v, const double* tau, double dt, double* sc_state) {
+  Work w;
+  w.sc_state = sc_state;
+  int rc = step_impl(m, q, v, tau, dt, 0, w);
+  return rc | w.sc_flags;
+}
+
+int gpo_dynamics_sc(const gpo_mechanism* m, const double* q, const double* v, const double* tau, double* vdot,
+                    double* sc_state) {
+  Work w;
+  w.sc_state = sc_state;
+  int rc = dynamics_continuous(m, q, v, tau, vdot, nullptr, w);
+  return rc | w.sc_flags;
 }
 
 int gpo_step(const gpo_mechanism* m, double* q, double* v, const double* tau, double dt, int integrator) {

@@ -58,6 +58,11 @@ typedef struct gpo_mechanism_desc {
   const double* hs_alpha;
   const double* hs_mu;
   const double* armature; /* [NB] or NULL; hybrid/articulated/mod.rs:247 semantics */
+  int32_t n_spring_contacts;  /* SpringContact, contact.rs:74-94 */
+  const int32_t* sc_body;     /* [NS] 1-based */
+  const double* sc_l_rest;    /* [NS] */
+  const double* sc_direction; /* [NS][3] unit, body frame */
+  const double* sc_k;         /* [NS] */
 } gpo_mechanism_desc;
 
 typedef struct gpo_mechanism gpo_mechanism;
@@ -100,6 +105,17 @@ int gpo_batch_rollout(const gpo_mechanism* m, double* q, double* v, const double
                       const double* params, int n_threads);
 int gpo_batch_dynamics(const gpo_mechanism* m, const double* q, const double* v, const double* tau,
                        int64_t n_envs, double* vdot, double* contact_forces, int n_threads);
+
+/* SpringContact (contact.rs:74-94, :133-186) carries state outside (q, v): per spring contact 8 doubles
+ * [registered halfspace (0 = none, h+1), contact x,y,z, direction x,y,z, l_rest]. init writes the
+ * unregistered state of MechanismState::new; step_sc is step() with SemiImplicitEuler (the reference
+ * refuses Runge-Kutta with spring contacts, simulate.rs:57-69) and updates sc_state in place.
+ * Returns bit 4 when the reference would panic with "Spring force is into the halfspace!". */
+int gpo_n_spring_contacts(const gpo_mechanism* m);
+void gpo_spring_state_init(const gpo_mechanism* m, double* sc_state);
+int gpo_step_sc(const gpo_mechanism* m, double* q, double* v, const double* tau, double dt, double* sc_state);
+int gpo_dynamics_sc(const gpo_mechanism* m, const double* q, const double* v, const double* tau, double* vdot,
+                    double* sc_state);
 
 /* Articulated::free_velocity (hybrid/articulated/mod.rs:124-197) with update_mass_matrix (:199-269):
  * world-frame Coriolis commutator, armature on the diagonal, Cholesky solve, no contact. */

@@ -466,3 +466,34 @@ def test_armature_adds_to_the_joint_diagonal():  # hybrid/articulated/mod.rs:243
     # the product's host code carries the armature through the flat description
     from gorilla_physics_b200 import Mechanism
     assert Mechanism.from_desc(d).desc().armature[0] == arm
+
+
+def _slip_direction():
+    a = math.radians(45.0)
+    d = np.array([math.sin(a), 0.0, -math.cos(a)])
+    return d / np.linalg.norm(d)
+
+
+def test_SLIP_hopping():  # contact.rs:836-903: SpringContact (stateful leg), SemiImplicitEuler, 3 s
+    m = Mechanism.from_model("slip")  # helpers.rs:308-337, SLIP_hopping's parameters
+    m.add_halfspace((0, 0, 1), -0.3)
+    o = oracle_of(m)
+    direction, l_rest = _slip_direction(), 0.2
+    q, v = pose_q(), np.array([0, 0, 0, 5.0, 0, 0])
+    st = o.spring_state_init()
+    e0 = o.kinetic_energy(q, v) + o.gravitational_energy(q)
+    dt = 1.0 / 2000.0
+    vz_prev, energies, hs = 0.0, [], []
+    for _ in range(int(3.0 / dt)):
+        q, v, st, flags = o.step_sc(q, v, st, dt)
+        assert flags == 0  # never "Spring force is into the halfspace!"
+        vz = v[5]
+        if vz_prev > 0.0 and vz <= 0.0:  # apex: swing the leg back to the front angle (the test does this by hand)
+            energies.append(o.kinetic_energy(q, v) + o.gravitational_energy(q))
+            hs.append(q[6])
+            st[0, 4:7] = direction
+            st[0, 7] = l_rest
+        vz_prev = vz
+    assert len(energies) > 0
+    assert max(abs(e - e0) for e in energies) < 1e-2
+    assert abs(hs[-3] - hs[-2]) < 1e-3 and abs(hs[-2] - hs[-1]) < 1e-3

@@ -492,3 +492,59 @@ def test_free_velocity_and_armature():
     vf = st.free_velocity(1.0 / 3000.0)
     ref = np.stack([orc.free_velocity(q[e], v[e], 1.0 / 3000.0) for e in range(64)])
     assert rel_err(vf, ref) < TOL_DYN
+
+
+def test_spring_contact_slip_matches_oracle():
+    """SpringContact (reference contact.rs:74-94, :133-186): the stateful SLIP leg. Many hoppers with
+    different launch speeds, stepped on the GPU and in the oracle, the apex logic of SLIP_hopping
+    (contact.rs:878-889) applied on the host to both; state AND spring-contact state must agree."""
+    mech = Mechanism.from_model("slip")
+    mech.add_halfspace((0, 0, 1), -0.3)
+    assert mech.kernel_variant == "generic" and mech.n_spring_contacts == 1
+    orc = oracle_of(mech)
+    a = math.radians(45.0)
+    direction = np.array([math.sin(a), 0.0, -math.cos(a)])
+    direction /= np.linalg.norm(direction)
+    n = 48
+    rng = np.random.default_rng(3)
+    q = np.tile(np.array([0, 0, 0, 1.0, 0, 0, 0]), (n, 1))
+    v = np.zeros((n, 6))
+    v[:, 3] = rng.uniform(3.0, 6.0, size=n)
+    v[:, 5] = rng.uniform(-0.5, 0.5, size=n)
+    dt = 1.0 / 2000.0
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    sc = st.spring_contact_state()
+    np.testing.assert_array_equal(sc[:, 0], np.tile(orc.spring_state_init()[0], (n, 1)))
+    qo, vo = q.copy(), v.copy()
+    sco = np.stack([orc.spring_state_init() for _ in range(n)])
+    vz_prev = v[:, 5].copy()
+    registered_seen = detached_seen = False
+    for step in range(1200):
+        st.step(dt)
+        qg, vg = st.state()
+        scg = st.spring_contact_state()
+        for e in range(n):
+            qo[e], vo[e], sco[e], flags = orc.step_sc(qo[e], vo[e], sco[e], dt)
+            assert flags == 0
+        registered_seen |= bool((sco[:, 0, 0] != 0).any())
+        apex = (vz_prev > 0.0) & (vo[:, 5] <= 0.0)
+        if apex.any():
+            detached_seen = True
+            sco[apex, 0, 4:7] = direction
+            sco[apex, 0, 7] = 0.2
+            scg[apex, 0, 4:7] = direction
+            scg[apex, 0, 7] = 0.2
+            st.set_spring_contact_state(scg)
+        vz_prev = vo[:, 5].copy()
+        if step % 100 == 99 or step < 3:
+            assert rel_err(qg, qo) < 1e-9 and rel_err(vg, vo) < 1e-8, step
+            np.testing.assert_array_equal(scg[:, 0, 0], sco[:, 0, 0])  # same registration events
+            np.testing.assert_allclose(scg, sco, rtol=0, atol=1e-9)
+    assert registered_seen and detached_seen
+    assert not st.status().any()
+    # Runge-Kutta is refused with spring contacts (reference simulate.rs:57-69)
+    with pytest.raises(Exception):
+        st.step(dt, integrator=Integrator.RungeKutta4)
+    st.set_spring_contact_state(None)
+    np.testing.assert_array_equal(st.spring_contact_state()[:, 0], np.tile(orc.spring_state_init()[0], (n, 1)))

@@ -34,7 +34,7 @@ extern "C" int gpdbg_dynamics(const gp_mechanism* m, const double* q, const doub
   double qq[DynTopo::NQ] = {0}, vv[DynTopo::NV] = {0}, tt[DynTopo::NV] = {0}, vd[DynTopo::NV] = {0};
   for (int k = 0; k < P.n_q; ++k) qq[k] = q[k];
   for (int k = 0; k < P.n_v; ++k) { vv[k] = v[k]; tt[k] = tau ? tau[k] : 0.0; }
-  DynOut out{cf, H, bias, 1, 0};
+  DynOut out{cf, H, bias, 1, 0, nullptr};
   unsigned st = dynamics_core<DynTopo, 2, true>(P, qq, vv, tt, vd, out);
   for (int k = 0; k < P.n_v; ++k) vdot[k] = vd[k];
   return (int)st;
