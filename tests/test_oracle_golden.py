@@ -497,3 +497,35 @@ def test_SLIP_hopping():  # contact.rs:836-903: SpringContact (stateful leg), Se
     assert len(energies) > 0
     assert max(abs(e - e0) for e in energies) < 1e-2
     assert abs(hs[-3] - hs[-2]) < 1e-3 and abs(hs[-2] - hs[-1]) < 1e-3
+
+
+def test_quadruped_inverse_kinematics():  # control/quadruped_control.rs:318-413
+    from tests.controllers_ref import QuadrupedTrottingController as C
+    np.testing.assert_allclose(C.inverse_kinematics([np.array([0.0, 0.0, 0.0])], 1.0)[0], [-PI / 2.0, PI], atol=1e-5)
+    np.testing.assert_allclose(C.inverse_kinematics([np.array([0.0, 0.0, -1.0])], 1.0)[0], [0.0, 0.0], atol=1e-5)
+    for x_t in (-0.0, -0.1, 0.1):
+        t1, t2 = C.inverse_kinematics([np.array([x_t, 0.0, -0.5])], 1.0)[0]
+        x = -0.5 * math.sin(-t1) + 0.5 * math.sin(t2 + t1)
+        z = -0.5 * math.cos(-t1) - 0.5 * math.cos(t2 + t1)
+        assert abs(x - x_t) < 1e-5 and abs(z + 0.5) < 1e-5
+
+
+def test_quadruped_trot_to_position():  # control/quadruped_control.rs:415-478
+    """14-dof floating base + 12 contact points, SemiImplicitEuler, dt = 1/3000, 3 s: the config-5 twin
+    the reference actually tests. The gait controller is restated test-side (tests/controllers_ref.py)."""
+    from tests.controllers_ref import QuadrupedTrottingController, quadruped_initial_state
+    dt, target_x = 1.0 / (60.0 * 50.0), -0.2
+    o = oracle_of(models.quadruped_on_ground())
+    q, v = quadruped_initial_state()
+    ctrl = QuadrupedTrottingController(dt, target_x, -0.8)
+    for _ in range(int(3.0 / dt)):
+        tau = ctrl.control(q, v)
+        q, v = o.step(q, v, tau, dt, SIE)
+    assert abs(q[4] - target_x) < 1e-1
+    # body velocity expressed in the world-aligned frame of the test: rotation.inverse() * v_lin
+    # (the reference applies the inverse rotation to the body-frame velocity; restated as written)
+    x, y, z, w = q[0:4]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    assert abs((R.T @ v[3:6])[0]) < 3e-1

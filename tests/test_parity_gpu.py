@@ -548,3 +548,42 @@ def test_spring_contact_slip_matches_oracle():
         st.step(dt, integrator=Integrator.RungeKutta4)
     st.set_spring_contact_state(None)
     np.testing.assert_array_equal(st.spring_contact_state()[:, 0], np.tile(orc.spring_state_init()[0], (n, 1)))
+
+
+def test_quadruped_trot_to_position_on_the_gpu():
+    """The reference's own end-to-end test of the 14-dof + 12-contact-point model
+    (control/quadruped_control.rs:415-478), with the host closure path: one controller per
+    environment computes torques on the host, the GPU does step(). Same acceptance as the reference
+    (|x - target| < 0.1, |v_x| < 0.3 after 3 s), for several targets at once, and the first part of the
+    trajectory against the oracle driven by the same controller."""
+    from tests.controllers_ref import QuadrupedTrottingController, quadruped_initial_state
+    mech = models.quadruped_on_ground()
+    assert mech.kernel_variant.startswith("quadruped")
+    orc = oracle_of(mech)
+    dt = 1.0 / (60.0 * 50.0)
+    targets = [-0.2, -0.6, -1.5, -1.8]
+    n = len(targets)
+    q0, v0 = quadruped_initial_state()
+    st = MechanismState(mech, n)
+    st.update(np.tile(q0, (n, 1)), np.tile(v0, (n, 1)))
+    ctrls = [QuadrupedTrottingController(dt, t, -0.8) for t in targets]
+    ctrl_o = QuadrupedTrottingController(dt, targets[0], -0.8)
+    qo, vo = q0.copy(), v0.copy()
+    q, v = st.state()
+    check_until = 600
+    for step in range(int(3.0 / dt)):
+        tau = np.stack([c.control(q[e], v[e]) for e, c in enumerate(ctrls)])
+        st.step(dt, tau=tau)
+        q, v = st.state()
+        if step < check_until:
+            qo, vo = orc.step(qo, vo, ctrl_o.control(qo, vo), dt, 0)
+            if step in (0, 9, 99, check_until - 1):
+                assert np.abs(q[0] - qo).max() < 1e-9 * (step + 1) and np.abs(v[0] - vo).max() < 1e-8 * (step + 1), step
+    assert not st.status().any()
+    for e, t in enumerate(targets):
+        assert abs(q[e, 4] - t) < 1e-1, (e, q[e, 4])
+        x, y, z, w = q[e, 0:4]
+        Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                       [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                       [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        assert abs((Rq.T @ v[e, 3:6])[0]) < 3e-1
