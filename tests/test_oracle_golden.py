@@ -529,3 +529,96 @@ def test_quadruped_trot_to_position():  # control/quadruped_control.rs:415-478
                   [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
                   [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
     assert abs((R.T @ v[3:6])[0]) < 3e-1
+
+
+def _pitch(quat_xyzw):
+    """nalgebra Rotation3::euler_angles().1 = -asin(R[2][0]) (SURVEY.md §8c, nalgebra 0.33.2)"""
+    x, y, z, w = quat_xyzw
+    return -math.asin(2.0 * (x * z - w * y))
+
+
+def _hopper_test_loop(o, q, v, dt, num_steps, hip_torque):
+    """Shared frame of control/hopper_control.rs:169-237 / :272-383: mechanical stop on the leg spring,
+    hip torque from `hip_torque(s, q, v, poses, twists)`, step, re-arm the spring at the bottom point."""
+    prev_body_vz = 0.0
+    for s in range(num_steps):
+        tau = np.zeros(8)
+        spring_q, spring_v = q[7], v[6]
+        if spring_q > 0.0:
+            tau[6] = -1e5 * (spring_q - 0.0) - 125.0 * spring_v  # mechanical_stop, energy_control.rs:20-22
+        poses, twists = o.poses(q), o.body_twists(q, v)
+        tau[7] = hip_torque(s, q, v, poses, twists)
+        q, v = o.step(q, v, tau, dt, SIE)
+        poses, twists = o.poses(q), o.body_twists(q, v)
+        body_vel = twists[2, 3:6] + np.cross(twists[2, 0:3], poses[2, 4:7])
+        if prev_body_vz < 0.0 and body_vel[2] >= 0.0:
+            q[7] = -0.42
+        prev_body_vz = body_vel[2]
+    return q, v, poses, twists, body_vel
+
+
+def test_hopper_foot_placement_position_control():  # control/hopper_control.rs:141-241 (SemiImplicitEuler, 10 s)
+    m_foot, m_hip, m_body, l_foot_to_hip = 1.0, 0.5, 9.5, 1.0
+    mech = Mechanism.from_model("hopper", [m_foot, 1.0, m_hip, 1.0, m_body, 4.0, l_foot_to_hip])
+    mech.add_halfspace((0, 0, 1), 0.0, alpha=1.0, mu=1.0)
+    o = oracle_of(mech)
+    q, v = mech.desc().zero_state()
+    q[4:7] = (0.5, 0.0, 0.5)
+
+    def hip_torque(s, q, v, poses, twists):
+        body_vx = (twists[2, 3:6] + np.cross(twists[2, 0:3], poses[2, 4:7]))[0]
+        body_x = poses[2, 4]
+        leg_angle = _pitch(poses[0, 0:4])
+        leg_angular_v = twists[0, 1]
+        vx_d = -math.copysign(1.0, body_x) * min(abs(body_x) * 10.0, 1.0)
+        x_err = -0.1 * (vx_d - body_vx)
+        target = -math.asin((m_body + m_hip + m_foot) * x_err / ((l_foot_to_hip + q[7]) * (m_body + m_hip)))
+        return 2000.0 * (leg_angle - target) + 200.0 * leg_angular_v
+
+    q, v, poses, *_ = _hopper_test_loop(o, q, v, 1e-3, int(10.0 / 1e-3), hip_torque)
+    assert abs(poses[2, 4]) < 0.05
+
+
+def test_hopper_servo_attitude_position_control():  # control/hopper_control.rs:243-395 (SemiImplicitEuler, 20 s)
+    m_foot, m_hip, m_body, l_foot_to_hip = 1.0, 0.5, 9.5, 1.0
+    mech = Mechanism.from_model("hopper", [m_foot, 1.0, m_hip, 1.0, m_body, 1.0, l_foot_to_hip])
+    mech.add_halfspace((0, 0, 1), 0.0, alpha=1.0, mu=2.0)
+    o = oracle_of(mech)
+    q, v = mech.desc().zero_state()
+    q[4:7] = (-3.0, 0.0, 0.5)
+    dt = 5e-4
+    mem = {"prev_foot_z": 0.0, "ground_hit_time": 0.0, "contact_duration": 0.0}
+
+    def hip_torque(s, q, v, poses, twists):
+        foot_z = poses[0, 6]
+        t = s * dt
+        if mem["prev_foot_z"] >= 0.0 and foot_z < 0.0:
+            mem["ground_hit_time"] = t
+        if mem["prev_foot_z"] < 0.0 and foot_z >= 0.0:
+            mem["contact_duration"] = t - mem["ground_hit_time"]
+        mem["prev_foot_z"] = foot_z
+        if foot_z >= 0.0:  # flight: foot placement
+            body_vx = (twists[2, 3:6] + np.cross(twists[2, 0:3], poses[2, 4:7]))[0]
+            body_x = poses[2, 4]
+            leg_angle = _pitch(poses[0, 0:4])
+            leg_angular_v = twists[0, 1]
+            w = l_foot_to_hip + q[7]
+            dvx_max = 0.2
+            vx_desired = -math.copysign(1.0, body_x) * min(abs(body_x) * 0.1, 0.2)
+            dvx = vx_desired - body_vx
+            x_err = -0.25 * math.copysign(1.0, dvx) * min(abs(dvx), dvx_max)
+            if vx_desired < body_vx - dvx_max:
+                vs = body_vx - dvx_max
+            elif vx_desired > body_vx + dvx_max:
+                vs = body_vx + dvx_max
+            else:
+                vs = vx_desired
+            x_stance = vs * (0.4 if mem["contact_duration"] == 0.0 else mem["contact_duration"])
+            x_touchdown = (m_body + m_hip + m_foot) * x_err / (m_body + m_hip) + x_stance / 2.0
+            return 2000.0 * (leg_angle - (-math.asin(x_touchdown / w))) + 200.0 * leg_angular_v
+        body_angle = _pitch(poses[2, 0:4])  # stance: servo the body attitude
+        return 1200.0 * -body_angle + 60.0 * -twists[2, 1]
+
+    q, v, poses, twists, body_vel = _hopper_test_loop(o, q, v, dt, int(20.0 / dt), hip_torque)
+    assert abs(poses[2, 4]) < 1e-1 and abs(_pitch(poses[2, 0:4])) < 1e-1
+    assert abs(body_vel[0]) < 1e-1 and abs(twists[2, 1]) < 1e-1
