@@ -130,38 +130,6 @@ GP_D V3 contact_force(double z, V3 n, V3 vel, double k, double alpha, double mu)
   return f;
 }
 
-// ---- CRBA: carry F = Ic S (one column, dof row `row`) from body i towards the root, filling
-// H[row][dofs of each supporting joint]. E, r are body i's joint transform (already built).
-template <class Topo>
-GP_D void mass_matrix_walk(const MechParams& P, int i, int row, SV F, const M3& E, V3 r, const double* q,
-                           const double* sn, const double* cs, double* H) {
-  constexpr int U = Topo::kUnroll;
-  const int depth = Topo::depth(P, i);
-  int cur = i;
-#pragma unroll U
-  for (int k = 1; k < Topo::lim(depth, Topo::NB); ++k) {
-    if (k < depth) {
-      if (k == 1) {
-        F = force_to_parent(E, r, F);
-      } else {
-        M3 Ec;
-        V3 rc;
-        joint_xform<Topo>(P, cur, q, sn[cur], cs[cur], Ec, rc);
-        F = force_to_parent(Ec, rc, F);
-      }
-      cur = Topo::anc_at(P, i, k);
-      const int jc = Topo::jtype(P, cur);
-      const int vc = Topo::voff(P, cur);
-      if (jc == JRevolute) H[hidx(row, vc)] = axis_dot<Topo>(P, cur, F.a);
-      else if (jc == JPrismatic) H[hidx(row, vc)] = axis_dot<Topo>(P, cur, F.l);
-      else if (jc == JFloating) {
-        H[hidx(row, vc)] = F.a.x; H[hidx(row, vc + 1)] = F.a.y; H[hidx(row, vc + 2)] = F.a.z;
-        H[hidx(row, vc + 3)] = F.l.x; H[hidx(row, vc + 4)] = F.l.y; H[hidx(row, vc + 5)] = F.l.z;
-      }
-    }
-  }
-}
-
 // ---- dynamics_continuous for one environment ------------------------------------------------
 // q[NQ], v[NV], tau[NV] (caller passes zeros for "no torque"); writes vdot[NV]; returns status.
 // CONTACT: 0 = no contact points / halfspaces, 1 = exactly one halfspace, 2 = up to kMaxHS.
@@ -359,6 +327,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
   double H[NV * (NV + 1) / 2];
   double b[NV];
   RBI Iacc[NB];  // children's composite inertias expressed in this body's frame
+  SV Fd[NV];     // mass-matrix columns on their way to the root (see below)
   if (!Topo::kStatic) {
     for (int k = 0; k < nv * (nv + 1) / 2; ++k) H[k] = 0.0;
   }
@@ -404,20 +373,23 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     }
 
     if constexpr (SYNC >= 2) gp_block_sync();
-    // mass-matrix rows of joint i: F = Ic S_i, H_ij = S_j^T F for every joint j supporting i
-    // (reference mechanism.rs:637-696, momentum.rs:17-47)
+    // mass-matrix columns: F_d = Ic S_d of every dof d travels towards the root WITH this body loop
+    // (Fd[d] is expressed in the coordinates of the body the loop has reached), so each joint
+    // transform is built once per body and applied to all the vectors that cross it;
+    // H_dj = S_j^T F_d for every joint j supporting d (reference mechanism.rs:637-696, momentum.rs:17-47)
+    const bool carry = (p >= 0) && !Topo::anchored(P, p);  // some joint above still has dofs
     if (jt == JRevolute) {
       SV F;
       F.a = sym_mul_axis<Topo>(P, i, Ic.J);
       F.l = cross_axis<Topo>(P, i, Ic.c, -1.0);  // m*0 - c x a
       H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a) + P.armature[i];  // hybrid/articulated/mod.rs:247
-      mass_matrix_walk<Topo>(P, i, vo, F, E, r, q, sn, cs, H);
+      Fd[vo] = F;
     } else if (jt == JPrismatic) {
       SV F;
       F.a = cross_axis<Topo>(P, i, Ic.c, 1.0);  // J*0 + c x a
       F.l = axis_scaled<Topo>(P, i, Ic.m);
       H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.l) + P.armature[i];
-      mass_matrix_walk<Topo>(P, i, vo, F, E, r, q, sn, cs, H);
+      Fd[vo] = F;
     } else if (jt == JFloating) {
       // S = identity: the F columns are the columns of the 6x6 composite inertia
       //   [ J   c^ ]      c^ = skew(c)
@@ -440,9 +412,25 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
 #pragma unroll
         for (int c2 = 0; c2 < 6; ++c2)
           if (c2 <= col) H[hidx(vo + col, vo + c2)] = Fv[c2];
-        if (p >= 0) mass_matrix_walk<Topo>(P, i, vo + col, F, E, r, q, sn, cs, H);
+        if (carry) Fd[vo + col] = F;
       }
     }
+    const int nvi = (jt == JFloating) ? 6 : ((jt == JFixed) ? 0 : 1);
+    for_dofs<Topo>(P, [&](auto dd) {
+      const int d = dd;
+      if (d >= vo && Topo::dof_under(P, d, i)) {
+        if (d >= vo + nvi) {  // a dof below this body: its F arrived here when the child was processed
+          const SV F = Fd[d];
+          if (jt == JRevolute) H[hidx(d, vo)] = axis_dot<Topo>(P, i, F.a);
+          else if (jt == JPrismatic) H[hidx(d, vo)] = axis_dot<Topo>(P, i, F.l);
+          else if (jt == JFloating) {
+            H[hidx(d, vo)] = F.a.x; H[hidx(d, vo + 1)] = F.a.y; H[hidx(d, vo + 2)] = F.a.z;
+            H[hidx(d, vo + 3)] = F.l.x; H[hidx(d, vo + 4)] = F.l.y; H[hidx(d, vo + 5)] = F.l.z;
+          }
+        }
+        if (carry) Fd[d] = force_to_parent(E, r, Fd[d]);
+      }
+    });
   });
 
   if constexpr (SYNC >= 1) gp_block_sync();

@@ -200,6 +200,9 @@ struct StaticTopo {
     }
   };
 
+  // bodies that are ancestor-or-self of dof K's body, as a bit mask
+  struct FDofBodies { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().anc_mask[tables().dof_body[K]]; } };
+
   // loop bound helper: static topologies always loop to the compile-time maximum (with a
   // guard inside) so that every trip count is a literal when the unroller first sees the loop
   GP_HD static constexpr int lim(int /*runtime_bound*/, int static_bound) { return static_bound; }
@@ -221,6 +224,10 @@ struct StaticTopo {
   // dof a's body is an ancestor-or-self of dof b's body (mass-matrix entry (b,a) is structurally non-zero)
   GP_HD static constexpr bool dof_anc(const MechParams&, int a, int b) {
     return ((select_chain<FDofAnc, 0, NV>(b) >> a) & 1ull) != 0ull;
+  }
+  // dof d belongs to the subtree rooted at body i (i itself included)
+  GP_HD static constexpr bool dof_under(const MechParams&, int d, int i) {
+    return ((select_chain<FDofBodies, 0, NV>(d) >> i) & 1ull) != 0ull;
   }
 };
 
@@ -251,6 +258,7 @@ struct DynTopo {
   GP_HD static bool dof_anc(const MechParams& P, int a, int b) {
     return ((P.anc_mask[P.dof_body[b]] >> P.dof_body[a]) & 1u) != 0u;
   }
+  GP_HD static bool dof_under(const MechParams& P, int d, int i) { return ((P.anc_mask[P.dof_body[d]] >> i) & 1u) != 0u; }
 };
 
 // ---------------------------------------------------------------- shipped specialisations

@@ -8,6 +8,11 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cmath>
+#ifndef __CUDA_ARCH__
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }  // device-only in CUDA's headers
+#endif
+
 #include "../gorilla_physics_b200/csrc/gp_host.h"
 #include "../gorilla_physics_b200/csrc/gp_dynamics.cuh"
 
