@@ -71,6 +71,123 @@ GP_D V3 sym_mul_axis(const MechParams& P, int i, const S3& J) {
   return mul(J, V3{P.axis[i][0], P.axis[i][1], P.axis[i][2]});
 }
 
+// ---- sin/cos of every revolute joint angle, evaluated together --------------------------------
+// nalgebra's from_axis_angle (reference revolute.rs:97-102) calls libm sin_cos per joint. Here the
+// angles of one environment go through ONE polynomial evaluation in lockstep: the coefficient is the
+// outer loop, the joint the inner one, so that every 64-bit literal is materialised once per step
+// instead of once per joint (on sm_100a an FP64 literal costs two UMOVs) and the 2 x n_revolute
+// Horner chains are independent work for the FP64 pipe. Cody-Waite reduction by pi/2 in three parts,
+// then the fdlibm minimax kernels on [-pi/4, pi/4] (|error| < 1 ulp); an environment with any
+// |angle| >= 1e5 (or a non-finite one) takes the library routine (Payne-Hanek) for all its joints.
+GP_D void sincos_reduce(double x, double& r, int& quad) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer
+  double j = fma(x, 0.63661977236758138, magic);
+#if defined(__CUDA_ARCH__)
+  quad = __double2loint(j);
+#else
+  quad = (int)(long long)nearbyint(x * 0.63661977236758138);
+#endif
+  j -= magic;
+  r = fma(-j, 1.5707963267948966e+00, x);
+  r = fma(-j, 6.1232339957367574e-17, r);
+  r = fma(-j, 8.4784276603688995e-32, r);
+}
+struct SinCos {
+  double s, c;
+};
+// (static kernels: one out-of-line copy per kernel instead of one per joint)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ SinCos sincos_library(double x) {
+#else
+inline SinCos sincos_library(double x) {
+#endif
+  SinCos o;
+  sincos(x, &o.s, &o.c);
+  return o;
+}
+GP_D void sincos_finish(int quad, double ks, double kc, double& sn, double& cs) {
+  if (quad & 1) {
+    const double t = ks;
+    ks = kc;
+    kc = t;
+  }
+  sn = (quad & 2) ? -ks : ks;
+  cs = ((quad + 1) & 2) ? -kc : kc;
+}
+GP_HD constexpr double sin_coef(int k) {
+  return k == 0 ? -1.66666666666666324348e-01
+       : k == 1 ? 8.33333333332248946124e-03
+       : k == 2 ? -1.98412698298579493134e-04
+       : k == 3 ? 2.75573137070700676789e-06
+       : k == 4 ? -2.50507602534068634195e-08
+                : 1.58969099521155010221e-10;
+}
+GP_HD constexpr double cos_coef(int k) {
+  return k == 0 ? 4.16666666666666019037e-02
+       : k == 1 ? -1.38888888888741095749e-03
+       : k == 2 ? 2.48015872894767294178e-05
+       : k == 3 ? -2.75573143513906633035e-07
+       : k == 4 ? 2.08757232129817482790e-09
+                : -1.13596475577881948265e-11;
+}
+
+template <class Topo>
+GP_D void joint_sincos(const MechParams& P, const double* q, double* sn, double* cs) {
+  constexpr int NB = Topo::NB;
+  // one test for the whole environment keeps the fast path in a single basic block
+  bool library = !Topo::kStatic;
+  if constexpr (Topo::kStatic) {
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      if (Topo::jtype(P, i) == JRevolute) library = library || !(fabs(q[Topo::qoff(P, i)]) < 1.0e5);
+    });
+  }
+  if (library) {
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      sn[i] = 0.0;
+      cs[i] = 1.0;
+      if (Topo::jtype(P, i) == JRevolute) {
+        const SinCos o = sincos_library(q[Topo::qoff(P, i)]);
+        sn[i] = o.s;
+        cs[i] = o.c;
+      }
+    });
+  } else {
+    double r[NB], z[NB], ps[NB], pc[NB];
+    int quad[NB];
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      sn[i] = 0.0;
+      cs[i] = 1.0;
+      if (Topo::jtype(P, i) == JRevolute) {
+        sincos_reduce(q[Topo::qoff(P, i)], r[i], quad[i]);
+        z[i] = r[i] * r[i];
+        ps[i] = sin_coef(5);
+        pc[i] = cos_coef(5);
+      }
+    });
+    static_for<0, 5>([&](auto kk) {
+      constexpr int k = 4 - decltype(kk)::value;
+      for_bodies<Topo>(P, [&](auto ii) {
+        const int i = ii;
+        if (Topo::jtype(P, i) == JRevolute) {
+          ps[i] = fma(ps[i], z[i], sin_coef(k));
+          pc[i] = fma(pc[i], z[i], cos_coef(k));
+        }
+      });
+    });
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      if (Topo::jtype(P, i) == JRevolute) {
+        const double ks = fma(r[i] * z[i], ps[i], r[i]);
+        const double kc = fma(z[i], fma(z[i], pc[i], -0.5), 1.0);
+        sincos_finish(quad[i], ks, kc, sn[i], cs[i]);
+      }
+    });
+  }
+}
+
 // ---- joint transform: successor -> predecessor (E, r) --------------------------------------
 // reference: revolute.rs:97-102, prismatic.rs:82-87, floating.rs:26-31 + pose.rs:30-33
 template <class Topo>
@@ -149,6 +266,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
   unsigned status = 0u;
 
   double sn[NB], cs[NB];  // cached sin/cos of revolute joints
+  joint_sincos<Topo>(P, q, sn, cs);
   SV vel[NB], acc[NB], frc[NB];
   constexpr int NHS = (CONTACT == 2) ? kMaxHS : 1;
   // spring contacts (contact.rs:133-186) need world poses and carry state; only the run-time-topology
@@ -166,9 +284,6 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     const int p = Topo::parent(P, i);
     const int jt = Topo::jtype(P, i);
     const int vo = Topo::voff(P, i);
-    sn[i] = 0.0;
-    cs[i] = 1.0;
-    if (jt == JRevolute) sincos(q[Topo::qoff(P, i)], &sn[i], &cs[i]);
     M3 E;
     V3 r;
     joint_xform<Topo>(P, i, q, sn[i], cs[i], E, r);
@@ -224,12 +339,30 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     vel[i] = vi;
     acc[i] = ai;
 
-    // Newton-Euler: f = I a + v x* (I v)   (reference dynamics.rs:41-100, body coordinates)
-    RBI I{lds3(P.J[i]), ld3(P.mc[i]), P.mass[i]};
-    SV h = mul(I, vi);
-    SV f = mul(I, ai);
-    f.a += cross(vi.a, h.a) + cross(vi.l, h.l);
-    f.l += cross(vi.a, h.l);
+    // Newton-Euler: f = I a + v x* (I v)   (reference dynamics.rs:41-100, body coordinates),
+    // every sum written as one chain of fused multiply-adds
+    const S3 Ji = lds3(P.J[i]);
+    const V3 ci = ld3(P.mc[i]);
+    const double mi = P.mass[i];
+    SV f;
+    if (!moving_parent && jt == JRevolute) {
+      // w = axis qd, no linear velocity, no angular acceleration: the velocity-product terms are
+      // qd^2 times constants folded on the host (gp_params.h ne_a, ne_l)
+      const double qd2 = v[vo] * v[vo];
+      const V3 ca = cross(ci, ai.l);
+      f.a = V3{fma(qd2, P.ne_a[i][0], ca.x), fma(qd2, P.ne_a[i][1], ca.y), fma(qd2, P.ne_a[i][2], ca.z)};
+      f.l = V3{fma(qd2, P.ne_l[i][0], mi * ai.l.x), fma(qd2, P.ne_l[i][1], mi * ai.l.y),
+               fma(qd2, P.ne_l[i][2], mi * ai.l.z)};
+    } else if (!moving_parent) {
+      // no angular acceleration from above (prismatic / floating / fixed root)
+      const SV h = mul(RBI{Ji, ci, mi}, vi);
+      f.a = cross_add(cross_add(cross(ci, ai.l), vi.a, h.a), vi.l, h.l);
+      f.l = cross_add(ai.l * mi, vi.a, h.l);
+    } else {
+      const SV h = mul(RBI{Ji, ci, mi}, vi);
+      f.a = cross_add(cross_add(mul_add(cross(ci, ai.l), Ji, ai.a), vi.a, h.a), vi.l, h.l);
+      f.l = cross_add(cross_sub(ai.l * mi, ci, ai.a), vi.a, h.l);
+    }
 
     if constexpr (CONTACT != 0) {
       M3 Rwi;
@@ -259,15 +392,16 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
 #pragma unroll
         for (int h = 0; h < NHS; ++h) {
           if (CONTACT == 1 || h < P.n_hs) {
-            const double d = dot(hn[i][h], loc) - ho[i][h];  // contact.rs:64-68, halfspace.rs:39-44
-            if (d <= 1e-8) {
-              const V3 vpt = vi.l + cross(vi.a, loc);  // twist.rs:130-132, body coordinates
-              fb += contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
+            const double d = dot_add(-ho[i][h], hn[i][h], loc);  // contact.rs:64-68, halfspace.rs:39-44
+            if (d <= 1e-8) {  // most points are in the air most of the time
+              const V3 vpt = cross_add(vi.l, vi.a, loc);  // twist.rs:130-132, body coordinates
+              const V3 fc = contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
+              f.a = cross_sub(f.a, loc, fc);
+              f.l -= fc;
+              if constexpr (WORLD) fb += fc;
             }
           }
         }
-        f.a -= cross(loc, fb);
-        f.l -= fb;
         if constexpr (WORLD) {
           if (out.contact_force) {
             const V3 fw = mul(Rwi, fb);
@@ -326,14 +460,15 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
   // ------------------------------------------------------------------ pass 2: leaf -> root
   double H[NV * (NV + 1) / 2];
   double b[NV];
-  RBI Iacc[NB];  // children's composite inertias expressed in this body's frame
+  RBI Iacc[NB];  // composite inertia of the subtree, gathered in the body's own coordinates
   SV Fd[NV];     // mass-matrix columns on their way to the root (see below)
   if (!Topo::kStatic) {
     for (int k = 0; k < nv * (nv + 1) / 2; ++k) H[k] = 0.0;
   }
+  // start from the body's own inertia plus the constant part of what its children add (gp_params.h)
   for_bodies<Topo>(P, [&](auto ii) {
     const int i = ii;
-    if (Topo::has_children(P, i)) Iacc[i] = RBI{S3{0, 0, 0, 0, 0, 0}, v3z(), 0.0};
+    if (Topo::has_children(P, i)) Iacc[i] = RBI{lds3(P.Jacc0[i]), ld3(P.cacc0[i]), P.msub[i]};
   });
 
   for_bodies_reverse<Topo>(P, [&](auto ii) {
@@ -343,12 +478,9 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     const int vo = Topo::voff(P, i);
 
     // composite rigid-body inertia of the subtree rooted at i (reference mechanism.rs:606-625)
-    RBI Ic{lds3(P.J[i]), ld3(P.mc[i]), P.mass[i]};
-    if (Topo::has_children(P, i)) {
-      Ic.J = Ic.J + Iacc[i].J;
-      Ic.c += Iacc[i].c;
-      Ic.m += Iacc[i].m;
-    }
+    RBI Ic;
+    if (Topo::has_children(P, i)) Ic = Iacc[i];
+    else Ic = RBI{lds3(P.J[i]), ld3(P.mc[i]), P.mass[i]};
 
     // bias torque c_i = S^T f_i (reference wrench.rs:96-126)
     const SV f = frc[i];
@@ -359,17 +491,15 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       b[vo + 3] = f.l.x; b[vo + 4] = f.l.y; b[vo + 5] = f.l.z;
     }
 
+    // some joint above still has dofs: forces, inertias and mass-matrix columns travel on
+    const bool carry = (p >= 0) && !Topo::anchored(P, p);
     M3 E;
     V3 r;
-    if (p >= 0) {
+    if (carry) {
       joint_xform<Topo>(P, i, q, sn[i], cs[i], E, r);
-      SV fp = force_to_parent(E, r, f);
-      frc[p].a += fp.a;
-      frc[p].l += fp.l;
-      RBI Ip = inertia_to_parent(E, r, Ic);
-      Iacc[p].J = Iacc[p].J + Ip.J;
-      Iacc[p].c += Ip.c;
-      Iacc[p].m += Ip.m;
+      force_acc_parent(frc[p], E, r, f);
+      if (jt == JRevolute || jt == JFixed) inertia_acc_parent<true>(Iacc[p], E, r, ld3(P.r0x2[i]), Ic);
+      else inertia_acc_parent<false>(Iacc[p], E, r, r, Ic);
     }
 
     if constexpr (SYNC >= 2) gp_block_sync();
@@ -377,7 +507,6 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     // (Fd[d] is expressed in the coordinates of the body the loop has reached), so each joint
     // transform is built once per body and applied to all the vectors that cross it;
     // H_dj = S_j^T F_d for every joint j supporting d (reference mechanism.rs:637-696, momentum.rs:17-47)
-    const bool carry = (p >= 0) && !Topo::anchored(P, p);  // some joint above still has dofs
     if (jt == JRevolute) {
       SV F;
       F.a = sym_mul_axis<Topo>(P, i, Ic.J);

@@ -142,6 +142,11 @@ GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q
   if (A.controller == GP_CTRL_SO101_PD) {
     // SO101PositionController, reference control/so101_control.rs:12-34
     const double kp = A.cp[0], kd = A.cp[1], cl = A.cp[2];
+#if defined(__CUDA_ARCH__)
+    // keeps this block a real (uniform) branch: without it the compiler evaluates the whole PD law every
+    // step and selects between it and the loaded torques, ~60 instructions per step for nothing
+    asm volatile("");
+#endif
     for_bodies<Topo>(P, [&](auto ii) {
       const int i = ii;
       const int jt = Topo::jtype(P, i);

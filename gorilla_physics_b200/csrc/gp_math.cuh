@@ -2,6 +2,8 @@
 // Device-side replacements for the nalgebra operations the reference leans on
 // (SURVEY.md §8c table); everything is expressed in body coordinates.
 #pragma once
+#include <cmath>
+
 #include "gp_topology.cuh"
 
 namespace gp {
@@ -23,6 +25,19 @@ GP_HD V3 cross(V3 a, V3 b) {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 GP_HD V3 ld3(const double* p) { return {p[0], p[1], p[2]}; }
+// acc + a x b as two fused multiply-adds per component (the plain `acc + cross(a, b)` costs a
+// multiply, an FMA and an add: the compiler may not re-associate)
+GP_HD V3 cross_add(V3 acc, V3 a, V3 b) {
+  return {fma(a.y, b.z, fma(-a.z, b.y, acc.x)), fma(a.z, b.x, fma(-a.x, b.z, acc.y)),
+          fma(a.x, b.y, fma(-a.y, b.x, acc.z))};
+}
+// acc - a x b
+GP_HD V3 cross_sub(V3 acc, V3 a, V3 b) {
+  return {fma(a.z, b.y, fma(-a.y, b.z, acc.x)), fma(a.x, b.z, fma(-a.z, b.x, acc.y)),
+          fma(a.y, b.x, fma(-a.x, b.y, acc.z))};
+}
+// acc + a . b
+GP_HD double dot_add(double acc, V3 a, V3 b) { return fma(a.z, b.z, fma(a.y, b.y, fma(a.x, b.x, acc))); }
 
 // rotation / general 3x3, row-major
 struct M3 {
@@ -35,6 +50,12 @@ GP_HD V3 mul(const M3& E, V3 v) {
 GP_HD V3 mulT(const M3& E, V3 v) {
   return {E.m[0] * v.x + E.m[3] * v.y + E.m[6] * v.z, E.m[1] * v.x + E.m[4] * v.y + E.m[7] * v.z,
           E.m[2] * v.x + E.m[5] * v.y + E.m[8] * v.z};
+}
+// acc + E v
+GP_HD V3 mul_add(V3 acc, const M3& E, V3 v) {
+  return {fma(E.m[2], v.z, fma(E.m[1], v.y, fma(E.m[0], v.x, acc.x))),
+          fma(E.m[5], v.z, fma(E.m[4], v.y, fma(E.m[3], v.x, acc.y))),
+          fma(E.m[8], v.z, fma(E.m[7], v.y, fma(E.m[6], v.x, acc.z)))};
 }
 GP_HD M3 mul(const M3& A, const M3& B) {
   M3 R;
@@ -71,6 +92,11 @@ GP_HD V3 mul(const S3& J, V3 v) {
   return {J.xx * v.x + J.xy * v.y + J.xz * v.z, J.xy * v.x + J.yy * v.y + J.yz * v.z,
           J.xz * v.x + J.yz * v.y + J.zz * v.z};
 }
+// acc + J v
+GP_HD V3 mul_add(V3 acc, const S3& J, V3 v) {
+  return {fma(J.xz, v.z, fma(J.xy, v.y, fma(J.xx, v.x, acc.x))), fma(J.yz, v.z, fma(J.yy, v.y, fma(J.xy, v.x, acc.y))),
+          fma(J.zz, v.z, fma(J.yz, v.y, fma(J.xz, v.x, acc.z)))};
+}
 GP_HD S3 operator+(const S3& a, const S3& b) {
   return {a.xx + b.xx, a.xy + b.xy, a.xz + b.xz, a.yy + b.yy, a.yz + b.yz, a.zz + b.zz};
 }
@@ -105,12 +131,18 @@ GP_HD SV svz() { return SV{v3z(), v3z()}; }
 // motion vector from predecessor to successor coordinates. E maps successor-frame vectors
 // to the predecessor frame, r is the successor origin in predecessor coordinates.
 GP_HD SV motion_to_child(const M3& E, V3 r, const SV& p) {
-  return SV{mulT(E, p.a), mulT(E, p.l + cross(p.a, r))};
+  return SV{mulT(E, p.a), mulT(E, cross_add(p.l, p.a, r))};
 }
 // force vector from successor to predecessor coordinates
 GP_HD SV force_to_parent(const M3& E, V3 r, const SV& f) {
   V3 fl = mul(E, f.l);
-  return SV{mul(E, f.a) + cross(r, fl), fl};
+  return SV{mul_add(cross(r, fl), E, f.a), fl};
+}
+// acc += (f expressed in predecessor coordinates)
+GP_HD void force_acc_parent(SV& acc, const M3& E, V3 r, const SV& f) {
+  V3 fl = mul(E, f.l);
+  acc.a = mul_add(cross_add(acc.a, r, fl), E, f.a);
+  acc.l += fl;
 }
 
 // rigid-body inertia about the frame origin: (J, c = m * com, m)
@@ -121,7 +153,7 @@ struct RBI {
 };
 // I * (w; v) = (J w + c x v ; m v - c x w)        reference util.rs:18-28 mul_inertia
 GP_HD SV mul(const RBI& I, const SV& v) {
-  return SV{mul(I.J, v.a) + cross(I.c, v.l), v.l * I.m - cross(I.c, v.a)};
+  return SV{mul_add(cross(I.c, v.l), I.J, v.a), cross_sub(v.l * I.m, I.c, v.a)};
 }
 // express an inertia given in the successor frame in the predecessor frame
 // (same algebra as reference inertia.rs:106-134, with Y = w r^T + r w^T, w = c' + (m/2) r)
@@ -140,6 +172,43 @@ GP_HD RBI inertia_to_parent(const M3& E, V3 r, const RBI& I) {
   R.c = c1 + r * I.m;
   R.m = I.m;
   return R;
+}
+
+
+// acc += (composite inertia I of a child, expressed in the parent's coordinates).
+// CONST_R (revolute / fixed joints: r and the subtree mass never change): the host has already folded
+// the parallel-axis terms m (r.r 1 - r r^T) and m r into the parent's accumulator (MechParams::Jacc0,
+// cacc0), r2 = 2 r comes from the constant bank, and what is left is
+//   J += E J E^T - (c1 r^T + r c1^T) + 2 (c1.r) 1,   c += c1,   c1 = E c.
+// Otherwise the same expression with w = c1 + (m/2) r in place of c1 covers the mass terms
+// (inertia_to_parent above), and c += c1 + m r. The composite mass is a host constant either way.
+template <bool CONST_R>
+GP_HD void inertia_acc_parent(RBI& acc, const M3& E, V3 r, V3 r2, const RBI& I) {
+  const V3 c1 = mul(E, I.c);
+  V3 w = c1;
+  if (!CONST_R) {
+    w = V3{fma(r.x, 0.5 * I.m, c1.x), fma(r.y, 0.5 * I.m, c1.y), fma(r.z, 0.5 * I.m, c1.z)};
+    r2 = r + r;
+    acc.c = V3{fma(r.x, I.m, acc.c.x), fma(r.y, I.m, acc.c.y), fma(r.z, I.m, acc.c.z)};
+  }
+  acc.c += c1;
+  double t[9];  // T = E J
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double a = E.m[3 * i], b = E.m[3 * i + 1], c = E.m[3 * i + 2];
+    t[3 * i + 0] = a * I.J.xx + b * I.J.xy + c * I.J.xz;
+    t[3 * i + 1] = a * I.J.xy + b * I.J.yy + c * I.J.yz;
+    t[3 * i + 2] = a * I.J.xz + b * I.J.yz + c * I.J.zz;
+  }
+  const V3 e0 = V3{E.m[0], E.m[1], E.m[2]}, e1 = V3{E.m[3], E.m[4], E.m[5]}, e2 = V3{E.m[6], E.m[7], E.m[8]};
+  const V3 t0 = V3{t[0], t[1], t[2]}, t1 = V3{t[3], t[4], t[5]}, t2 = V3{t[6], t[7], t[8]};
+  // diagonal: -2 w_x r_x + 2 w.r = 2 (w_y r_y + w_z r_z)
+  acc.J.xx = fma(w.z, r2.z, fma(w.y, r2.y, dot_add(acc.J.xx, t0, e0)));
+  acc.J.yy = fma(w.z, r2.z, fma(w.x, r2.x, dot_add(acc.J.yy, t1, e1)));
+  acc.J.zz = fma(w.y, r2.y, fma(w.x, r2.x, dot_add(acc.J.zz, t2, e2)));
+  acc.J.xy = fma(-r.x, w.y, fma(-w.x, r.y, dot_add(acc.J.xy, t0, e1)));
+  acc.J.xz = fma(-r.x, w.z, fma(-w.x, r.z, dot_add(acc.J.xz, t0, e2)));
+  acc.J.yz = fma(-r.y, w.z, fma(-w.y, r.z, dot_add(acc.J.yz, t1, e2)));
 }
 
 }  // namespace gp

@@ -115,6 +115,44 @@ int finalize_mechanism(gp_mechanism* m) {
     P.spring_l[i] = m->spring_l[i];
     P.armature[i] = m->armature[i];
   }
+  // constants of the composite-inertia pass (see gp_params.h): children come after their parents,
+  // so one leaf-to-root sweep sees every subtree mass before it is needed
+  for (int i = 0; i < nb; ++i) {
+    P.msub[i] = P.mass[i];
+    for (int k = 0; k < 6; ++k) P.Jacc0[i][k] = P.J[i][k];
+    for (int k = 0; k < 3; ++k) {
+      P.cacc0[i][k] = P.mc[i][k];
+      P.r0x2[i][k] = 2.0 * P.r0[i][k];
+    }
+    const double* a = P.axis[i];
+    const double* J = P.J[i];
+    const double Ja[3] = {J[0] * a[0] + J[1] * a[1] + J[2] * a[2], J[1] * a[0] + J[3] * a[1] + J[4] * a[2],
+                          J[2] * a[0] + J[4] * a[1] + J[5] * a[2]};
+    const double ac = a[0] * P.mc[i][0] + a[1] * P.mc[i][1] + a[2] * P.mc[i][2];
+    P.ne_a[i][0] = a[1] * Ja[2] - a[2] * Ja[1];
+    P.ne_a[i][1] = a[2] * Ja[0] - a[0] * Ja[2];
+    P.ne_a[i][2] = a[0] * Ja[1] - a[1] * Ja[0];
+    const double aa = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    for (int k = 0; k < 3; ++k) P.ne_l[i][k] = a[k] * ac - P.mc[i][k] * aa;
+  }
+  for (int i = nb - 1; i >= 0; --i) {
+    const int p = P.parent[i];
+    if (p < 0) continue;
+    P.msub[p] += P.msub[i];
+    if (P.jtype[i] == JRevolute || P.jtype[i] == JFixed) {
+      const double m = P.msub[i];
+      const double* r = P.r0[i];
+      const double rr = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+      P.Jacc0[p][0] += m * (rr - r[0] * r[0]);
+      P.Jacc0[p][1] += -m * r[0] * r[1];
+      P.Jacc0[p][2] += -m * r[0] * r[2];
+      P.Jacc0[p][3] += m * (rr - r[1] * r[1]);
+      P.Jacc0[p][4] += -m * r[1] * r[2];
+      P.Jacc0[p][5] += m * (rr - r[2] * r[2]);
+      for (int k = 0; k < 3; ++k) P.cacc0[p][k] += m * r[k];
+    }
+  }
+
   // contact points are stored body-major already
   int c = 0;
   for (int b = 0; b < nb; ++b) {

@@ -75,6 +75,21 @@ struct MechParams {
   double spring_l[kMaxBodies];
   double armature[kMaxBodies];  // added to the joint's own diagonal entry of H
 
+  // ---- constants of the composite-inertia pass, folded by gp_mechanism_create (gp_dynamics.cuh pass 2)
+  // A child behind a revolute or fixed joint sits at a constant offset r and its subtree has a
+  // constant mass m, so the parallel-axis part m (r.r 1 - r r^T) of what it adds to its parent's
+  // composite inertia, and m r of the first moment, never change: they start out in the parent's
+  // accumulator.
+  double msub[kMaxBodies];      // mass of the subtree rooted at the body
+  double Jacc0[kMaxBodies][6];  // J + sum over such children c of msub[c] (r.r 1 - r r^T)
+  double cacc0[kMaxBodies][3];  // mc + sum over such children c of msub[c] r
+  double r0x2[kMaxBodies][3];   // 2 r0
+  // Newton-Euler force of a revolute joint whose parent does not move (root, or a body fixed to
+  // the world): f = (c x a_l + qd^2 ne_a ; m a_l + qd^2 ne_l),  ne_a = axis x (J axis),
+  // ne_l = axis (axis.c) - c
+  double ne_a[kMaxBodies][3];
+  double ne_l[kMaxBodies][3];
+
   // ---- contact (contact.rs:17-38, halfspace.rs:6-11)
   double cp_loc[kMaxCP][3];
   double cp_k[kMaxCP];

@@ -2,8 +2,10 @@
 // Compiles the device functions of gp_dynamics.cuh for the host (-DGP_HOST_DEBUG) so that a
 // kernel bug can be chased on a machine without a GPU. Reads a mechanism by model name, evaluates
 // dynamics_core once for a given state and prints vdot / H / bias.
-//   nvcc -DGP_HOST_DEBUG -std=c++17 --expt-relaxed-constexpr -I. tools/host_debug.cu \
-//        gorilla_physics_b200/csrc/gp_mechanism.cpp gorilla_physics_b200/csrc/gp_models.cpp ... 
+//   g++ -DGP_HOST_DEBUG -std=c++17 -O1 -shared -fPIC -I/usr/local/cuda/include -x c++ -o /tmp/proto/libgpdbg.so \
+//       tools/host_debug.cu gorilla_physics_b200/csrc/gp_mechanism.cpp gorilla_physics_b200/csrc/gp_models.cpp \
+//       -L/usr/local/cuda/lib64 -lcudart
+//   python tools/host_debug.py all
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -43,4 +45,37 @@ extern "C" int gpdbg_dynamics(const gp_mechanism* m, const double* q, const doub
   unsigned st = dynamics_core<DynTopo, 2, true>(P, qq, vv, tt, vd, out);
   for (int k = 0; k < P.n_v; ++k) vdot[k] = vd[k];
   return (int)st;
+}
+
+// the compile-time-topology instantiation the library would pick for this mechanism (same code the
+// static step kernels run, including the batched sin/cos); returns -1 when none matches
+template <class Spec>
+static int run_static(const gp_mechanism* m, const double* q, const double* v, const double* tau, double* vdot,
+                      double* H, double* bias, double* cf) {
+  using T = StaticTopo<Spec>;
+  const MechParams& P = m->params;
+  double qq[T::NQ + 1] = {0}, vv[T::NV + 1] = {0}, tt[T::NV + 1] = {0}, vd[T::NV + 1] = {0};
+  for (int k = 0; k < P.n_q; ++k) qq[k] = q[k];
+  for (int k = 0; k < P.n_v; ++k) { vv[k] = v[k]; tt[k] = tau ? tau[k] : 0.0; }
+  DynOut out{cf, H, bias, 1, 0, nullptr};
+  unsigned st = dynamics_core<T, 2, true>(P, qq, vv, tt, vd, out);
+  for (int k = 0; k < P.n_v; ++k) vdot[k] = vd[k];
+  return (int)st;
+}
+extern "C" int gpdbg_dynamics_static(const gp_mechanism* m, const double* q, const double* v, const double* tau,
+                                     double* vdot, double* H, double* bias, double* cf) {
+  const MechParams& P = m->params;
+  TopoData td{};
+  td.nb = P.nb;
+  for (int i = 0; i < P.nb; ++i) {
+    td.parent[i] = P.parent[i];
+    td.jtype[i] = P.jtype[i];
+    const bool scalar = (P.jtype[i] == JRevolute || P.jtype[i] == JPrismatic);
+    td.axis[i] = (scalar && P.axis[i][0] == 0.0 && P.axis[i][1] == 0.0 && P.axis[i][2] == 1.0) ? AxZ : AxAny;
+  }
+#define GP_TRY(Spec) if (topo_matches(Spec::data(), td)) return run_static<Spec>(m, q, v, tau, vdot, H, bias, cf);
+  GP_TRY(SpecPendulum) GP_TRY(SpecDoublePendulum) GP_TRY(SpecCartPole) GP_TRY(SpecSO101) GP_TRY(SpecFloating)
+  GP_TRY(SpecHopper1D) GP_TRY(SpecHopper) GP_TRY(SpecQuadruped) GP_TRY(SpecNavbot)
+#undef GP_TRY
+  return -1;
 }

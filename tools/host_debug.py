@@ -18,6 +18,7 @@ for n in ("gp_model_create", "gp_mechanism_create", "gp_mechanism_add_halfspace"
     getattr(dbg, n).restype = C.c_int
 dbg.gp_mechanism_create.argtypes = [C.POINTER(_abi.GpMechanismDesc), C.POINTER(C.c_void_p)]
 dbg.gpdbg_dynamics.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp]
+dbg.gpdbg_dynamics_static.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp]
 
 
 def run(name):
@@ -46,7 +47,16 @@ def run(name):
         qq = np.ascontiguousarray(q[e]); vv = np.ascontiguousarray(v[e]); tt = np.ascontiguousarray(tau[e])
         dbg.gpdbg_dynamics(h, qq.ctypes.data_as(dp), vv.ctypes.data_as(dp), tt.ctypes.data_as(dp),
                            vdot.ctypes.data_as(dp), H.ctypes.data_as(dp), b.ctypes.data_as(dp), cf.ctypes.data_as(dp))
+        vs = np.zeros(nv); Hs = np.zeros((nv, nv)); bs = np.zeros(nv); cfs = np.zeros_like(cf)
+        rc = dbg.gpdbg_dynamics_static(h, qq.ctypes.data_as(dp), vv.ctypes.data_as(dp), tt.ctypes.data_as(dp),
+                                       vs.ctypes.data_as(dp), Hs.ctypes.data_as(dp), bs.ctypes.data_as(dp), cfs.ctypes.data_as(dp))
         ref = orc.dynamics(q[e], v[e], tau[e], want="all")
+        if rc >= 0:
+            es = np.abs(vs - ref["vdot"]).max() / max(np.abs(ref["vdot"]).max(), 1e-9)
+            ecf = np.abs(cfs - cf).max()
+            if e == 0 or es > 1e-9:
+                print(f"{name} env {e}: static-topology vdot err {es:.2e}, contact force vs generic {ecf:.1e}")
+            worst = max(worst, es)
         eM = np.abs(H - ref["mass_matrix"]).max() / np.abs(ref["mass_matrix"]).max()
         eb = np.abs(b - ref["bias"]).max() / max(np.abs(ref["bias"]).max(), 1e-9)
         ev = np.abs(vdot - ref["vdot"]).max() / max(np.abs(ref["vdot"]).max(), 1e-9)
