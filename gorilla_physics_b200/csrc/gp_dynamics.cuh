@@ -136,6 +136,17 @@ GP_D void joint_sincos(const MechParams& P, const double* q, double* sn, double*
   constexpr int NB = Topo::NB;
   // one test for the whole environment keeps the fast path in a single basic block
   bool library = !Topo::kStatic;
+  if constexpr (Topo::kStatic && !Topo::kBatchedSinCos) {
+    // (the quadruped kernel is short of registers at its start: 8 angles in flight cost more in spills
+    // than the shared literals save, profiles/r1_tuning.md)
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      sn[i] = 0.0;
+      cs[i] = 1.0;
+      if (Topo::jtype(P, i) == JRevolute) sincos(q[Topo::qoff(P, i)], &sn[i], &cs[i]);
+    });
+    return;
+  }
   if constexpr (Topo::kStatic) {
     for_bodies<Topo>(P, [&](auto ii) {
       const int i = ii;
@@ -339,31 +350,11 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     vel[i] = vi;
     acc[i] = ai;
 
-    // Newton-Euler: f = I a + v x* (I v)   (reference dynamics.rs:41-100, body coordinates),
-    // every sum written as one chain of fused multiply-adds
-    const S3 Ji = lds3(P.J[i]);
-    const V3 ci = ld3(P.mc[i]);
-    const double mi = P.mass[i];
-    SV f;
-    if (!moving_parent && jt == JRevolute) {
-      // w = axis qd, no linear velocity, no angular acceleration: the velocity-product terms are
-      // qd^2 times constants folded on the host (gp_params.h ne_a, ne_l)
-      const double qd2 = v[vo] * v[vo];
-      const V3 ca = cross(ci, ai.l);
-      f.a = V3{fma(qd2, P.ne_a[i][0], ca.x), fma(qd2, P.ne_a[i][1], ca.y), fma(qd2, P.ne_a[i][2], ca.z)};
-      f.l = V3{fma(qd2, P.ne_l[i][0], mi * ai.l.x), fma(qd2, P.ne_l[i][1], mi * ai.l.y),
-               fma(qd2, P.ne_l[i][2], mi * ai.l.z)};
-    } else if (!moving_parent) {
-      // no angular acceleration from above (prismatic / floating / fixed root)
-      const SV h = mul(RBI{Ji, ci, mi}, vi);
-      f.a = cross_add(cross_add(cross(ci, ai.l), vi.a, h.a), vi.l, h.l);
-      f.l = cross_add(ai.l * mi, vi.a, h.l);
-    } else {
-      const SV h = mul(RBI{Ji, ci, mi}, vi);
-      f.a = cross_add(cross_add(mul_add(cross(ci, ai.l), Ji, ai.a), vi.a, h.a), vi.l, h.l);
-      f.l = cross_add(cross_sub(ai.l * mi, ci, ai.a), vi.a, h.l);
-    }
-
+    // The contact wrench (subtracted from the body force, dynamics.rs:244-246) is gathered first and
+    // the Newton-Euler chains below start from it: the branchy contact loop then sits between the
+    // kinematics of this body and its force, and the (independent) force of this body and kinematics
+    // of the next share one basic block for the instruction scheduler.
+    V3 ka = v3z(), kl = v3z();  // minus the contact wrench on this body
     if constexpr (CONTACT != 0) {
       M3 Rwi;
       if constexpr (WORLD) {  // body -> world rotation (reference mechanism.rs:153-170), parity output only
@@ -382,8 +373,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
           ho[i][h] = op_ - dot(np_, r);
         }
       }
-      // point-vs-halfspace contact (reference contact.rs:103-128); the wrench is subtracted from
-      // the body force (dynamics.rs:244-246)
+      // point-vs-halfspace contact (reference contact.rs:103-128)
       const int c0 = P.cp_begin[i], c1 = P.cp_begin[i + 1];
 #pragma unroll 1  // keep ONE copy of the force law per body: unrolling this loop x4 bloated the kernel by 27 KB
       for (int c = c0; c < c1; ++c) {
@@ -396,8 +386,8 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
             if (d <= 1e-8) {  // most points are in the air most of the time
               const V3 vpt = cross_add(vi.l, vi.a, loc);  // twist.rs:130-132, body coordinates
               const V3 fc = contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
-              f.a = cross_sub(f.a, loc, fc);
-              f.l -= fc;
+              ka = cross_sub(ka, loc, fc);
+              kl -= fc;
               if constexpr (WORLD) fb += fc;
             }
           }
@@ -413,6 +403,31 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
         }
       }
     }
+    // Newton-Euler: f = I a + v x* (I v)   (reference dynamics.rs:41-100, body coordinates),
+    // every sum written as one chain of fused multiply-adds
+    const S3 Ji = lds3(P.J[i]);
+    const V3 ci = ld3(P.mc[i]);
+    const double mi = P.mass[i];
+    SV f;
+    if (!moving_parent && jt == JRevolute) {
+      // w = axis qd, no linear velocity, no angular acceleration: the velocity-product terms are
+      // qd^2 times constants folded on the host (gp_params.h ne_a, ne_l)
+      const double qd2 = v[vo] * v[vo];
+      const V3 ca = cross_add(ka, ci, ai.l);
+      f.a = V3{fma(qd2, P.ne_a[i][0], ca.x), fma(qd2, P.ne_a[i][1], ca.y), fma(qd2, P.ne_a[i][2], ca.z)};
+      f.l = V3{fma(qd2, P.ne_l[i][0], fma(mi, ai.l.x, kl.x)), fma(qd2, P.ne_l[i][1], fma(mi, ai.l.y, kl.y)),
+               fma(qd2, P.ne_l[i][2], fma(mi, ai.l.z, kl.z))};
+    } else if (!moving_parent) {
+      // no angular acceleration from above (prismatic / floating / fixed root)
+      const SV h = mul(RBI{Ji, ci, mi}, vi);
+      f.a = cross_add(cross_add(cross_add(ka, ci, ai.l), vi.a, h.a), vi.l, h.l);
+      f.l = cross_add(fma3(ai.l, mi, kl), vi.a, h.l);
+    } else {
+      const SV h = mul(RBI{Ji, ci, mi}, vi);
+      f.a = cross_add(cross_add(mul_add(cross_add(ka, ci, ai.l), Ji, ai.a), vi.a, h.a), vi.l, h.l);
+      f.l = cross_add(cross_sub(fma3(ai.l, mi, kl), ci, ai.a), vi.a, h.l);
+    }
+
     if constexpr (SPRINGS) {
       if (out.sc_state) {
         for (int s = 0; s < P.n_sc; ++s) {
@@ -470,6 +485,57 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     const int i = ii;
     if (Topo::has_children(P, i)) Iacc[i] = RBI{lds3(P.Jacc0[i]), ld3(P.cacc0[i]), P.msub[i]};
   });
+
+  // Sparse L^T D L factorisation of H (Cholesky family, unit lower-triangular L, no pivoting; entries
+  // with dof_anc == false are structural zeros and never touched: branch-induced sparsity, no fill-in)
+  // and the first triangular solve, one COLUMN at a time: column c of H is complete as soon as the body
+  // loop below has passed the body that owns dof c, so its part of the factorisation is done right there
+  // and overlaps the rest of the pass instead of forming a long dependent tail after it
+  // (the reference solves with a dense partial-pivot LU, dynamics.rs:255-276).
+  //   N[d]   = H[d][c] - sum_{k > d under d} L[k][d] N[k]        (deepest dof first)
+  //   L[d][c] = N[d] / D[d],   D[c] = H[c][c] - sum_d L[d][c] N[d]
+  //   rhs[c] = tau[c] + joint spring - bias[c] - sum_d L[d][c] rhs[d]       (x = L^-T rhs)
+  // H[d][c] ends up holding L[d][c], H[c][c] holds 1 / D[c], b[c] the partially solved right-hand side.
+  // (kernels that already spill - the 14-dof trees - do better with the whole factorisation after the
+  // pass, right-looking, see below: Topo::kColumnsInPass2, profiles/r1_tuning.md)
+  constexpr bool kColumnsInPass2 = Topo::kColumnsInPass2;
+  auto finish_column = [&](auto cc) {
+    const int c = cc;
+    const int jb = Topo::dof_body(P, c);
+    double t = tau[c];  // rhs = tau + joint springs - c   (reference dynamics.rs:298-315, :255-276)
+    if (Topo::jtype(P, jb) == JPrismatic) {
+      if (P.has_spring[jb]) t += -P.spring_k[jb] * (q[Topo::qoff(P, jb)] - P.spring_l[jb]);
+    }
+    double rb = t - b[c];
+#pragma unroll U
+    for (int d2 = 0; d2 < Topo::lim(nv - 1 - c, NV); ++d2) {
+      const int d = nv - 1 - d2;
+      if (d > c && Topo::dof_anc(P, c, d)) {
+        double num = H[hidx(d, c)];
+#pragma unroll U
+        for (int k2 = 0; k2 < Topo::lim(nv - 1 - d, NV); ++k2) {
+          const int k = nv - 1 - k2;
+          if (k > d && Topo::dof_anc(P, d, k)) num = fma(-H[hidx(k, d)], H[hidx(k, c)], num);
+        }
+        H[hidx(d, c)] = num;
+      }
+    }
+    double dd = H[hidx(c, c)];
+#pragma unroll U
+    for (int d2 = 0; d2 < Topo::lim(nv - 1 - c, NV); ++d2) {
+      const int d = nv - 1 - d2;
+      if (d > c && Topo::dof_anc(P, c, d)) {
+        const double num = H[hidx(d, c)];
+        const double l = num * H[hidx(d, d)];
+        dd = fma(-l, num, dd);
+        rb = fma(-l, b[d], rb);
+        H[hidx(d, c)] = l;
+      }
+    }
+    if (!(dd > 0.0)) status |= kEnvNotSPD;
+    H[hidx(c, c)] = 1.0 / dd;
+    b[c] = rb;
+  };
 
   for_bodies_reverse<Topo>(P, [&](auto ii) {
     const int i = ii;
@@ -560,6 +626,17 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
         if (carry) Fd[d] = force_to_parent(E, r, Fd[d]);
       }
     });
+    // the columns of this body's dofs are complete now (the parity kernels first report H and the bias)
+    if constexpr (!DUMP && kColumnsInPass2) {
+      if constexpr (Topo::kStatic) {
+        for_dofs_reverse<Topo>(P, [&](auto cc) {
+          const int c = cc;
+          if (c >= vo && c < vo + nvi) finish_column(cc);
+        });
+      } else {
+        for (int c = vo + nvi - 1; c >= vo; --c) finish_column(c);
+      }
+    }
   });
 
   if constexpr (SYNC >= 1) gp_block_sync();
@@ -583,51 +660,51 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     }
   }
 
-  // rhs = tau + joint springs - c   (reference dynamics.rs:298-315, :255-276)
-  for_bodies<Topo>(P, [&](auto ii) {
-    const int i = ii;
-    const int jt = Topo::jtype(P, i);
-    const int vo = Topo::voff(P, i);
-    if (jt == JRevolute) b[vo] = tau[vo] - b[vo];
-    else if (jt == JPrismatic) {
-      double t = tau[vo];
-      if (P.has_spring[i]) t += -P.spring_k[i] * (q[Topo::qoff(P, i)] - P.spring_l[i]);
-      b[vo] = t - b[vo];
-    } else if (jt == JFloating) {
+  if constexpr (kColumnsInPass2) {
+    if constexpr (DUMP) for_dofs_reverse<Topo>(P, finish_column);
+  } else {
+    // the same factorisation, right-looking and after the pass: eliminate the deepest dof first and
+    // update the entries of its ancestors in place; then x = L^-T rhs
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      const int jt = Topo::jtype(P, i);
+      const int vo = Topo::voff(P, i);
+      if (jt == JRevolute) b[vo] = tau[vo] - b[vo];
+      else if (jt == JPrismatic) {
+        double t = tau[vo];
+        if (P.has_spring[i]) t += -P.spring_k[i] * (q[Topo::qoff(P, i)] - P.spring_l[i]);
+        b[vo] = t - b[vo];
+      } else if (jt == JFloating) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) b[vo + k] = tau[vo + k] - b[vo + k];
-    }
-  });
-
-  // ------------------------------------------------------------------ sparse L^T D L solve
-  // H = L^T D L with unit lower-triangular L, eliminated from the last dof upwards so that
-  // branch-induced sparsity is preserved (no fill-in); entries with dof_anc == false are
-  // structural zeros and never touched.
-  for_dofs_reverse<Topo>(P, [&](auto kk) {
-    const int k = kk;
-    const double d = H[hidx(k, k)];
-    if (!(d > 0.0)) status |= kEnvNotSPD;
-    const double invd = 1.0 / d;
-#pragma unroll U
-    for (int i2 = 0; i2 < Topo::lim(k, NV); ++i2) {
-      const int i = k - 1 - i2;
-      if (i >= 0 && Topo::dof_anc(P, i, k)) {
-        const double a = H[hidx(k, i)] * invd;
-#pragma unroll U
-        for (int j = 0; j < Topo::lim(i + 1, NV); ++j)
-          if (j <= i && Topo::dof_anc(P, j, k)) H[hidx(i, j)] -= a * H[hidx(k, j)];
-        H[hidx(k, i)] = a;
+        for (int k = 0; k < 6; ++k) b[vo + k] = tau[vo + k] - b[vo + k];
       }
-    }
-    H[hidx(k, k)] = invd;
-  });
-  // x = L^-T b
-  for_dofs_reverse<Topo>(P, [&](auto kk) {
-    const int k = kk;
+    });
+    for_dofs_reverse<Topo>(P, [&](auto kk) {
+      const int k = kk;
+      const double d = H[hidx(k, k)];
+      if (!(d > 0.0)) status |= kEnvNotSPD;
+      const double invd = 1.0 / d;
 #pragma unroll U
-    for (int j = 0; j < Topo::lim(k, NV); ++j)
-      if (j < k && Topo::dof_anc(P, j, k)) b[j] -= H[hidx(k, j)] * b[k];
-  });
+      for (int i2 = 0; i2 < Topo::lim(k, NV); ++i2) {
+        const int i = k - 1 - i2;
+        if (i >= 0 && Topo::dof_anc(P, i, k)) {
+          const double a = H[hidx(k, i)] * invd;
+#pragma unroll U
+          for (int j = 0; j < Topo::lim(i + 1, NV); ++j)
+            if (j <= i && Topo::dof_anc(P, j, k)) H[hidx(i, j)] -= a * H[hidx(k, j)];
+          H[hidx(k, i)] = a;
+        }
+      }
+      H[hidx(k, k)] = invd;
+    });
+    for_dofs_reverse<Topo>(P, [&](auto kk) {
+      const int k = kk;
+#pragma unroll U
+      for (int j = 0; j < Topo::lim(k, NV); ++j)
+        if (j < k && Topo::dof_anc(P, j, k)) b[j] -= H[hidx(k, j)] * b[k];
+    });
+  }
+
   // x = D^-1 x ; x = L^-1 x
   for_dofs<Topo>(P, [&](auto kk) {
     const int k = kk;

@@ -238,10 +238,10 @@ GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q
       return;
     }
   }
-  // GP_CTRL_NONE: torques as loaded
-#pragma unroll U
-  for (int k = 0; k < Topo::nv(P); ++k) tau[k] = tau_in[k];
+  // GP_CTRL_NONE: tau keeps the torques the kernel loaded before its step loop
   (void)NV;
+  (void)U;
+  (void)tau_in;
 }
 
 GP_D bool all_finite(const double* a, int n) {
@@ -265,6 +265,9 @@ constexpr int step_min_blocks() {
 #ifndef GP_STEP_SYNC
 #define GP_STEP_SYNC 1
 #endif
+#ifndef GP_STEP_SYNC_EVERY
+#define GP_STEP_SYNC_EVERY 4  // barrier every so many time steps (power of two); profiles/r1_tuning.md
+#endif
 template <class Topo, int CONTACT, int INTEG>
 __global__ void __launch_bounds__(Topo::kBlockSize, (step_min_blocks<Topo, CONTACT>()))
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
@@ -284,6 +287,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   for (int k = 0; k < nv; ++k) {
     v[k] = A.v[(long long)k * A.ld + env];
     tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
+    tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
   }
   unsigned status = 0u;
   double cstate[2] = {0.0, 0.0};
@@ -300,7 +304,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
     // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
     // then share instruction-cache lines instead of each streaming the whole body from L2
-    __syncthreads();
+    if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
     }
     controller_tau<Topo>(P, A, q, v, tau_in, tau, cstate);
     if (INTEG == IntegSIE) {

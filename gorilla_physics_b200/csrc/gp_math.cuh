@@ -36,6 +36,8 @@ GP_HD V3 cross_sub(V3 acc, V3 a, V3 b) {
   return {fma(a.z, b.y, fma(-a.y, b.z, acc.x)), fma(a.x, b.z, fma(-a.z, b.x, acc.y)),
           fma(a.y, b.x, fma(-a.x, b.y, acc.z))};
 }
+// a * s + acc
+GP_HD V3 fma3(V3 a, double s, V3 acc) { return {fma(a.x, s, acc.x), fma(a.y, s, acc.y), fma(a.z, s, acc.z)}; }
 // acc + a . b
 GP_HD double dot_add(double acc, V3 a, V3 b) { return fma(a.z, b.z, fma(a.y, b.y, fma(a.x, b.x, acc))); }
 

@@ -172,6 +172,10 @@ struct StaticTopo {
   static const char* name() { return Spec::name(); }
   static constexpr int min_blocks(int contact) { return Spec::min_blocks(contact); }
   static constexpr int kBlockSize = Spec::block_size();
+  static constexpr bool kBatchedSinCos = Spec::batched_sincos();
+  // factorise H column by column inside the leaf-to-root pass (gp_dynamics.cuh): pays where the kernel
+  // has registers to spare, i.e. everywhere but the 14-dof trees
+  static constexpr bool kColumnsInPass2 = tables().nv < 12;
 
   struct FParent { template <int K> static constexpr unsigned long long at() { return (unsigned long long)(tables().parent[K] + 1); } };
   struct FJtype { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().jtype[K]; } };
@@ -238,6 +242,8 @@ struct DynTopo {
   static constexpr int NV = kMaxNV;
   static constexpr int kNVreal = kMaxNV;
   static constexpr int kBlockSize = 128;
+  static constexpr bool kBatchedSinCos = false;
+  static constexpr bool kColumnsInPass2 = true;
   static constexpr int kUnroll = 1;
   static const char* name() { return "generic"; }
 
@@ -273,18 +279,21 @@ struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static const char* name() { return "pendulum_R"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "double_pendulum_RR"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "cart_pole_PR"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
   static constexpr TopoData data() {
@@ -296,24 +305,28 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
   // barrier) and share instruction-cache lines; 246 registers, no spills (profiles/r1_tuning.md)
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 256; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
   static const char* name() { return "floating_F"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper1d_FPP"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper_FPR"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
+  static constexpr bool batched_sincos() { return true; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
   static constexpr TopoData data() {
@@ -323,6 +336,9 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
   static const char* name() { return "quadruped_F8R"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 256; }
+  // 8 angles in flight at the start of the step cost this kernel more in spills than the shared
+  // literals save (profiles/r1_tuning.md)
+  static constexpr bool batched_sincos() { return false; }
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
   static constexpr TopoData data() {
@@ -332,6 +348,7 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static const char* name() { return "navbot_F8Rz"; }
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 256; }
+  static constexpr bool batched_sincos() { return true; }
 };
 
 #undef GP_R

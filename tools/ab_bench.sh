@@ -1,13 +1,13 @@
 #!/bin/bash
-# Developer tool: A/B two builds of libgorilla_b200.so on the GPU box.
-#   tools/ab_bench.sh <libA.so> <libB.so> [workloads...]   -> gpurun_out/ab.txt
-A=$1; B=$2; shift 2
+# Developer tool: compare builds of libgorilla_b200.so on the GPU box (tuning builds: see csrc/Makefile).
+#   tools/ab_bench.sh "<libA.so> <libB.so> ..." [workloads...]   -> gpurun_out/ab.txt
+LIBS=$1; shift
 W=${@:-so101_contact so101 navbot_contact quadruped hopper_1d rimless_wheel double_pendulum cart_pole}
 mkdir -p gpurun_out
 : > gpurun_out/ab.txt
 for w in $W; do
-  for lib in $A $B; do
-    for rep in 1 2; do
+  for rep in 1 2; do
+    for lib in $LIBS; do
       GP_LIB_PATH=$lib python bench.py --workload $w --steps 10 --warmup 3 --inner 64 --no-cpu-baseline 2>/dev/null \
         | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('$w', '$lib', '%.4g' % d['value'], 'e2e %.4g' % d['e2e']['value'], d['clocks']['sm_mhz'])" >> gpurun_out/ab.txt
     done
