@@ -241,21 +241,19 @@ GP_D V3 contact_force(double z, V3 n, V3 vel, double k, double alpha, double mu)
   // z <= 0 inside the 1e-8 margin: the reference's powf(negative, 1.5) is NaN and
   // f64::max(NaN, 0) = 0, i.e. no force
   if (!(z > 0.0)) return v3z();
+  // straight-line from here: two independent reciprocal square roots (z^-1/2 for z^3/2, 1/|v_t| for the
+  // friction direction) and no further branches
   const double z_dot = -dot(vel, n);
-  const double zn = z * sqrt(z);  // z^(3/2)
+  const double zn = z * (z * gp_rsqrt(fmax(z, 1e-280)));  // z^(3/2); below 1e-280 the product underflows to 0 like the true value
   const double lambda = 1.5 * alpha * k;
-  const double pi_n = fmax(lambda * zn * z_dot + k * zn, 0.0);
-  V3 f = n * pi_n;
-  V3 v_t = vel + n * z_dot;
+  const double pi_n = fmax(zn * fma(lambda, z_dot, k), 0.0);  // lambda zn z_dot + k zn
+  const V3 v_t = fma3(n, z_dot, vel);
   const double vt2 = dot(v_t, v_t);
-  if (vt2 != 0.0) {
-    // -mu_eff * pi * v_t / |v_t| with mu_eff = mu * min(1, |v_t| / 1e-3):
-    //   |v_t| >  1e-3 : -mu pi / |v_t|        |v_t| <= 1e-3 : -mu pi / 1e-3
-    const double inv_norm = rsqrt(vt2);
-    const double g = -mu * pi_n * ((vt2 > 1e-6) ? inv_norm : 1e3);
-    f += v_t * g;
-  }
-  return f;
+  // -mu_eff * pi * v_t / |v_t| with mu_eff = mu * min(1, |v_t| / 1e-3):
+  //   |v_t| >  1e-3 : -mu pi / |v_t|        |v_t| <= 1e-3 : -mu pi / 1e-3   (v_t = 0 adds nothing)
+  const double inv_norm = gp_rsqrt(fmax(vt2, 1e-6));
+  const double g = -mu * pi_n * ((vt2 > 1e-6) ? inv_norm : 1e3);
+  return fma3(v_t, g, n * pi_n);
 }
 
 // ---- dynamics_continuous for one environment ------------------------------------------------
@@ -533,7 +531,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       }
     }
     if (!(dd > 0.0)) status |= kEnvNotSPD;
-    H[hidx(c, c)] = 1.0 / dd;
+    H[hidx(c, c)] = gp_rcp(dd);
     b[c] = rb;
   };
 
@@ -683,7 +681,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       const int k = kk;
       const double d = H[hidx(k, k)];
       if (!(d > 0.0)) status |= kEnvNotSPD;
-      const double invd = 1.0 / d;
+      const double invd = gp_rcp(d);
 #pragma unroll U
       for (int i2 = 0; i2 < Topo::lim(k, NV); ++i2) {
         const int i = k - 1 - i2;

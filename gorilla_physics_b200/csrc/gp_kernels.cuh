@@ -26,7 +26,7 @@ GP_D void integrate_pose(const double* qi, V3 w, V3 vl, double dt, double* qo) {
   const V3 t = cross(qv, vl) * 2.0;
   const V3 tdot = vl + t * s + cross(qv, t);
   const double nx = x + dx * dt, ny = y + dy * dt, nz = z + dz * dt, nw = s + dw * dt;
-  const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+  const double inv = gp_rsqrt(nx * nx + ny * ny + nz * nz + nw * nw);  // norm is 1 + O(dt^2)
   qo[0] = nx * inv;
   qo[1] = ny * inv;
   qo[2] = nz * inv;
