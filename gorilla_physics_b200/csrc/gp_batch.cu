@@ -4,6 +4,8 @@
 // There is NO CPU fallback in this file or anywhere in the library: without a usable CUDA
 // device every entry point returns GP_ERR_NO_DEVICE.
 #include <cmath>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "gp_host.h"
@@ -254,7 +256,8 @@ int64_t step_count(double final_time, double dt) {
 }
 
 int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
-                 int n_cp, long long env0 = 0, long long n_sub = -1, cudaStream_t stream = nullptr) {
+                 int n_cp, long long env0 = 0, long long n_sub = -1, cudaStream_t stream = nullptr,
+                 double* q_aos = nullptr, double* v_aos = nullptr) {
   if (n_sub < 0) n_sub = b->n;
   if (!stream) stream = b->stream;
   const gp_mechanism* m = b->mech;
@@ -283,6 +286,8 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   A.sc_state = b->sc_state ? b->sc_state + env0 : nullptr;
   A.n = n_sub;
   A.ld = b->ld;
+  A.q_aos_in = A.q_aos_out = q_aos;  // in place: every thread reads its environment before it writes it
+  A.v_aos_in = A.v_aos_out = v_aos;
   A.dt = dt;
   A.n_steps = n_steps;
   A.integrator = integrator;
@@ -348,7 +353,9 @@ int simulate_pipelined(gp_batch* b, double* q_host, double* v_host, const double
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->device);
   const long long wave = (long long)n_sm * m->table->block_size;
   const long long n_waves = (b->n + wave - 1) / wave;
-  const long long chunk = wave * ((n_waves + 3) / 4);
+  int n_chunks = 4;
+  if (const char* e = std::getenv("GP_PIPE_CHUNKS")) n_chunks = std::max(1, std::atoi(e));  // tuning only
+  const long long chunk = wave * ((n_waves + n_chunks - 1) / n_chunks);
   const size_t per_env = (size_t)(nq + nv + (tau_host ? nv : 0));
   for (int s = 0; s < 2; ++s) {
     if (!b->pipe_stream[s]) GP_CUDA(cudaStreamCreateWithFlags(&b->pipe_stream[s], cudaStreamNonBlocking));
@@ -365,15 +372,9 @@ int simulate_pipelined(gp_batch* b, double* q_host, double* v_host, const double
     double* sv = sq + (size_t)chunk * nq;
     double* stau = sv + (size_t)chunk * nv;
     const unsigned grid = (unsigned)((nc + kTile - 1) / kTile);
-    if (nq) {
-      GP_CUDA(cudaMemcpyAsync(sq, q_host + (size_t)env0 * nq, (size_t)nc * nq * sizeof(double), cudaMemcpyHostToDevice, st));
-      aos_to_soa_kernel<<<grid, 256, (size_t)kTile * nq * sizeof(double), st>>>(sq, b->q + env0, nc, b->ld, nq);
-      b->launches++;
-    }
+    if (nq) GP_CUDA(cudaMemcpyAsync(sq, q_host + (size_t)env0 * nq, (size_t)nc * nq * sizeof(double), cudaMemcpyHostToDevice, st));
     if (nv) {
       GP_CUDA(cudaMemcpyAsync(sv, v_host + (size_t)env0 * nv, (size_t)nc * nv * sizeof(double), cudaMemcpyHostToDevice, st));
-      aos_to_soa_kernel<<<grid, 256, (size_t)kTile * nv * sizeof(double), st>>>(sv, b->v + env0, nc, b->ld, nv);
-      b->launches++;
       if (tau_host) {
         GP_CUDA(cudaMemcpyAsync(stau, tau_host + (size_t)env0 * nv, (size_t)nc * nv * sizeof(double), cudaMemcpyHostToDevice, st));
         aos_to_soa_kernel<<<grid, 256, (size_t)kTile * nv * sizeof(double), st>>>(stau, b->tau + env0, nc, b->ld, nv);
@@ -381,19 +382,12 @@ int simulate_pipelined(gp_batch* b, double* q_host, double* v_host, const double
       }
     }
     GP_CUDA(cudaGetLastError());
-    int rc = launch_steps(b, dt, integrator, n_steps, controller, cp, n_cp, env0, nc, st);
+    // the step kernel reads the environment-major staging copy directly and writes the final state
+    // both to the batch (planes) and back to the staging copy: no layout-change kernels in between
+    int rc = launch_steps(b, dt, integrator, n_steps, controller, cp, n_cp, env0, nc, st, sq, sv);
     if (rc) return rc;
-    if (nq) {
-      soa_to_aos_kernel<<<grid, 256, (size_t)kTile * nq * sizeof(double), st>>>(b->q + env0, sq, nc, b->ld, nq);
-      GP_CUDA(cudaMemcpyAsync(q_host + (size_t)env0 * nq, sq, (size_t)nc * nq * sizeof(double), cudaMemcpyDeviceToHost, st));
-      b->launches++;
-    }
-    if (nv) {
-      soa_to_aos_kernel<<<grid, 256, (size_t)kTile * nv * sizeof(double), st>>>(b->v + env0, sv, nc, b->ld, nv);
-      GP_CUDA(cudaMemcpyAsync(v_host + (size_t)env0 * nv, sv, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-      b->launches++;
-    }
-    GP_CUDA(cudaGetLastError());
+    if (nq) GP_CUDA(cudaMemcpyAsync(q_host + (size_t)env0 * nq, sq, (size_t)nc * nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (nv) GP_CUDA(cudaMemcpyAsync(v_host + (size_t)env0 * nv, sv, (size_t)nc * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   GP_CUDA(cudaStreamSynchronize(b->pipe_stream[0]));
   GP_CUDA(cudaStreamSynchronize(b->pipe_stream[1]));

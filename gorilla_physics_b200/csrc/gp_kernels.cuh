@@ -281,11 +281,20 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   const int nq = Topo::nq(P), nv = Topo::nv(P);
 
   double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
+  if (A.q_aos_in) {
+    // one environment's values are contiguous: a warp reads one contiguous stretch, once per launch
 #pragma unroll U
-  for (int k = 0; k < nq; ++k) q[k] = A.q[(long long)k * A.ld + env];
+    for (int k = 0; k < nq; ++k) q[k] = A.q_aos_in[env * nq + k];
+#pragma unroll U
+    for (int k = 0; k < nv; ++k) v[k] = A.v_aos_in[env * nv + k];
+  } else {
+#pragma unroll U
+    for (int k = 0; k < nq; ++k) q[k] = A.q[(long long)k * A.ld + env];
+#pragma unroll U
+    for (int k = 0; k < nv; ++k) v[k] = A.v[(long long)k * A.ld + env];
+  }
 #pragma unroll U
   for (int k = 0; k < nv; ++k) {
-    v[k] = A.v[(long long)k * A.ld + env];
     tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
     tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
   }
@@ -355,6 +364,12 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
 #pragma unroll U
   for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
+  if (A.q_aos_out) {
+#pragma unroll U
+    for (int k = 0; k < nq; ++k) A.q_aos_out[env * nq + k] = q[k];
+#pragma unroll U
+    for (int k = 0; k < nv; ++k) A.v_aos_out[env * nv + k] = v[k];
+  }
   if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
   if (status) A.status[env] |= status;
 }

@@ -26,6 +26,14 @@ struct StepArgs {
   double cp[4];    // controller parameters
   double* ctrl_state;  // [2][ld] per-environment controller state (GP_CTRL_HOPPER_1D) or nullptr
   double* sc_state;    // [n_sc*8][ld] spring-contact state or nullptr
+  // simulate() through host buffers (gp_batch_simulate): environment-major staging copies of the
+  // reference's flat vectors, [n][n_q] / [n][n_v]. When set the kernel takes its initial state from
+  // *_aos_in instead of q / v, and writes the final state to *_aos_out as well as to q / v, so that no
+  // separate layout-change kernels sit between the copies and the rollout.
+  const double* q_aos_in;
+  const double* v_aos_in;
+  double* q_aos_out;
+  double* v_aos_out;
 };
 
 struct DynArgs {
