@@ -587,3 +587,82 @@ def test_quadruped_trot_to_position_on_the_gpu():
                        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
                        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
         assert abs((Rq.T @ v[e, 3:6])[0]) < 3e-1
+
+
+@pytest.mark.gpu
+def test_huge_joint_angles_take_the_library_reduction():
+    """The step kernels evaluate the joint sines/cosines of an environment together with a three-part
+    pi/2 reduction that is only valid below 1e5 rad; an environment holding a larger angle must fall back
+    to the library's exact (Payne-Hanek) reduction for all its joints (reference: libm sin_cos through
+    nalgebra, revolute.rs:97-102). Static and run-time-topology kernels, dynamics and one fused step."""
+    for factory in (lambda: Mechanism.from_model("so101"), lambda: Mechanism.from_model("double_pendulum")):
+        mech = factory()
+        desc = mech.desc()
+        orc = oracle_of(desc)
+        n = 64
+        q, v = random_states(desc, n, seed=77)
+        q[1, 0] = 123456.789            # one huge angle next to ordinary ones
+        q[2, -1] = -9.87654321e7
+        q[3, :] = 1.0e5                 # exactly at the switch-over
+        q[4, :] = np.nextafter(1.0e5, 0.0)
+        q[5, 0] = 3.0e15                # spacing of doubles here is 0.5 rad: still a defined angle
+        st = MechanismState(mech, n)
+        st.update(q, v)
+        vdot = st.dynamics(tau=None)
+        vdot_ref, _ = orc.batch_dynamics(q, v, None)
+        assert rel_err(vdot, vdot_ref) < TOL_DYN
+        dt = 1.0e-4
+        st.step(dt, n_steps=1)
+        q1, v1 = st.state()
+        q_ref, v_ref = orc.batch_rollout(q, v, dt, 1)
+        assert rel_err(v1, v_ref) < TOL_DYN
+        assert np.abs(q1 - q_ref).max() <= 1e-10 * np.maximum(np.abs(q_ref), 1.0).max()
+        assert not st.status().any()
+
+
+@pytest.mark.gpu
+def test_contact_force_law_corner_cases():
+    """Hunt-Crossley + regularised Coulomb (reference contact.rs:260-302) at the places where its branches
+    meet: penetrations from 1e-300 to 0.3 (the kernel takes z^(3/2) from a reciprocal square root seed),
+    the (0, 1e-8] margin where powf(negative, 1.5) is NaN and the force is zero, sliding speeds on both
+    sides of the 1e-3 regularisation, no sliding at all. One ball per environment with a contact point at
+    its origin (placed exactly) and one off-centre."""
+    mech = Mechanism.from_desc(models.ball())
+    mech.add_contact_point(1, (0.0, 0.0, 0.0))      # at the body origin: the penetration is exactly -t_z
+    mech.add_contact_point(1, (0.25, 0.0, -1.0e-3))  # and one off-centre point (moment arm), 1 mm lower
+    mech = _with_ground(mech, 0.0)
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    depths = [1e-300, 1e-200, 1e-30, 1e-17, 1e-12, 1e-9, 1e-6, 1e-3, 0.3, 0.0, -1e-9, -9.9e-9, -1.0e-8, -1.1e-8]
+    speeds = [0.0, 1e-30, 1e-9, 9.99e-4, 1.0e-3, 1.001e-3, 0.5]
+    states = []
+    for d in depths:
+        for s in speeds:
+            for vz in (-0.3, 0.0, 0.4):
+                qv = np.zeros(desc.n_q)
+                qv[3] = 1.0                    # identity quaternion (x, y, z, w)
+                qv[6] = -d                     # the origin sits d below the ground plane z = 0
+                vv = np.zeros(desc.n_v)
+                vv[3], vv[4], vv[5] = s, 0.5 * s, vz
+                states.append((qv, vv))
+    q = np.array([s[0] for s in states])
+    v = np.array([s[1] for s in states])
+    st = MechanismState(mech, len(states))
+    st.update(q, v)
+    vdot, cf = st.dynamics(tau=None, contact_forces=True)
+    vdot_ref, cf_ref = orc.batch_dynamics(q, v, None)
+    assert np.isfinite(cf).all() and np.isfinite(vdot).all()
+    assert (np.abs(cf_ref).reshape(len(states), -1).max(axis=1) > 0).sum() > len(states) // 3
+    # per contact point, relative to that point's own force (they span 300 orders of magnitude)
+    scale = np.maximum(np.abs(cf_ref).max(axis=2, keepdims=True), 1e-290)
+    assert (np.abs(cf - cf_ref) / scale).max() < TOL_DYN
+    # where the reference gives exactly zero force (margin, separating faster than the spring pushes) so do we
+    assert not cf[np.abs(cf_ref).max(axis=2) == 0.0].any()
+    assert rel_err(vdot, vdot_ref) < TOL_DYN
+    # and the step kernel's copy of the law (CONTACT == 1 instantiation) agrees with the oracle after one step
+    dt = 1.0e-4
+    st.step(dt, n_steps=1)
+    q1, v1 = st.state()
+    q_ref, v_ref = orc.batch_rollout(q, v, dt, 1)
+    assert rel_err(v1, v_ref) < TOL_DYN
+    assert not st.status().any()
