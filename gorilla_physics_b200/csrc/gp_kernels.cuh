@@ -6,6 +6,7 @@
 // runs them one by one). Mechanism constants arrive as one __grid_constant__ kernel parameter
 // (constant bank), so FP64 instructions read them as direct operands.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "gp_dynamics.cuh"
@@ -429,9 +430,29 @@ energy_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Ener
 // ---- launchers (table type in gp_launch.h) ------------------------------------------------
 inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
+// Threads per block of a step launch. The tuned size (one 256-thread block per SM for the big kernels)
+// assumes there are enough environments for every SM; a small batch (8 K environments is 32 such
+// blocks for 148 SMs) is cut into smaller blocks so that all SMs work, two warps on many SMs beating
+// eight warps on a few.
+inline int step_block_for(long long n, int tuned) {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n_sm = v;
+    else
+      n_sm = 148;
+  }
+  static const bool fixed = std::getenv("GP_STEP_FIXED_BLOCK") != nullptr;  // tuning only
+  int b = tuned;
+  while (!fixed && b > 32 && 4 * ((n + b - 1) / b) < 3 * n_sm) b /= 2;  // until 3/4 of the SMs have a block
+  return b;
+}
+
 template <class Topo>
 cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
-  const dim3 g(grid_for(A.n, Topo::kBlockSize)), b(Topo::kBlockSize);
+  const int block = step_block_for(A.n, Topo::kBlockSize);
+  const dim3 g(grid_for(A.n, block)), b(block);
   if (integ_class == IntegSIE) {
     if (contact == 0) step_kernel<Topo, 0, IntegSIE><<<g, b, 0, s>>>(P, A);
     else if (contact == 1) step_kernel<Topo, 1, IntegSIE><<<g, b, 0, s>>>(P, A);
