@@ -1,0 +1,29 @@
+#!/bin/bash
+# GPU box: one `ncu --set full` capture of the step kernel per bench workload, digested into
+# profiles/<round>_<workload>_step_kernel.json, plus the launch list of the default bench command and
+# profiles/flop_counts.json (what bench.py's roofline reads).   tools/refresh_profiles.sh r1
+R=${1:-r1}
+mkdir -p gpurun_out profiles
+declare -A N=( [so101_contact]=262144 [so101]=262144 [double_pendulum]=1048576 [cart_pole]=1048576 [rimless_wheel]=262144 [hopper_1d]=262144 [quadruped]=65536 [navbot_contact]=65536 )
+for w in so101_contact so101 double_pendulum cart_pole rimless_wheel hopper_1d quadruped navbot_contact; do
+  tools/ncu_capture.sh $w ${N[$w]} $R > /dev/null 2>&1
+  cp gpurun_out/${R}_$w.json gpurun_out/profile_${R}_${w}_step_kernel.json
+  python tools/ncu_stall_map.py gpurun_out/${R}_$w.ncu-rep 300 > gpurun_out/profile_${R}_${w}_stall_map.txt 2>&1
+  rm -f gpurun_out/${R}_$w.ncu-rep
+done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/profile_${R}_launches.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/profile_${R}_launches.log 2>&1
+python - <<PY
+import json, glob
+out = {"_how": "ncu --set full + smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum on one step-kernel launch of \`python bench.py --workload W --inner 64 --steps 3 --warmup 3\` (tools/refresh_profiles.sh on the GPU box, B200); flop = 2*dfma + dadd + dmul; per env-step = / (n_envs * 64). Per-workload summaries: profiles/${R}_<workload>_step_kernel.json (tools/ncu_summary.py)",
+       "flop_per_env_step": {}, "fp64_inst_per_env_step": {}, "dram_bytes_per_launch": {}, "fp64_pipe_pct_active": {}}
+for f in sorted(glob.glob("gpurun_out/profile_${R}_*_step_kernel.json")):
+    w = f.split("profile_${R}_")[1].replace("_step_kernel.json", "")
+    d = json.load(open(f))[0]
+    out["flop_per_env_step"][w] = round(d["flop_per_env_step"], 1)
+    out["fp64_inst_per_env_step"][w] = round(d["fp64_inst_per_env_step"], 1)
+    out["dram_bytes_per_launch"][w] = int(d["dram_bytes_read"] + d["dram_bytes_write"])
+    out["fp64_pipe_pct_active"][w] = round(d["fp64_pipe_pct_of_peak_active"], 1)
+json.dump(out, open("gpurun_out/profile_flop_counts.json", "w"), indent=1)
+print(json.dumps(out, indent=1))
+PY
