@@ -257,7 +257,8 @@ int64_t step_count(double final_time, double dt) {
 
 int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
                  int n_cp, long long env0 = 0, long long n_sub = -1, cudaStream_t stream = nullptr,
-                 double* q_aos = nullptr, double* v_aos = nullptr) {
+                 double* q_aos = nullptr, double* v_aos = nullptr, double* hist_q = nullptr,
+                 double* hist_v = nullptr) {
   if (n_sub < 0) n_sub = b->n;
   if (!stream) stream = b->stream;
   const gp_mechanism* m = b->mech;
@@ -288,6 +289,9 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   A.ld = b->ld;
   A.q_aos_in = A.q_aos_out = q_aos;  // in place: every thread reads its environment before it writes it
   A.v_aos_in = A.v_aos_out = v_aos;
+  A.hist_q = hist_q;
+  A.hist_v = hist_v;
+  A.hist_n = n_sub;
   A.dt = dt;
   A.n_steps = n_steps;
   A.integrator = integrator;
@@ -743,15 +747,48 @@ int gp_batch_simulate(gp_batch* b, double* q_host, double* v_host, const double*
   if (!history_q && !history_v) {
     if ((rc = launch_steps(b, dt, integrator, (int)n_steps, controller, cp, n_cp))) return rc;
   } else {
-    // simulate() records every state (reference simulate.rs:99-108)
+    // simulate() records every state (reference simulate.rs:99-108). The step kernel writes the state
+    // after each of its fused steps into a device-side record (environment-major, the layout of the
+    // reference's vectors), a block of steps per launch; two record buffers on two streams let the copy of
+    // one block to the host overlap the rollout of the next. One launch per block instead of a launch,
+    // two layout changes and two copies per step.
     const size_t sq = (size_t)b->n * m->n_q, sv = (size_t)b->n * m->n_v;
     if (history_q) std::memcpy(history_q, q_host, sq * sizeof(double));
     if (history_v) std::memcpy(history_v, v_host, sv * sizeof(double));
-    for (int64_t s = 0; s < n_steps; ++s) {
-      if ((rc = launch_steps(b, dt, integrator, 1, controller, cp, n_cp))) return rc;
-      if ((rc = gp_batch_get_state(b, history_q ? history_q + (s + 1) * sq : nullptr,
-                                   history_v ? history_v + (s + 1) * sv : nullptr)))
-        return rc;
+    if (n_steps > 0) {
+      const size_t per_step = (sq + sv) * sizeof(double);
+      int64_t block = (int64_t)((size_t)128 << 20) / (int64_t)(per_step ? per_step : 1);  // <= 128 MB per record buffer
+      if (block < 1) block = 1;
+      if (block > n_steps) block = n_steps;
+      for (int s = 0; s < 2; ++s) {
+        if (!b->pipe_stream[s]) GP_CUDA(cudaStreamCreateWithFlags(&b->pipe_stream[s], cudaStreamNonBlocking));
+        if ((rc = ensure(&b->pipe_stage[s], &b->pipe_stage_bytes[s], (size_t)block * per_step))) return rc;
+      }
+      GP_CUDA(cudaStreamSynchronize(b->stream));
+      cudaEvent_t done[2] = {nullptr, nullptr};
+      for (int s = 0; s < 2; ++s) GP_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+      int slot = 0;
+      for (int64_t s0 = 0; s0 < n_steps && rc == GP_OK; s0 += block, slot ^= 1) {
+        const int64_t ns = (s0 + block <= n_steps) ? block : n_steps - s0;
+        cudaStream_t st = b->pipe_stream[slot];
+        double* hq = b->pipe_stage[slot];
+        double* hv = hq + (size_t)block * sq;
+        // the rollout of this block continues the state the previous block (other stream) left behind
+        if (s0 > 0 && cudaStreamWaitEvent(st, done[slot ^ 1], 0) != cudaSuccess) rc = GP_ERR_CUDA;
+        if (rc == GP_OK) rc = launch_steps(b, dt, integrator, (int)ns, controller, cp, n_cp, 0, -1, st, nullptr, nullptr, hq, hv);
+        if (rc == GP_OK && cudaEventRecord(done[slot], st) != cudaSuccess) rc = GP_ERR_CUDA;
+        if (rc == GP_OK && history_q &&
+            cudaMemcpyAsync(history_q + (size_t)(s0 + 1) * sq, hq, (size_t)ns * sq * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+          rc = GP_ERR_CUDA;
+        if (rc == GP_OK && history_v &&
+            cudaMemcpyAsync(history_v + (size_t)(s0 + 1) * sv, hv, (size_t)ns * sv * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+          rc = GP_ERR_CUDA;
+      }
+      cudaStreamSynchronize(b->pipe_stream[0]);
+      cudaStreamSynchronize(b->pipe_stream[1]);
+      for (int s = 0; s < 2; ++s) cudaEventDestroy(done[s]);
+      if (rc == GP_ERR_CUDA) set_error("gp_batch_simulate: CUDA error while recording the history: %s", cudaGetErrorString(cudaGetLastError()));
+      if (rc) return rc;
     }
   }
   return gp_batch_get_state(b, q_host, v_host);

@@ -354,6 +354,16 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
 #pragma unroll U
       for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * A.dt;
     }
+    if (A.hist_q != nullptr && active) {  // (uniform test; history launches are bandwidth-bound anyway)
+      double* hq = A.hist_q + ((long long)s * A.hist_n + env) * nq;
+#pragma unroll U
+      for (int k = 0; k < nq; ++k) hq[k] = q[k];
+      if (A.hist_v != nullptr) {
+        double* hv = A.hist_v + ((long long)s * A.hist_n + env) * nv;
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) hv[k] = v[k];
+      }
+    }
   }
 
   if (!active) return;

@@ -34,6 +34,12 @@ struct StepArgs {
   const double* v_aos_in;
   double* q_aos_out;
   double* v_aos_out;
+  // simulate() with history (reference simulate.rs:99-108 pushes every state): when set, the state after
+  // fused step s of this launch is also written to hist_q[s][env][n_q] / hist_v[s][env][n_v]
+  // (environment-major like the reference's vectors; hist_n = environments per step record).
+  double* hist_q;
+  double* hist_v;
+  long long hist_n;
 };
 
 struct DynArgs {
