@@ -333,6 +333,14 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
       }
       A.ctrl_state = b->ctrl_state + env0;
       break;
+    case GP_CTRL_PENDULUM_GRAVITY_INVERSION:
+    case GP_CTRL_PENDULUM_ENERGY_SHAPING:
+    case GP_CTRL_PENDULUM_SWINGUP_BALANCE:
+      if (!(m->table->is_static && td.nb == 1 && td.jtype[0] == JRevolute)) {
+        set_error("the pendulum controllers need a single revolute joint (control/mod.rs:57-105)");
+        return GP_ERR_INVALID;
+      }
+      break;
     default:
       set_error("unknown controller %d", controller);
       return GP_ERR_INVALID;

@@ -161,6 +161,28 @@ GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q
     });
     return;
   }
+  if constexpr (Topo::NQ == 1 && Topo::NV == 1) {
+    if (A.controller >= GP_CTRL_PENDULUM_GRAVITY_INVERSION && A.controller <= GP_CTRL_PENDULUM_SWINGUP_BALANCE) {
+      // pendulum_gravity_inversion / pendulum_energy_shaping / pendulum_swing_up_and_balance,
+      // reference control/mod.rs:57-105 (state.bodies[0], state.treejoints[0].axis())
+      const double mass = P.mass[0];
+      const V3 com = V3{P.mc[0][0] / mass, P.mc[0][1] / mass, P.mc[0][2] / mass};
+      const double length_to_com = sqrt(dot(com, com));
+      const double qq = q[0], vv = v[0];
+      bool shaping = A.controller == GP_CTRL_PENDULUM_ENERGY_SHAPING;
+      if (A.controller == GP_CTRL_PENDULUM_SWINGUP_BALANCE) shaping = fabs(qq - 3.14159265358979323846) > 0.15;
+      if (shaping) {
+        const V3 omega = V3{P.axis[0][0] * vv, P.axis[0][1] * vv, P.axis[0][2] * vv};
+        const double E_desired = mass * kGravity * length_to_com;
+        const double KE = 0.5 * dot(omega, mul(lds3(P.J[0]), omega));
+        const double PE = mass * kGravity * length_to_com * (-cos(qq));
+        tau[0] = -0.1 * vv * (KE + PE - E_desired);
+      } else {
+        tau[0] = 2.0 * mass * kGravity * length_to_com * sin(qq) + -10.0 * vv;
+      }
+      return;
+    }
+  }
   if constexpr (Topo::NQ == 2 && Topo::NV == 2) {
     if (A.controller == GP_CTRL_ACROBOT_SWINGUP) {
       // swingup_acrobot, reference control/swingup.rs:9-69

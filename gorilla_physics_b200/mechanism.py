@@ -43,6 +43,9 @@ class Controller(enum.IntEnum):
     CARTPOLE_SWINGUP = 3   # reference control/swingup.rs:76-110, params [m_c, m_p, l]
     HOPPER_1D = 4          # reference control/energy_control.rs:24-101 (stateful), params
     #                        [k_spring, h_setpoint, body_leg_length, leg_foot_length]
+    PENDULUM_GRAVITY_INVERSION = 5   # reference control/mod.rs:57-67 (single revolute pendulum, no params)
+    PENDULUM_ENERGY_SHAPING = 6      # reference control/mod.rs:78-96
+    PENDULUM_SWINGUP_BALANCE = 7     # reference control/mod.rs:98-105
 
 
 def _f64(a, shape=None):

@@ -91,10 +91,16 @@ enum gp_controller {
                                   params: [kp, kd, clamp] (reference: 1000, 0.1, 10) */
   GP_CTRL_ACROBOT_SWINGUP = 2, /* swingup_acrobot, control/swingup.rs:9-69; params: [m, l] */
   GP_CTRL_CARTPOLE_SWINGUP = 3, /* swingup_cart_pole, control/swingup.rs:76-110; params: [m_c, m_p, l] */
-  GP_CTRL_HOPPER_1D = 4        /* Hopper1DController, control/energy_control.rs:24-101; params:
+  GP_CTRL_HOPPER_1D = 4,       /* Hopper1DController, control/energy_control.rs:24-101; params:
                                   [k_spring, h_setpoint, body_leg_length, leg_foot_length]. Stateful: two
                                   f64 per environment (leg_length_setpoint, v_vertical_prev) live in the
                                   batch, start at 0 and persist across gp_batch_step calls */
+  /* single revolute pendulum (one body), control/mod.rs:57-105; no parameters: mass, |centre of mass|,
+     moment and joint axis are read from the mechanism like the reference reads state.bodies[0] */
+  GP_CTRL_PENDULUM_GRAVITY_INVERSION = 5, /* u = 2 m g l_c sin q - 10 qd, control/mod.rs:57-67 */
+  GP_CTRL_PENDULUM_ENERGY_SHAPING = 6,    /* u = -0.1 qd (KE + PE - m g l_c), control/mod.rs:78-96 */
+  GP_CTRL_PENDULUM_SWINGUP_BALANCE = 7    /* energy shaping while |q - pi| > 0.15, else gravity inversion,
+                                             control/mod.rs:98-105 */
 };
 
 /* per-environment status bits (replace the reference's panics) */

@@ -808,6 +808,31 @@ int control_impl(const gpo_mechanism* m, const double* q, const double* v, int c
       tau[1] = 0.0;
       return 0;
     }
+    case 5: case 6: case 7: {  // pendulum_gravity_inversion / _energy_shaping / _swing_up_and_balance, control/mod.rs:57-105
+      if (m->nb != 1 || m->bodies[0].jtype != J_REV) return 1;
+      const Body& b = m->bodies[0];
+      double mass = b.mass;
+      V3 com{b.cross_part.x / mass, b.cross_part.y / mass, b.cross_part.z / mass};  // SpatialInertia::center_of_mass
+      double length_to_com = std::sqrt(com.x * com.x + com.y * com.y + com.z * com.z);
+      double qq = q[0], vv = v[0];
+      bool shaping = controller == 6 || (controller == 7 && std::fabs(qq - PI) > 0.15);
+      if (shaping) {
+        V3 omega{b.axis.x * vv, b.axis.y * vv, b.axis.z * vv};
+        double E_desired = mass * GRAVITY * length_to_com;
+        V3 Jw{b.moment.m[0][0] * omega.x + b.moment.m[0][1] * omega.y + b.moment.m[0][2] * omega.z,
+              b.moment.m[1][0] * omega.x + b.moment.m[1][1] * omega.y + b.moment.m[1][2] * omega.z,
+              b.moment.m[2][0] * omega.x + b.moment.m[2][1] * omega.y + b.moment.m[2][2] * omega.z};
+        double KE = 0.5 * (omega.x * Jw.x + omega.y * Jw.y + omega.z * Jw.z);
+        double PE = mass * GRAVITY * length_to_com * (-std::cos(qq));
+        double E_diff = KE + PE - E_desired;
+        tau[0] = -0.1 * vv * E_diff;
+      } else {
+        double gravity_inversion = 2.0 * mass * GRAVITY * length_to_com * std::sin(qq);
+        double damping = -10.0 * vv;
+        tau[0] = gravity_inversion + damping;
+      }
+      return 0;
+    }
     default:
       return 2;
   }

@@ -85,7 +85,8 @@ int gpo_step(const gpo_mechanism* m, double* q, double* v, const double* tau, do
              int integrator);
 
 /* controllers: 0 none (tau as given / zeros), 1 SO101 PD [kp,kd,clamp],
- * 2 swingup_acrobot [m,l], 3 swingup_cart_pole [m_c,m_p,l]; in gpo_rollout / gpo_batch_rollout also
+ * 2 swingup_acrobot [m,l], 3 swingup_cart_pole [m_c,m_p,l], 5/6/7 pendulum_gravity_inversion /
+ * pendulum_energy_shaping / pendulum_swing_up_and_balance (control/mod.rs:57-105, no params); in gpo_rollout / gpo_batch_rollout also
  * 4 Hopper1DController [k_spring,h_setpoint,body_leg_length,leg_foot_length] (stateful, starts at 0,0) */
 int gpo_control(const gpo_mechanism* m, const double* q, const double* v, int controller,
                 const double* params, double* tau_out);

@@ -28,6 +28,14 @@ def rod_pendulum(m=5.0, l=7.0, rod_to_world=None, axis=(0.0, 1.0, 0.0), point_ma
     return d
 
 
+def hanging_rod_pendulum(m=5.0, l=7.0):
+    """reference control/mod.rs:147-165 fixture: rod hanging along -z from the joint, axis +y, q = 0 at the bottom"""
+    d = MechanismDesc()
+    d.add_body(0, REVOLUTE, axis=(0.0, 1.0, 0.0), init_iso=iso(),
+               moment=np.diag([m * l * l / 3.0, m * l * l / 3.0, 0.0]), cross_part=(0.0, 0.0, -m * l / 2.0), mass=m)
+    return d
+
+
 def double_pendulum_horizontal(m=5.0, l=7.0, axis=(0.0, 1.0, 0.0)):
     """reference dynamics.rs:1038-1087 / examples/acrobot.rs (axis -y, m=1)"""
     d = MechanismDesc()

@@ -622,3 +622,35 @@ def test_hopper_servo_attitude_position_control():  # control/hopper_control.rs:
     q, v, poses, twists, body_vel = _hopper_test_loop(o, q, v, dt, int(20.0 / dt), hip_torque)
     assert abs(poses[2, 4]) < 1e-1 and abs(_pitch(poses[2, 0:4])) < 1e-1
     assert abs(body_vel[0]) < 1e-1 and abs(twists[2, 1]) < 1e-1
+
+
+def test_pendulum_gravity_inversion():  # control/mod.rs:146-194 (RK4, dt=1e-2, 200 s)
+    m, l = 5.0, 7.0
+    o = oracle_of(models.hanging_rod_pendulum(m, l))
+    n = simulate_step_count(200.0, 1e-2)
+    q, v = o.rollout([0.1], [0.0], 1e-2, n, RK4, controller=5)
+    assert abs(q[0] - PI) < 1e-3, "Pendulum should swing to the top"
+    assert abs(v[0]) < 1e-4, "Pendulum should stop at the top"
+
+
+def test_pendulum_energy_shaping():  # control/mod.rs:196-240 (SemiImplicitEuler, dt=1e-2, 50 s)
+    m, l = 5.0, 7.0
+    o = oracle_of(models.hanging_rod_pendulum(m, l))
+    n = simulate_step_count(50.0, 1e-2)
+    q, v, hq, hv = o.rollout([0.0], [0.1], 1e-2, n, SIE, controller=6, history=True)
+    assert hq[:, 0].max() > 3.0, "Pendulum should swing to near the top"
+
+
+def test_pendulum_swing_up_and_balance():  # control/mod.rs:98-105
+    m, l = 5.0, 7.0
+    o = oracle_of(models.hanging_rod_pendulum(m, l))
+    # (the reference has no test of the combined law; |q - pi| is taken without wrapping, so it only
+    # balances on the first approach. Checked here: which branch it takes, and the two closed forms.)
+    tau_shape = o.control([1.0], [0.5], 6, [0.0])
+    tau_inv = o.control([PI - 0.1], [0.5], 5, [0.0])
+    assert o.control([1.0], [0.5], 7, [0.0])[0] == tau_shape[0]
+    assert o.control([PI - 0.1], [0.5], 7, [0.0])[0] == tau_inv[0]
+    # closed forms (control/mod.rs:61-66, :88-95) with l_c = l / 2, J about the joint axis = m l^2 / 3
+    assert tau_inv[0] == pytest.approx(2.0 * m * GRAVITY * (l / 2) * math.sin(PI - 0.1) - 10.0 * 0.5, rel=1e-14)
+    ke = 0.5 * (m * l * l / 3.0) * 0.25
+    assert tau_shape[0] == pytest.approx(-0.1 * 0.5 * (ke - m * GRAVITY * (l / 2) * math.cos(1.0) - m * GRAVITY * l / 2), rel=1e-13)

@@ -264,6 +264,31 @@ def test_in_kernel_controllers_match_oracle():
     st.update(q, v)
     st.step(1e-2, n_steps=200, controller=Controller.CARTPOLE_SWINGUP, ctrl_params=(1.0, 2.0, 1.0))
     assert_rollout_parity(orc, q, v, st.q, st.v, 1e-2, 200, controller=3, params=(1.0, 2.0, 1.0))
+    # single pendulum laws (reference control/mod.rs:57-105): gravity inversion, energy shaping, swing-up + balance
+    mech = Mechanism.from_desc(models.hanging_rod_pendulum())
+    assert mech.kernel_variant == "pendulum_R"
+    orc = oracle_of(mech)
+    q, v = random_states(mech.desc(), n, seed=14, q_range=math.pi, v_range=1.0)
+    q[:8, 0] = math.pi + np.linspace(-0.2, 0.2, 8)  # both sides of the 0.15 rad switch of the combined law
+    for ctrl, integ, oi in ((Controller.PENDULUM_GRAVITY_INVERSION, Integrator.RungeKutta4, 2),
+                            (Controller.PENDULUM_ENERGY_SHAPING, Integrator.SemiImplicitEuler, 0),
+                            (Controller.PENDULUM_SWINGUP_BALANCE, Integrator.RungeKutta4, 2)):
+        st = MechanismState(mech, n)
+        st.update(q, v)
+        st.step(1e-2, n_steps=1, integrator=integ, controller=ctrl)
+        q_ref, v_ref = orc.batch_rollout(q, v, 1e-2, 1, integrator=oi, controller=int(ctrl))
+        assert rel_err(st.q, q_ref) < TOL_STEP and rel_err(st.v, v_ref) < TOL_STEP
+        st.update(q, v)
+        st.step(1e-2, n_steps=300, integrator=integ, controller=ctrl)
+        assert_rollout_parity(orc, q, v, st.q, st.v, 1e-2, 300, integrator=oi, controller=int(ctrl))
+    # the reference's own two outcome tests (control/mod.rs:146-240) as ONE fused launch each
+    st = MechanismState(mech, 1)
+    st.update(np.array([[0.1]]), np.array([[0.0]]))
+    st.step(1e-2, n_steps=20000, integrator=Integrator.RungeKutta4, controller=Controller.PENDULUM_GRAVITY_INVERSION)
+    assert abs(st.q[0, 0] - math.pi) < 1e-3 and abs(st.v[0, 0]) < 1e-4
+    # other topologies are refused
+    with pytest.raises(Exception):
+        MechanismState(Mechanism.from_model("so101"), 4).step(1e-3, controller=Controller.PENDULUM_ENERGY_SHAPING)
 
 
 def test_full_size_replication_property():
