@@ -278,9 +278,10 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
   joint_sincos<Topo>(P, q, sn, cs);
   SV vel[NB], acc[NB], frc[NB];
   constexpr int NHS = (CONTACT == 2) ? kMaxHS : 1;
-  // spring contacts (contact.rs:133-186) need world poses and carry state; only the run-time-topology
-  // kernels in the general contact mode implement them (gp_mechanism picks those kernels)
-  constexpr bool SPRINGS = !Topo::kStatic && CONTACT == 2;
+  // spring contacts (contact.rs:133-186) need world poses and carry state; the run-time-topology kernels
+  // and the single-floating-body specialisation implement them, in the general contact mode
+  // (gp_mechanism picks a kernel that does)
+  constexpr bool SPRINGS = Topo::kSprings && CONTACT == 2;
   constexpr bool WORLD = ((CONTACT != 0) && DUMP) || SPRINGS;
   V3 hn[CONTACT ? NB : 1][NHS];     // halfspace normals in body coordinates
   double ho[CONTACT ? NB : 1][NHS];  // plane offsets: signed distance of x is hn.x - ho

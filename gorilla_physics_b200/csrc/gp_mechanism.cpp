@@ -185,12 +185,12 @@ int finalize_mechanism(gp_mechanism* m) {
   }
 
   // kernel variant: first compiled specialisation whose signature matches, else generic
-  // (spring contacts are only implemented by the run-time-topology kernels)
+  // (spring contacts: only kernels that implement them)
   int nvar = 0;
   const KernelTable* const* vars = all_variants(&nvar);
   m->table = vars[nvar - 1];
-  for (int k = 0; k < nvar - 1 && m->n_sc() == 0; ++k)
-    if (topo_matches(vars[k]->topo, td)) {
+  for (int k = 0; k < nvar - 1; ++k)
+    if (topo_matches(vars[k]->topo, td) && (m->n_sc() == 0 || vars[k]->springs)) {
       m->table = vars[k];
       break;
     }

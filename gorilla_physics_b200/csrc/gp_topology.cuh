@@ -173,6 +173,9 @@ struct StaticTopo {
   static constexpr int min_blocks(int contact) { return Spec::min_blocks(contact); }
   static constexpr int kBlockSize = Spec::block_size();
   static constexpr bool kBatchedSinCos = Spec::batched_sincos();
+  // stateful SpringContact legs (reference contact.rs:74-94, :133-186) compiled into the general-contact
+  // kernels of this topology: the single floating body (SLIP, helpers.rs:308-337)
+  static constexpr bool kSprings = Spec::springs();
   // factorise H column by column inside the leaf-to-root pass (gp_dynamics.cuh): pays where the kernel
   // has registers to spare, i.e. everywhere but the 14-dof trees
   static constexpr bool kColumnsInPass2 = tables().nv < 12;
@@ -243,6 +246,7 @@ struct DynTopo {
   static constexpr int kNVreal = kMaxNV;
   static constexpr int kBlockSize = 128;
   static constexpr bool kBatchedSinCos = false;
+  static constexpr bool kSprings = true;
   static constexpr bool kColumnsInPass2 = true;
   static constexpr int kUnroll = 1;
   static const char* name() { return "generic"; }
@@ -280,6 +284,7 @@ struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
@@ -287,6 +292,7 @@ struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, co
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
@@ -294,6 +300,7 @@ struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
   static constexpr TopoData data() {
@@ -306,6 +313,7 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 256; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
@@ -313,6 +321,7 @@ struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, b
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return true; }
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
@@ -320,6 +329,7 @@ struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (c
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
@@ -327,6 +337,7 @@ struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(s
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
   static constexpr TopoData data() {
@@ -339,6 +350,7 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
   // 8 angles in flight at the start of the step cost this kernel more in spills than the shared
   // literals save (profiles/r1_tuning.md)
   static constexpr bool batched_sincos() { return false; }
+  static constexpr bool springs() { return false; }
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
   static constexpr TopoData data() {
@@ -349,6 +361,7 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static constexpr int min_blocks(int) { return 1; }
   static constexpr int block_size() { return 256; }
   static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
 };
 
 #undef GP_R

@@ -519,14 +519,19 @@ def test_free_velocity_and_armature():
     assert rel_err(vf, ref) < TOL_DYN
 
 
-def test_spring_contact_slip_matches_oracle():
+@pytest.mark.parametrize("generic", [False, True], ids=["static", "generic"])
+def test_spring_contact_slip_matches_oracle(generic):
     """SpringContact (reference contact.rs:74-94, :133-186): the stateful SLIP leg. Many hoppers with
     different launch speeds, stepped on the GPU and in the oracle, the apex logic of SLIP_hopping
-    (contact.rs:878-889) applied on the host to both; state AND spring-contact state must agree."""
+    (contact.rs:878-889) applied on the host to both; state AND spring-contact state must agree.
+    Single-floating-body specialisation and the run-time-topology kernel."""
     mech = Mechanism.from_model("slip")
     mech.add_halfspace((0, 0, 1), -0.3)
-    assert mech.kernel_variant == "generic" and mech.n_spring_contacts == 1
+    assert mech.kernel_variant == "floating_F" and mech.n_spring_contacts == 1
     orc = oracle_of(mech)
+    if generic:
+        mech = generic_twin(mech)
+        assert mech.n_spring_contacts == 1 and mech.n_halfspaces == 1
     a = math.radians(45.0)
     direction = np.array([math.sin(a), 0.0, -math.cos(a)])
     direction /= np.linalg.norm(direction)

@@ -22,7 +22,7 @@ using namespace gp;
 
 namespace gp {
 // the debug build has no kernels: satisfy the variant registry with empty tables
-static KernelTable dummy{"debug", TopoData{}, false, 128, nullptr, nullptr, nullptr};
+static KernelTable dummy{"debug", TopoData{}, false, 128, true, nullptr, nullptr, nullptr};
 const KernelTable* variant_generic() { return &dummy; }
 const KernelTable* variant_pendulum() { return &dummy; }
 const KernelTable* variant_double_pendulum() { return &dummy; }
