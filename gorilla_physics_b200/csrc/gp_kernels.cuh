@@ -481,18 +481,31 @@ inline int step_block_for(long long n, int tuned) {
   return b;
 }
 
+// The Runge-Kutta step kernels of a topology live in their own translation unit (variants/*_rk.cu defines
+// GP_TU_RUNGE_KUTTA and instantiates launch_step_rk explicitly; the other unit only declares it), so that the
+// two halves of a big topology compile in parallel.
 template <class Topo>
-cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
+cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, const StepArgs& A);
+#ifdef GP_TU_RUNGE_KUTTA
+template <class Topo>
+cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, const StepArgs& A) {
   const int block = step_block_for(A.n, Topo::kBlockSize);
   const dim3 g(grid_for(A.n, block)), b(block);
-  if (integ_class == IntegSIE) {
-    if (contact == 0) step_kernel<Topo, 0, IntegSIE><<<g, b, 0, s>>>(P, A);
-    else if (contact == 1) step_kernel<Topo, 1, IntegSIE><<<g, b, 0, s>>>(P, A);
-    else step_kernel<Topo, 2, IntegSIE><<<g, b, 0, s>>>(P, A);
-  } else {
-    // the Runge-Kutta kernels are instantiated for the general contact mode only
-    step_kernel<Topo, 2, IntegRK><<<g, b, 0, s>>>(P, A);
-  }
+  if (contact == 0) step_kernel<Topo, 0, IntegRK><<<g, b, 0, s>>>(P, A);
+  else if (contact == 1) step_kernel<Topo, 1, IntegRK><<<g, b, 0, s>>>(P, A);
+  else step_kernel<Topo, 2, IntegRK><<<g, b, 0, s>>>(P, A);
+  return cudaGetLastError();
+}
+#endif
+
+template <class Topo>
+cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
+  if (integ_class != IntegSIE) return launch_step_rk<Topo>(contact, s, P, A);
+  const int block = step_block_for(A.n, Topo::kBlockSize);
+  const dim3 g(grid_for(A.n, block)), b(block);
+  if (contact == 0) step_kernel<Topo, 0, IntegSIE><<<g, b, 0, s>>>(P, A);
+  else if (contact == 1) step_kernel<Topo, 1, IntegSIE><<<g, b, 0, s>>>(P, A);
+  else step_kernel<Topo, 2, IntegSIE><<<g, b, 0, s>>>(P, A);
   return cudaGetLastError();
 }
 template <class Topo>

@@ -3,6 +3,8 @@
 #include "../gp_kernels.cuh"
 
 namespace gp {
+// Runge-Kutta kernels: variant_cart_pole_rk.cu
+extern template cudaError_t launch_step_rk<StaticTopo<SpecCartPole>>(int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_cart_pole() {
   static const KernelTable t = make_static_table<StaticTopo<SpecCartPole>, SpecCartPole>();
   return &t;

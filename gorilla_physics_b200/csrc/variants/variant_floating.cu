@@ -3,6 +3,8 @@
 #include "../gp_kernels.cuh"
 
 namespace gp {
+// Runge-Kutta kernels: variant_floating_rk.cu
+extern template cudaError_t launch_step_rk<StaticTopo<SpecFloating>>(int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_floating() {
   static const KernelTable t = make_static_table<StaticTopo<SpecFloating>, SpecFloating>();
   return &t;

@@ -3,6 +3,8 @@
 #include "../gp_kernels.cuh"
 
 namespace gp {
+// Runge-Kutta kernels: variant_navbot_rk.cu
+extern template cudaError_t launch_step_rk<StaticTopo<SpecNavbot>>(int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_navbot() {
   static const KernelTable t = make_static_table<StaticTopo<SpecNavbot>, SpecNavbot>();
   return &t;
