@@ -1,0 +1,126 @@
+"""The oracle against a SECOND, independently derived CPU restatement (tests/featherstone_ref.py:
+textbook body-coordinate RNEA + CRBA with dense 6x6 Pluecker algebra and numpy.linalg.solve) and against
+frozen golden vectors (tests/golden/oracle_frozen.json, written by tools/make_oracle_golden.py).
+
+Why: the reference holds no known-answer test for SO-101, for the navbot or for the contact force law on
+its own (SURVEY.md §8c "unpinned"); the oracle's other models are pinned by the reference's tests in
+test_oracle_golden.py. Two formulations that share no code agreeing to 1e-11 is the strongest CPU-side
+pin available here without a Rust toolchain; the frozen vectors keep the oracle from drifting afterwards.
+"""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from gorilla_physics_b200 import FLOATING, Mechanism, quat_from_euler
+from gorilla_physics_b200.desc import JOINT_NQ
+from oracle.binding import OracleMechanism
+from tests import featherstone_ref as fs
+from tests import models
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "oracle_frozen.json"
+TOL = 1e-11  # relative to the largest entry of the quantity (observed: <= 1e-13)
+
+
+def states(desc, n, seed, q_range=1.0, v_range=1.0, base_t=(0.0, 0.0, 0.0), t_jitter=0.3, rpy_jitter=0.5):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, desc.n_q))
+    v = rng.uniform(-v_range, v_range, size=(n, desc.n_v))
+    for jt, qo in zip(desc.joint_type, desc.q_offsets()):
+        if jt == FLOATING:
+            for e in range(n):
+                q[e, qo:qo + 4] = quat_from_euler(*rng.uniform(-rpy_jitter, rpy_jitter, size=3))
+            q[:, qo + 4:qo + 7] = np.asarray(base_t) + rng.uniform(-t_jitter, t_jitter, size=(n, 3))
+        elif JOINT_NQ[int(jt)] == 1:
+            q[:, qo] = rng.uniform(-q_range, q_range, size=n)
+    tau = rng.uniform(-1.0, 1.0, size=(n, desc.n_v))
+    return q, v, tau
+
+
+def spring_pair_desc():
+    return models.spring_pair()[0]
+
+
+# name -> (description factory, state kwargs, must the sample contain active contacts?)
+CASES = {
+    "so101": (lambda: Mechanism.from_model("so101").desc(), dict(), False),
+    "so101_contact": (lambda: models.so101_with_contact().desc(), dict(q_range=2.6), True),
+    "navbot": (lambda: Mechanism.from_model("navbot").desc(), dict(base_t=(0, 0, 0.075), t_jitter=0.01, rpy_jitter=0.1), False),
+    "navbot_contact": (lambda: models.navbot_with_contact().desc(),
+                       dict(base_t=(0, 0, 0.02), t_jitter=0.01, rpy_jitter=0.1, q_range=0.2), True),
+    "quadruped": (lambda: models.quadruped_on_ground().desc(), dict(base_t=(0, 0, 0.3), t_jitter=0.1, rpy_jitter=0.3), True),
+    "hopper_1d": (lambda: models.hopper1d_on_ground().desc(), dict(base_t=(0, 0, -8.0), t_jitter=0.5, rpy_jitter=0.2), True),
+    "rimless_wheel": (lambda: models.rimless_wheel_on_slope().desc(), dict(base_t=(0, 0, -10.5), t_jitter=1.0, rpy_jitter=0.4), True),
+    "spring_pair": (spring_pair_desc, dict(), False),
+    "double_pendulum": (lambda: Mechanism.from_model("double_pendulum").desc(), dict(q_range=math.pi), False),
+    "cart_pole": (lambda: Mechanism.from_model("cart_pole").desc(), dict(q_range=math.pi), False),
+}
+for _s in range(8):
+    CASES[f"random_tree_{_s}"] = ((lambda s=_s: models.random_tree(s, 3 + s)), dict(), False)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-9))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_independent_featherstone_derivation(name):
+    factory, kw, need_contact = CASES[name]
+    desc = factory()
+    orc = OracleMechanism(desc)
+    ref = fs.Model(desc)
+    q, v, tau = states(desc, 12, seed=11, **kw)
+    active = 0
+    for e in range(q.shape[0]):
+        a = orc.dynamics(q[e], v[e], tau[e], want="all")
+        b = fs.dynamics(ref, q[e], v[e], tau[e])
+        cf_b = b["contact_forces"][orc.cp_order] if orc.n_cp else b["contact_forces"]  # oracle lists points body-major
+        active += int((np.abs(cf_b).sum(axis=1) > 0).sum())
+        assert rel_err(a["mass_matrix"], b["mass_matrix"]) < TOL
+        assert rel_err(a["bias"], b["bias"]) < TOL
+        assert rel_err(a["contact_forces"], cf_b) < TOL
+        assert rel_err(a["vdot"], b["vdot"]) < 1e-10  # north-star per-step tolerance (conditioning of H included)
+    if need_contact:
+        assert active > 0, "sample never touched the ground: the contact path was not exercised"
+
+
+def test_contact_force_law_corners_match_independent_statement():
+    """C2 (reference contact.rs:260-302) through the oracle: a unit point mass on a floating joint, one
+    contact point at its origin, so the reported contact force IS the force law; compared with the plain
+    numpy statement of the law at its corners (margin, slip regularisation, separating normal velocity)."""
+    from gorilla_physics_b200 import MechanismDesc
+    d = MechanismDesc()
+    d.add_body(0, FLOATING, moment=np.eye(3), mass=1.0)
+    d.add_contact_point(1, (0.0, 0.0, 0.0), k=30e3)
+    n = np.array([0.2, -0.1, 1.0])
+    n /= np.linalg.norm(n)
+    d.add_halfspace(n, 0.0, alpha=0.7, mu=0.4)
+    orc = OracleMechanism(d)
+    for z in (-1e-9, 0.0, 1e-300, 1e-12, 1e-6, 1e-3, 0.05, 0.3):
+        for vel in ((0, 0, 0), (0, 0, -1.0), (0, 0, 5.0), (1e-4, 0, 0), (1e-3, 0, 0), (2e-3, 1e-3, -0.1), (3.0, -2.0, 0.5)):
+            q = np.concatenate([[0, 0, 0, 1.0], -z * n])
+            v = np.concatenate([[0.3, -0.2, 0.1], vel])  # angular velocity does not move the origin
+            got = orc.dynamics(q, v, None, want="all")["contact_forces"][0]
+            want = fs.contact_force_law(z, np.asarray(vel, dtype=float), n, 30e3, 0.7, 0.4)
+            assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1.0), (z, vel, got, want)
+
+
+def test_frozen_golden_vectors():
+    """tools/make_oracle_golden.py wrote these once from the oracle (after the checks above passed)."""
+    gold = json.loads(GOLDEN.read_text())
+    for name, rec in gold["cases"].items():
+        desc = CASES[name][0]()
+        orc = OracleMechanism(desc)
+        for s in rec["samples"]:
+            a = orc.dynamics(np.array(s["q"]), np.array(s["v"]), np.array(s["tau"]), want="all")
+            assert rel_err(s["vdot"], a["vdot"]) < 1e-12, name
+            assert rel_err(s["contact_forces"], a["contact_forces"]) < 1e-12, name
+        q, v = np.array(rec["rollout"]["q0"]), np.array(rec["rollout"]["v0"])
+        q1, v1 = orc.rollout(q, v, rec["rollout"]["dt"], rec["rollout"]["steps"])
+        assert rel_err(rec["rollout"]["q1"], q1) < 1e-9, name
+        assert rel_err(rec["rollout"]["v1"], v1) < 1e-9, name

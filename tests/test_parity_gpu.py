@@ -696,3 +696,50 @@ def test_contact_force_law_corner_cases():
     q_ref, v_ref = orc.batch_rollout(q, v, dt, 1)
     assert rel_err(v1, v_ref) < TOL_DYN
     assert not st.status().any()
+
+
+@pytest.mark.parametrize("name", ["so101", "so101_contact", "navbot", "navbot_contact", "quadruped", "hopper_1d",
+                                  "rimless_wheel"])
+def test_committed_golden_vectors(name):
+    """The CUDA path against tests/golden/oracle_frozen.json (tools/make_oracle_golden.py): the models the
+    reference holds no known-answer test for, frozen after the oracle was cross-checked against an
+    independent derivation (tests/test_oracle_independent.py). No oracle code runs in this test."""
+    import json
+    from pathlib import Path
+    from tests.test_oracle_independent import CASES
+    rec = json.loads((Path(__file__).resolve().parent / "golden" / "oracle_frozen.json").read_text())["cases"][name]
+    mech = Mechanism.from_desc(CASES[name][0]())
+    q = np.array([s["q"] for s in rec["samples"]])
+    v = np.array([s["v"] for s in rec["samples"]])
+    tau = np.array([s["tau"] for s in rec["samples"]])
+    st = MechanismState(mech, len(q))
+    st.update(q, v)
+    vdot, cf = st.dynamics(tau=tau, contact_forces=True)
+    assert rel_err(vdot, np.array([s["vdot"] for s in rec["samples"]])) < TOL_DYN
+    if mech.desc().n_contact_points:
+        assert rel_err(cf, np.array([s["contact_forces"] for s in rec["samples"]])) < TOL_DYN
+    ro = rec["rollout"]
+    st = MechanismState(mech, 1)
+    st.update(np.array([ro["q0"]]), np.array([ro["v0"]]))
+    st.step(ro["dt"], integrator=Integrator.SemiImplicitEuler, n_steps=ro["steps"])
+    q1, v1 = st.state()
+    assert rel_err(q1, np.array([ro["q1"]])) < TOL_ROLLOUT
+    assert rel_err(v1, np.array([ro["v1"]]), floor=1e-3) < 1e-6  # 50 steps through stiff contact onset
+
+
+@pytest.mark.parametrize("name", ["so101_contact", "navbot_contact", "quadruped"])
+def test_dynamics_against_independent_featherstone_derivation(name):
+    """The CUDA path directly against the textbook body-coordinate RNEA + CRBA in numpy
+    (tests/featherstone_ref.py), which shares no code with the oracle or the kernels."""
+    from tests import featherstone_ref as fs
+    from tests.test_oracle_independent import CASES, states
+    factory, kw, _ = CASES[name]
+    desc = factory()
+    mech = Mechanism.from_desc(desc)
+    q, v, tau = states(desc, 32, seed=5, **kw)
+    st = MechanismState(mech, len(q))
+    st.update(q, v)
+    vdot = st.dynamics(tau=tau)
+    ref = fs.Model(desc)
+    want = np.array([fs.dynamics(ref, q[e], v[e], tau[e])["vdot"] for e in range(len(q))])
+    assert rel_err(vdot, want) < TOL_DYN
