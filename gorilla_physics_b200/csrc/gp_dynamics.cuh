@@ -31,7 +31,24 @@ struct DynOut {
   long long ld;
   long long env;
   double* sc_state;  // spring-contact state planes [(s*8 + k)*ld + env] of the batch, or nullptr
+  // contact points as (x, y, z, k) rows in SHARED memory, or nullptr (then MechParams is indexed): the
+  // per-lane hit list below reads them with a lane-dependent index, which shared memory serves in one
+  // access where the constant bank would replay once per distinct address
+  const double* cp_table = nullptr;
 };
+
+// Topologies whose bodies carry several contact points (Topo::kContactList) test all the points of a
+// body first (three FMAs and a compare per point, warp-uniform) and then run the force law over a
+// PER-LANE list of the points in contact: a warp iterates max-over-lanes(points in contact) times
+// instead of once per point that ANY of its 32 environments has in contact. A wheel or a rimless
+// wheel's spokes touch the ground with one or two of their eight points, but with different ones in
+// different environments (profiles/r1_tuning.md).
+#ifndef GP_ROOT_INVERSE
+#define GP_ROOT_INVERSE 1  // 0: tuning builds that factorise the single floating body's inertia every step
+#endif
+#ifndef GP_CONTACT_LIST
+#define GP_CONTACT_LIST 1  // 0: tuning builds without the list
+#endif
 
 GP_D void gp_block_sync() {
 #if defined(__CUDA_ARCH__)
@@ -374,30 +391,87 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       }
       // point-vs-halfspace contact (reference contact.rs:103-128)
       const int c0 = P.cp_begin[i], c1 = P.cp_begin[i + 1];
-#pragma unroll 1  // keep ONE copy of the force law per body: unrolling this loop x4 bloated the kernel by 27 KB
-      for (int c = c0; c < c1; ++c) {
-        const V3 loc = ld3(P.cp_loc[c]);
+      // one contact point against every halfspace: adds minus its wrench to (ka, kl)
+      auto point_contact = [&](int c, V3 loc, double kc) {
         V3 fb = v3z();
+        bool any = false;
 #pragma unroll
         for (int h = 0; h < NHS; ++h) {
           if (CONTACT == 1 || h < P.n_hs) {
             const double d = dot_add(-ho[i][h], hn[i][h], loc);  // contact.rs:64-68, halfspace.rs:39-44
             if (d <= 1e-8) {  // most points are in the air most of the time
               const V3 vpt = cross_add(vi.l, vi.a, loc);  // twist.rs:130-132, body coordinates
-              const V3 fc = contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
+              const V3 fc = contact_force(-d, hn[i][h], vpt, kc, P.hs_alpha[h], P.hs_mu[h]);
               ka = cross_sub(ka, loc, fc);
               kl -= fc;
               if constexpr (WORLD) fb += fc;
+              any = true;
             }
           }
         }
-        if constexpr (WORLD) {
-          if (out.contact_force) {
+        if constexpr (WORLD) {  // (the parity kernel zeroes the output first: points in the air stay zero)
+          if (out.contact_force && any) {
             const V3 fw = mul(Rwi, fb);
             double* o = out.contact_force + (long long)(3 * c) * out.ld + out.env;
             o[0] = fw.x;
             o[out.ld] = fw.y;
             o[2 * out.ld] = fw.z;
+          }
+        }
+      };
+      if (GP_CONTACT_LIST && Topo::kContactList && Topo::contact_list(P, i, c1 - c0)) {
+        unsigned hit = 0u;  // bit (c - c0): this environment has point c inside some halfspace
+        for (int c = c0; c < c1; ++c) {
+          const V3 loc = ld3(P.cp_loc[c]);
+          bool in = false;
+#pragma unroll
+          for (int h = 0; h < NHS; ++h) {
+            if (CONTACT == 1 || h < P.n_hs) in = in || (dot_add(-ho[i][h], hn[i][h], loc) <= 1e-8);
+          }
+          if (in) hit |= 1u << (c - c0);
+        }
+#pragma unroll 1
+        while (hit != 0u) {
+#if defined(__CUDA_ARCH__)
+          const int c = c0 + __ffs((int)hit) - 1;
+#else
+          int c = c0;
+          while (!((hit >> (c - c0)) & 1u)) ++c;
+#endif
+          hit &= hit - 1u;
+          if (out.cp_table) {
+            const double* t = out.cp_table + 4 * c;
+            point_contact(c, V3{t[0], t[1], t[2]}, t[3]);
+          } else {
+            point_contact(c, ld3(P.cp_loc[c]), P.cp_k[c]);
+          }
+        }
+      } else {
+#pragma unroll 1  // keep ONE copy of the force law per body: unrolling this loop x4 bloated the kernel by 27 KB
+        for (int c = c0; c < c1; ++c) {
+          const V3 loc = ld3(P.cp_loc[c]);
+          V3 fb = v3z();
+#pragma unroll
+          for (int h = 0; h < NHS; ++h) {
+            if (CONTACT == 1 || h < P.n_hs) {
+              const double d = dot_add(-ho[i][h], hn[i][h], loc);
+              if (d <= 1e-8) {
+                const V3 vpt = cross_add(vi.l, vi.a, loc);
+                const V3 fc = contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
+                ka = cross_sub(ka, loc, fc);
+                kl -= fc;
+                if constexpr (WORLD) fb += fc;
+              }
+            }
+          }
+          if constexpr (WORLD) {
+            if (out.contact_force) {
+              const V3 fw = mul(Rwi, fb);
+              double* o = out.contact_force + (long long)(3 * c) * out.ld + out.env;
+              o[0] = fw.x;
+              o[out.ld] = fw.y;
+              o[2 * out.ld] = fw.z;
+            }
           }
         }
       }
@@ -470,6 +544,25 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     if constexpr (SYNC >= 2) gp_block_sync();
   });
   if constexpr (SYNC == 1) gp_block_sync();
+
+  // A single floating body (cube, ball, rimless wheel): the mass matrix is the body's own constant
+  // inertia and its inverse was folded on the host (gp_params.h root_inv), so the whole of pass 2 and the
+  // factorisation reduce to vdot = H^-1 (tau - f)
+  if constexpr (GP_ROOT_INVERSE && Topo::kStatic && NB == 1 && NV == 6 && !DUMP) {
+    if (P.root_inv_ok) {
+      const SV f = frc[0];
+      const double rhs[6] = {tau[0] - f.a.x, tau[1] - f.a.y, tau[2] - f.a.z,
+                             tau[3] - f.l.x, tau[4] - f.l.y, tau[5] - f.l.z};
+#pragma unroll
+      for (int r_ = 0; r_ < 6; ++r_) {
+        double x = 0.0;
+#pragma unroll
+        for (int c_ = 0; c_ < 6; ++c_) x = fma(P.root_inv[c_ <= r_ ? hidx(r_, c_) : hidx(c_, r_)], rhs[c_], x);
+        vdot[r_] = x;
+      }
+      return status;
+    }
+  }
 
   // ------------------------------------------------------------------ pass 2: leaf -> root
   double H[NV * (NV + 1) / 2];

@@ -318,7 +318,11 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   }
 #pragma unroll U
   for (int k = 0; k < nv; ++k) {
+#ifdef GP_ZERO_TAU  // tuning builds only: what would the registers that hold the torques be worth?
+    tau_in[k] = 0.0;
+#else
     tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
+#endif
     tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
   }
   unsigned status = 0u;
@@ -329,6 +333,18 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   }
   // (clones of the last environment in a partially filled block must not touch its spring-contact state)
   DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
+  if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) {
+    // contact points for the per-lane hit list of dynamics_core (lane-dependent index: shared memory)
+    __shared__ double s_cp[kMaxCP * 4];
+    for (int c = threadIdx.x; c < P.n_cp; c += blockDim.x) {
+      s_cp[4 * c] = P.cp_loc[c][0];
+      s_cp[4 * c + 1] = P.cp_loc[c][1];
+      s_cp[4 * c + 2] = P.cp_loc[c][2];
+      s_cp[4 * c + 3] = P.cp_k[c];
+    }
+    __syncthreads();
+    none.cp_table = s_cp;
+  }
 
 #pragma unroll 1
   for (int s = 0; s < A.n_steps; ++s) {
@@ -466,6 +482,9 @@ inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n
 // assumes there are enough environments for every SM; a small batch (8 K environments is 32 such
 // blocks for 148 SMs) is cut into smaller blocks so that all SMs work, two warps on many SMs beating
 // eight warps on a few.
+// (Rejected, profiles/r1_tuning.md: evening out the last wave with slightly smaller blocks - 65536
+// environments are 1.73 waves of 256-thread blocks but 1.98 waves of 224-thread ones. These kernels are
+// latency-bound, a wave of 7 warps takes as long as a wave of 8: quadruped -13 %, navbot -5 %.)
 inline int step_block_for(long long n, int tuned) {
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -476,6 +495,8 @@ inline int step_block_for(long long n, int tuned) {
       n_sm = 148;
   }
   static const bool fixed = std::getenv("GP_STEP_FIXED_BLOCK") != nullptr;  // tuning only
+  static const char* forced = std::getenv("GP_STEP_BLOCK");                  // tuning only
+  if (forced) return std::atoi(forced);
   int b = tuned;
   while (!fixed && b > 32 && 4 * ((n + b - 1) / b) < 3 * n_sm) b /= 2;  // until 3/4 of the SMs have a block
   return b;
@@ -489,11 +510,13 @@ cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, con
 #ifdef GP_TU_RUNGE_KUTTA
 template <class Topo>
 cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, const StepArgs& A) {
-  const int block = step_block_for(A.n, Topo::kBlockSize);
-  const dim3 g(grid_for(A.n, block)), b(block);
-  if (contact == 0) step_kernel<Topo, 0, IntegRK><<<g, b, 0, s>>>(P, A);
-  else if (contact == 1) step_kernel<Topo, 1, IntegRK><<<g, b, 0, s>>>(P, A);
-  else step_kernel<Topo, 2, IntegRK><<<g, b, 0, s>>>(P, A);
+  auto go = [&](auto* kernel) {
+    const int block = step_block_for(A.n, Topo::kBlockSize);
+    kernel<<<grid_for(A.n, block), block, 0, s>>>(P, A);
+  };
+  if (contact == 0) go(&step_kernel<Topo, 0, IntegRK>);
+  else if (contact == 1) go(&step_kernel<Topo, 1, IntegRK>);
+  else go(&step_kernel<Topo, 2, IntegRK>);
   return cudaGetLastError();
 }
 #endif
@@ -501,11 +524,13 @@ cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, con
 template <class Topo>
 cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
   if (integ_class != IntegSIE) return launch_step_rk<Topo>(contact, s, P, A);
-  const int block = step_block_for(A.n, Topo::kBlockSize);
-  const dim3 g(grid_for(A.n, block)), b(block);
-  if (contact == 0) step_kernel<Topo, 0, IntegSIE><<<g, b, 0, s>>>(P, A);
-  else if (contact == 1) step_kernel<Topo, 1, IntegSIE><<<g, b, 0, s>>>(P, A);
-  else step_kernel<Topo, 2, IntegSIE><<<g, b, 0, s>>>(P, A);
+  auto go = [&](auto* kernel) {
+    const int block = step_block_for(A.n, Topo::kBlockSize);
+    kernel<<<grid_for(A.n, block), block, 0, s>>>(P, A);
+  };
+  if (contact == 0) go(&step_kernel<Topo, 0, IntegSIE>);
+  else if (contact == 1) go(&step_kernel<Topo, 1, IntegSIE>);
+  else go(&step_kernel<Topo, 2, IntegSIE>);
   return cudaGetLastError();
 }
 template <class Topo>

@@ -153,6 +153,49 @@ int finalize_mechanism(gp_mechanism* m) {
     }
   }
 
+  // inverse of the constant mass matrix of a single floating body (gp_params.h root_inv)
+  P.root_inv_ok = 0;
+  for (int k = 0; k < 21; ++k) P.root_inv[k] = 0.0;
+  if (nb == 1 && P.jtype[0] == JFloating) {
+    const double* J = P.J[0];
+    const double* c = P.mc[0];
+    const double ms = P.mass[0];
+    long double H[6][6] = {{J[0], J[1], J[2], 0, -c[2], c[1]}, {J[1], J[3], J[4], c[2], 0, -c[0]},
+                           {J[2], J[4], J[5], -c[1], c[0], 0}, {0, c[2], -c[1], ms, 0, 0},
+                           {-c[2], 0, c[0], 0, ms, 0},         {c[1], -c[0], 0, 0, 0, ms}};
+    long double L[6][6] = {};
+    bool spd = true;
+    for (int j = 0; j < 6 && spd; ++j) {  // Cholesky H = L L^T
+      long double d = H[j][j];
+      for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+      if (!(d > 0.0L)) { spd = false; break; }
+      L[j][j] = sqrtl(d);
+      for (int i = j + 1; i < 6; ++i) {
+        long double t = H[i][j];
+        for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+        L[i][j] = t / L[j][j];
+      }
+    }
+    if (spd) {
+      long double Li[6][6] = {};  // L^-1 (lower triangular), then H^-1 = L^-T L^-1
+      for (int j = 0; j < 6; ++j) {
+        Li[j][j] = 1.0L / L[j][j];
+        for (int i = j + 1; i < 6; ++i) {
+          long double t = 0.0L;
+          for (int k = j; k < i; ++k) t -= L[i][k] * Li[k][j];
+          Li[i][j] = t / L[i][i];
+        }
+      }
+      for (int r = 0; r < 6; ++r)
+        for (int cc = 0; cc <= r; ++cc) {
+          long double t = 0.0L;
+          for (int k = r; k < 6; ++k) t += Li[k][r] * Li[k][cc];
+          P.root_inv[r * (r + 1) / 2 + cc] = (double)t;
+        }
+      P.root_inv_ok = 1;
+    }
+  }
+
   // contact points are stored body-major already
   int c = 0;
   for (int b = 0; b < nb; ++b) {

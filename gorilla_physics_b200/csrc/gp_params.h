@@ -105,6 +105,15 @@ struct MechParams {
   double sc_l_rest[kMaxSC];
   double sc_k[kMaxSC];
   double sc_dir[kMaxSC][3];
+
+  // ---- (appended last: the offsets of everything above are what the tuned kernels were scheduled with)
+  // A mechanism that is ONE floating body (cube, ball, rimless wheel) has a constant mass matrix, the
+  // body's own 6x6 inertia: its inverse is folded here (packed lower triangle, [angular; linear]) and the
+  // single-floating-body step kernel multiplies by it instead of factorising the same matrix every step.
+  // root_inv_ok = 0: not such a mechanism, or the inertia is not positive definite (kernel factorises,
+  // and flags the environments, as before).
+  int root_inv_ok;
+  double root_inv[21];
 };
 
 }  // namespace gp

@@ -176,6 +176,10 @@ struct StaticTopo {
   // stateful SpringContact legs (reference contact.rs:74-94, :133-186) compiled into the general-contact
   // kernels of this topology: the single floating body (SLIP, helpers.rs:308-337)
   static constexpr bool kSprings = Spec::springs();
+  // per-lane list of the points in contact (gp_dynamics.cuh): kContactList = some body of the topology
+  // uses it (the step kernel then stages the contact points in shared memory), contact_list = this body does
+  static constexpr bool kContactList = Spec::contact_list(-1);
+  GP_HD static constexpr bool contact_list(const MechParams&, int body, int /*n_points*/) { return Spec::contact_list(body); }
   // factorise H column by column inside the leaf-to-root pass (gp_dynamics.cuh): pays where the kernel
   // has registers to spare, i.e. everywhere but the 14-dof trees
   static constexpr bool kColumnsInPass2 = tables().nv < 12;
@@ -247,6 +251,9 @@ struct DynTopo {
   static constexpr int kBlockSize = 128;
   static constexpr bool kBatchedSinCos = false;
   static constexpr bool kSprings = true;
+  static constexpr bool kContactList = true;
+  // run-time topology: bodies with many points take the list (both loops exist once in the rolled body)
+  GP_HD static bool contact_list(const MechParams&, int /*body*/, int n_points) { return n_points >= 4; }
   static constexpr bool kColumnsInPass2 = true;
   static constexpr int kUnroll = 1;
   static const char* name() { return "generic"; }
@@ -285,14 +292,16 @@ struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
   static const char* name() { return "double_pendulum_RR"; }
-  static constexpr int min_blocks(int) { return 1; }
+  static constexpr int min_blocks(int) { return 6; }  // 80 registers, 24 warps per SM: +3.6 % over 150 registers / 12 warps
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
@@ -301,6 +310,7 @@ struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
   static constexpr TopoData data() {
@@ -314,6 +324,7 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
   static constexpr int block_size() { return 256; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
@@ -322,14 +333,16 @@ struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, b
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return true; }
+  static constexpr bool contact_list(int) { return true; }  // cube corners, rimless-wheel spokes
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
   static const char* name() { return "hopper1d_FPP"; }
-  static constexpr int min_blocks(int) { return 1; }
+  static constexpr int min_blocks(int) { return 4; }  // 128 registers (332 B of spills), 16 warps per SM: +2.6 % over 208 / 8
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
@@ -338,6 +351,7 @@ struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(s
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
   static constexpr TopoData data() {
@@ -351,6 +365,7 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
   // literals save (profiles/r1_tuning.md)
   static constexpr bool batched_sincos() { return false; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int) { return false; }  // one or two points per body: the list only costs registers (-22 %)
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
   static constexpr TopoData data() {
@@ -362,6 +377,7 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static constexpr int block_size() { return 256; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool contact_list(int body) { return body < 0 || body == 4 || body == 8; }  // the wheels (8 points on each rim)
 };
 
 #undef GP_R
