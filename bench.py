@@ -33,9 +33,11 @@ UNIT = "env-steps/s"
 
 # FP64 work per environment time step of the kernel that runs each workload: 2*DFMA + DADD + DMUL
 # thread-level instructions per env-step as counted by ncu
-# (smsp__sass_thread_inst_executed_op_d{fma,add,mul}_pred_on.sum of one step-kernel launch divided by
-# n_envs * inner steps). profiles/flop_counts.json holds the numbers with the capture they come
-# from; DESIGN.md §4 explains why this (executed, not reference-formulation) count is used.
+# (smsp__sass_thread_inst_executed_op_d{fma,add,mul}_pred_on.sum summed over the 40 timed launches of
+# this file's default command, divided by n_envs * inner steps * 40: contact workloads execute more
+# once their bodies lie on the ground, tools/ncu_flops_over_bench.py). profiles/flop_counts.json holds
+# the numbers with the capture they come from; DESIGN.md §4 explains why this (executed, not
+# reference-formulation) count is used.
 def load_flop_counts():
     try:
         return json.loads((ROOT / "profiles" / "flop_counts.json").read_text())["flop_per_env_step"]
@@ -173,10 +175,11 @@ def cpu_reference_rate(workload, seconds_target=12.0, threads=None):
         kw = dict(base_t=(0, 0, 2.5), t_jitter=1.0, rpy_jitter=0.0, q_range=0.0)
     q, v = random_states(desc, n, seed=1, **kw)
     # calibrate, then run ~seconds_target
+    orc.batch_rollout(q, v, dt, 20, n_threads=threads)  # first call: library load, thread start-up
     t0 = time.perf_counter()
-    orc.batch_rollout(q, v, dt, 20, n_threads=threads)
+    orc.batch_rollout(q, v, dt, 400, n_threads=threads)
     t_cal = time.perf_counter() - t0
-    steps = max(20, int(20 * seconds_target / max(t_cal, 1e-6)))
+    steps = max(20, int(400 * seconds_target / max(t_cal, 1e-6)))
     t0 = time.perf_counter()
     orc.batch_rollout(q, v, dt, steps, n_threads=threads)
     el = time.perf_counter() - t0
