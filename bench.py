@@ -62,6 +62,17 @@ WORKLOADS = {
 }
 
 
+def load_reference_flops(workload):
+    """flop/env-step of the REFERENCE's formulation (oracle with a counting scalar type,
+    tools/count_reference_flops.py -> profiles/roofline.json); information only: `achieved` counts what
+    the kernel executes, which is 2.4-5.6x less"""
+    try:
+        return json.loads((ROOT / "profiles" / "roofline.json").read_text())["workloads"][workload][
+            "reference_formulation_flop_per_env_step"]
+    except Exception:
+        return None
+
+
 def load_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch (ncu --set full), or None"""
     try:
@@ -345,6 +356,7 @@ def main():
         "traffic": load_traffic(args.workload),
         "peak_source": "gp_measure_fp64_peak: DFMA chain on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure)",
         "flop_per_env_step": flops,
+        "reference_formulation_flop_per_env_step": load_reference_flops(args.workload),
         "hbm": {"achieved": alg_bytes_per_launch / avg_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes_per_launch / avg_launch_s / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

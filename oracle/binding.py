@@ -72,7 +72,14 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(str(_LIB_PATH))
+        _lib = configure(C.CDLL(str(_LIB_PATH)))
+    return _lib
+
+
+def configure(L):
+    """Declare the argument types of the gpo_* entry points on a loaded library (or on a proxy that
+    maps the names, see tools/count_reference_flops.py)."""
+    if True:
         vp = C.c_void_p
         L.gpo_mechanism_create.argtypes = [C.POINTER(_Desc), C.POINTER(vp)]
         L.gpo_mechanism_destroy.argtypes = [vp]
@@ -116,8 +123,7 @@ def lib() -> C.CDLL:
         L.gpo_quat_from_scaled_axis.restype = None
         L.gpo_twist_transform.argtypes = [_dp, _dp, _dp]
         L.gpo_twist_transform.restype = None
-        _lib = L
-    return _lib
+    return L
 
 
 def _d(a):

@@ -16,7 +16,7 @@ namespace {
 
 constexpr double GRAVITY = 9.81;  // lib.rs:39
 constexpr double PI = 3.14159265358979323846;
-constexpr double TWO_PI = 2.0 * PI;
+constexpr double TWO_PI = 6.28318530717958647692;  // 2 PI (a literal: the counting build's scalar has no constexpr arithmetic)
 
 // ---------------------------------------------------------------- small algebra (nalgebra 0.33.2)
 struct V3 {
@@ -481,7 +481,7 @@ void contact_dynamics(const gpo_mechanism* m, Work& w, double* contact_forces) {
           V3 contact_location{st[1], st[2], st[3]};
           V3 dvec = contact_location - body_location;
           V3 spring_direction = dvec / norm(dvec);
-          const HalfSpace& hs = m->halfspaces[(size_t)st[0] - 1];
+          const HalfSpace& hs = m->halfspaces[(size_t)(long long)st[0] - 1];
           if (dot(spring_direction, hs.normal) > 0.0) w.sc_flags |= 4;  // panic!("Spring force is into the halfspace!")
           double direction_distance = norm(dvec);
           if (direction_distance < st[7]) {
@@ -922,7 +922,7 @@ int gpo_mechanism_create(const gpo_mechanism_desc* d, gpo_mechanism** out) {
     if (b.parent < 0 || b.parent > i) { delete m; return 1; }  // parent must precede (mechanism.rs:98-125)
     b.jtype = d->joint_type[i];
     b.axis = {d->axis[3 * i], d->axis[3 * i + 1], d->axis[3 * i + 2]};
-    const double* s = d->init_iso + 7 * i;
+    const auto* s = d->init_iso + 7 * i;
     b.init_iso = {{s[3], s[0], s[1], s[2]}, {s[4], s[5], s[6]}};
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) b.moment.m[r][c] = d->moment[9 * i + 3 * r + c];

@@ -124,3 +124,41 @@ def test_frozen_golden_vectors():
         q1, v1 = orc.rollout(q, v, rec["rollout"]["dt"], rec["rollout"]["steps"])
         assert rel_err(rec["rollout"]["q1"], q1) < 1e-9, name
         assert rel_err(rec["rollout"]["v1"], v1) < 1e-9, name
+
+
+def test_counting_build_is_the_same_arithmetic():
+    """oracle/gp_oracle_count.cpp (the oracle with a flop-counting scalar type, profiles/roofline.json) must
+    compute bit-identical results to the oracle proper, and count a plausible amount of work."""
+    import ctypes as C
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    subprocess.run(["make", "-s", "-C", str(root / "oracle"), "count"], check=True)
+    real = C.CDLL(str(root / "oracle" / "libgp_oracle_count.so"))
+    desc = CASES["so101_contact"][0]()
+    orc = OracleMechanism(desc)
+    q, v, tau = states(desc, 4, seed=3, q_range=2.6)
+    want_q, want_v = orc.batch_rollout(q, v, 1.0 / 6000.0, 200, n_threads=1)
+
+    from oracle import binding
+
+    class Proxy:
+        def __getattr__(self, name):
+            return getattr(real, name.replace("gpo_", "gpc_", 1))
+
+    saved = binding._lib
+    try:
+        binding._lib = binding.configure(Proxy())
+        real.gpc_reset_counters.restype = None
+        real.gpc_read_counters.restype = None
+        cnt_orc = OracleMechanism(desc)
+        real.gpc_reset_counters()
+        got_q, got_v = cnt_orc.batch_rollout(q, v, 1.0 / 6000.0, 200, n_threads=1)
+        cnt = (C.c_longlong * 6)()
+        real.gpc_read_counters(cnt)
+        del cnt_orc
+    finally:
+        binding._lib = saved
+    np.testing.assert_array_equal(got_q, want_q)
+    np.testing.assert_array_equal(got_v, want_v)
+    per_step = sum(cnt) / (4 * 200)
+    assert 5e3 < per_step < 2e4, per_step  # ~9e3 flop per SO-101 step in the reference's formulation
