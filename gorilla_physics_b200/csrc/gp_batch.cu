@@ -35,6 +35,10 @@ struct gp_batch {
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   double* pipe_stage[2] = {nullptr, nullptr};
   size_t pipe_stage_bytes[2] = {0, 0};
+  // ticket-mode scratch (gp_launch.h StepArgs::ticket_buf), one per stream that launches step kernels:
+  // [0] the batch's own stream, [1], [2] the pipeline streams
+  unsigned* tickets[3] = {nullptr, nullptr, nullptr};
+  long long ticket_capacity = 0;
 };
 
 namespace {
@@ -347,6 +351,19 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   }
   if (n_steps == 0) return GP_OK;
   const int ic = integrator == GP_SEMI_IMPLICIT_EULER ? IntegSIE : IntegRK;
+  // ticket-mode scratch of the launching stream (the launcher decides whether to use it); not with
+  // in-kernel history records or spring-contact state, which the kernel addresses per launch
+  if (!hist_q && !A.sc_state && ic == IntegSIE) {
+    const int slot = (stream == b->stream) ? 0 : (stream == b->pipe_stream[0] ? 1 : (stream == b->pipe_stream[1] ? 2 : -1));
+    if (slot >= 0) {
+      if (!b->tickets[slot]) {
+        b->ticket_capacity = 2 + (b->n + 31) / 32;  // one entry per block of >= 32 environments
+        GP_CUDA(cudaMalloc((void**)&b->tickets[slot], (size_t)b->ticket_capacity * sizeof(unsigned)));
+      }
+      A.ticket_buf = b->tickets[slot];
+      A.ticket_capacity = b->ticket_capacity;
+    }
+  }
   GP_CUDA(m->table->step(contact_mode(m), ic, stream, m->params, A));
   b->launches++;
   return GP_OK;
@@ -496,6 +513,7 @@ void gp_batch_destroy(gp_batch* b) {
   }
   cudaFree(b->stage);
   cudaFree(b->scratch);
+  for (int s = 0; s < 3; ++s) cudaFree(b->tickets[s]);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }

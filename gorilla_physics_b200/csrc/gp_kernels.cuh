@@ -296,15 +296,64 @@ __global__ void __launch_bounds__(Topo::kBlockSize, (step_min_blocks<Topo, CONTA
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   constexpr int NQ = Topo::NQ, NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
+  const int nq = Topo::nq(P), nv = Topo::nv(P);
+  // contact points for the per-lane hit list of dynamics_core (lane-dependent index: shared memory)
+  __shared__ double s_cp[(CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) ? kMaxCP * 4 : 1];
+  if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) {
+    for (int c = threadIdx.x; c < P.n_cp; c += blockDim.x) {
+      s_cp[4 * c] = P.cp_loc[c][0];
+      s_cp[4 * c + 1] = P.cp_loc[c][1];
+      s_cp[4 * c + 2] = P.cp_loc[c][2];
+      s_cp[4 * c + 3] = P.cp_k[c];
+    }
+    __syncthreads();
+  }
+
+  // Work item = (block of environments, range of the fused steps). Normally one per thread block: its own
+  // environments, all the steps. In ticket mode (A.tickets, see gp_launch.h) a persistent grid draws items
+  // from a counter in step-chunk-major order; the chunks of one environment block run in order (an item
+  // waits until its predecessor has published the state), possibly on different SMs, the state travelling
+  // through the q / v planes in between. Tickets are handed out in an order in which every dependency
+  // points to an EARLIER ticket, held by a running block, so the scheme cannot deadlock whatever part of
+  // the grid is resident.
+  // (compiled in only for the topologies that gain from it, Topo::kTickets: the others keep exactly the
+  // plain kernel - the restructured loop cost the SO-101 contact kernel 5 % in instruction scheduling)
+  constexpr bool TK = Topo::kTickets;
+  __shared__ unsigned s_ticket;
+  long long group = blockIdx.x;
+  int step_begin = 0, step_end = A.n_steps, chunk_index = 0;
+  bool first_chunk = true, last_chunk = true;
+  for (;;) {
+  if (TK && A.tickets) {
+    if (threadIdx.x == 0) s_ticket = atomicAdd(A.tickets, 1u);
+    __syncthreads();
+    const unsigned t = s_ticket;
+    if (t >= (unsigned)A.ticket_total) return;
+    chunk_index = (int)(t / (unsigned)A.ticket_groups);
+    group = (long long)(t - (unsigned)chunk_index * (unsigned)A.ticket_groups);
+    if (chunk_index > 0 && threadIdx.x == 0) {
+      const unsigned* done = A.tickets + 1 + group;
+      unsigned seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");
+        if (seen < (unsigned)chunk_index) __nanosleep(200);
+      } while (seen < (unsigned)chunk_index);
+      __threadfence();
+    }
+    __syncthreads();  // the predecessor's state is visible; s_ticket may be overwritten
+    step_begin = chunk_index * A.ticket_chunk;
+    step_end = min(step_begin + A.ticket_chunk, A.n_steps);
+    first_chunk = chunk_index == 0;
+    last_chunk = step_end == A.n_steps;
+  }
   // threads past the end redo the last environment (and store nothing) so that the whole block
   // can meet at the per-step barrier below
-  const long long env_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long env_raw = group * blockDim.x + threadIdx.x;
   const bool active = env_raw < A.n;
   const long long env = active ? env_raw : A.n - 1;
-  const int nq = Topo::nq(P), nv = Topo::nv(P);
 
   double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
-  if (A.q_aos_in) {
+  if (A.q_aos_in && first_chunk) {
     // one environment's values are contiguous: a warp reads one contiguous stretch, once per launch
 #pragma unroll U
     for (int k = 0; k < nq; ++k) q[k] = A.q_aos_in[env * nq + k];
@@ -312,9 +361,10 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     for (int k = 0; k < nv; ++k) v[k] = A.v_aos_in[env * nv + k];
   } else {
 #pragma unroll U
-    for (int k = 0; k < nq; ++k) q[k] = A.q[(long long)k * A.ld + env];
+    // (ticket mode: another SM may have written the planes during this launch, so read them at L2)
+    for (int k = 0; k < nq; ++k) q[k] = TK ? __ldcg(A.q + (long long)k * A.ld + env) : A.q[(long long)k * A.ld + env];
 #pragma unroll U
-    for (int k = 0; k < nv; ++k) v[k] = A.v[(long long)k * A.ld + env];
+    for (int k = 0; k < nv; ++k) v[k] = TK ? __ldcg(A.v + (long long)k * A.ld + env) : A.v[(long long)k * A.ld + env];
   }
 #pragma unroll U
   for (int k = 0; k < nv; ++k) {
@@ -328,26 +378,15 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   unsigned status = 0u;
   double cstate[2] = {0.0, 0.0};
   if (A.ctrl_state) {
-    cstate[0] = A.ctrl_state[env];
-    cstate[1] = A.ctrl_state[A.ld + env];
+    cstate[0] = TK ? __ldcg(A.ctrl_state + env) : A.ctrl_state[env];
+    cstate[1] = TK ? __ldcg(A.ctrl_state + A.ld + env) : A.ctrl_state[A.ld + env];
   }
   // (clones of the last environment in a partially filled block must not touch its spring-contact state)
   DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
-  if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) {
-    // contact points for the per-lane hit list of dynamics_core (lane-dependent index: shared memory)
-    __shared__ double s_cp[kMaxCP * 4];
-    for (int c = threadIdx.x; c < P.n_cp; c += blockDim.x) {
-      s_cp[4 * c] = P.cp_loc[c][0];
-      s_cp[4 * c + 1] = P.cp_loc[c][1];
-      s_cp[4 * c + 2] = P.cp_loc[c][2];
-      s_cp[4 * c + 3] = P.cp_k[c];
-    }
-    __syncthreads();
-    none.cp_table = s_cp;
-  }
+  if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) none.cp_table = s_cp;
 
 #pragma unroll 1
-  for (int s = 0; s < A.n_steps; ++s) {
+  for (int s = step_begin; s < step_end; ++s) {
     if constexpr (GP_STEP_SYNC && Topo::kBlockSize >= 256) {
     // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
     // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
@@ -404,23 +443,36 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     }
   }
 
-  if (!active) return;
-  if (A.ctrl_state) {
-    A.ctrl_state[env] = cstate[0];
-    A.ctrl_state[A.ld + env] = cstate[1];
+  if (active) {
+    if (A.ctrl_state) {
+      A.ctrl_state[env] = cstate[0];
+      A.ctrl_state[A.ld + env] = cstate[1];
+    }
+#pragma unroll U
+    for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
+#pragma unroll U
+    for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
+    if (A.q_aos_out && last_chunk) {
+#pragma unroll U
+      for (int k = 0; k < nq; ++k) A.q_aos_out[env * nq + k] = q[k];
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) A.v_aos_out[env * nv + k] = v[k];
+    }
+    if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
+    if (status) {
+      if constexpr (TK) atomicOr(A.status + env, status);  // (at L2: an earlier chunk may have run on another SM)
+      else A.status[env] |= status;
+    }
   }
-#pragma unroll U
-  for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
-#pragma unroll U
-  for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
-  if (A.q_aos_out) {
-#pragma unroll U
-    for (int k = 0; k < nq; ++k) A.q_aos_out[env * nq + k] = q[k];
-#pragma unroll U
-    for (int k = 0; k < nv; ++k) A.v_aos_out[env * nv + k] = v[k];
+  if (!TK || !A.tickets) return;
+  // publish: every thread's stores, then the chunk count of this environment block
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = (unsigned)chunk_index + 1u;
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.tickets + 1 + group), "r"(done) : "memory");
   }
-  if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
-  if (status) A.status[env] |= status;
+  }  // next work item
 }
 
 // ---- dynamics kernel: dynamics_continuous once, with the parity outputs ----------------------
@@ -485,7 +537,7 @@ inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n
 // (Rejected, profiles/r1_tuning.md: evening out the last wave with slightly smaller blocks - 65536
 // environments are 1.73 waves of 256-thread blocks but 1.98 waves of 224-thread ones. These kernels are
 // latency-bound, a wave of 7 warps takes as long as a wave of 8: quadruped -13 %, navbot -5 %.)
-inline int step_block_for(long long n, int tuned) {
+inline int sm_count() {
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0, v = 0;
@@ -494,12 +546,51 @@ inline int step_block_for(long long n, int tuned) {
     else
       n_sm = 148;
   }
+  return n_sm;
+}
+inline int step_block_for(long long n, int tuned) {
+  const int n_sm = sm_count();
   static const bool fixed = std::getenv("GP_STEP_FIXED_BLOCK") != nullptr;  // tuning only
   static const char* forced = std::getenv("GP_STEP_BLOCK");                  // tuning only
   if (forced) return std::atoi(forced);
   int b = tuned;
   while (!fixed && b > 32 && 4 * ((n + b - 1) / b) < 3 * n_sm) b /= 2;  // until 3/4 of the SMs have a block
   return b;
+}
+
+// One step launch. Ticket mode (see step_kernel and gp_launch.h) when the blocks of the batch would leave
+// the last wave badly filled: the launch costs ceil(blocks / resident blocks) waves whatever the last one
+// holds, e.g. 256 blocks of a 9-body kernel on 148 one-block SMs = 2 waves for 1.73 waves of work. Cut into
+// 4 step chunks the same launch is 1024 work items = 6.92 rounds of a quarter of the time.
+template <class Kernel>
+inline void launch_step_kernel(Kernel* kernel, int tuned_block, bool tickets_compiled_in, cudaStream_t s, const MechParams& P,
+                               const StepArgs& A0) {
+  StepArgs A = A0;
+  const int block = step_block_for(A.n, tuned_block);
+  const long long groups = grid_for(A.n, block);
+  long long grid = groups;
+  A.tickets = nullptr;
+  static const bool off = std::getenv("GP_NO_TICKETS") != nullptr;  // tuning only
+  if (!off && tickets_compiled_in && A.ticket_buf && A.n_steps >= 8 && groups + 1 <= A.ticket_capacity) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
+    const long long slots = (long long)occ * sm_count();
+    const long long waves = (groups + slots - 1) / slots;
+    if (groups > slots && (double)(waves * slots) > 1.08 * (double)groups) {
+      int chunk = (A.n_steps + 3) / 4;
+      chunk = (chunk + 3) / 4 * 4;  // a multiple of the kernel's barrier cadence
+      const int chunks = (A.n_steps + chunk - 1) / chunk;
+      if (chunks >= 2 && groups * chunks < 0x7fffffffLL &&
+          cudaMemsetAsync(A.ticket_buf, 0, (size_t)(1 + groups) * sizeof(unsigned), s) == cudaSuccess) {
+        A.tickets = A.ticket_buf;
+        A.ticket_groups = (int)groups;
+        A.ticket_chunk = chunk;
+        A.ticket_total = (int)(groups * chunks);
+        grid = groups < slots ? groups : slots;
+      }
+    }
+  }
+  kernel<<<(unsigned)grid, block, 0, s>>>(P, A);
 }
 
 // The Runge-Kutta step kernels of a topology live in their own translation unit (variants/*_rk.cu defines
@@ -510,10 +601,7 @@ cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, con
 #ifdef GP_TU_RUNGE_KUTTA
 template <class Topo>
 cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, const StepArgs& A) {
-  auto go = [&](auto* kernel) {
-    const int block = step_block_for(A.n, Topo::kBlockSize);
-    kernel<<<grid_for(A.n, block), block, 0, s>>>(P, A);
-  };
+  auto go = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A); };
   if (contact == 0) go(&step_kernel<Topo, 0, IntegRK>);
   else if (contact == 1) go(&step_kernel<Topo, 1, IntegRK>);
   else go(&step_kernel<Topo, 2, IntegRK>);
@@ -524,10 +612,7 @@ cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, con
 template <class Topo>
 cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
   if (integ_class != IntegSIE) return launch_step_rk<Topo>(contact, s, P, A);
-  auto go = [&](auto* kernel) {
-    const int block = step_block_for(A.n, Topo::kBlockSize);
-    kernel<<<grid_for(A.n, block), block, 0, s>>>(P, A);
-  };
+  auto go = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A); };
   if (contact == 0) go(&step_kernel<Topo, 0, IntegSIE>);
   else if (contact == 1) go(&step_kernel<Topo, 1, IntegSIE>);
   else go(&step_kernel<Topo, 2, IntegSIE>);

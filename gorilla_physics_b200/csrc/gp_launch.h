@@ -40,6 +40,19 @@ struct StepArgs {
   double* hist_q;
   double* hist_v;
   long long hist_n;
+  // Ticket mode (gp_kernels.cuh, step_kernel): a batch whose blocks do not fill whole waves (65536
+  // environments of a 9-body tree are 256 blocks for 148 one-block SMs: 1.73 waves, the second one runs on
+  // 108 SMs) is cut into (block of environments) x (chunk of the fused steps) work items that a persistent
+  // grid draws from a counter, so every SM stays busy until the last round.
+  //   host side:   ticket_buf / ticket_capacity = zero-able scratch of the launching stream (or nullptr)
+  //   device side: tickets = ticket_buf when the launcher chose ticket mode (it zeroes it first), else nullptr;
+  //                tickets[0] = next ticket, tickets[1 + g] = chunks completed for environment block g
+  unsigned* ticket_buf;
+  long long ticket_capacity;  // in unsigneds
+  unsigned* tickets;
+  int ticket_groups;  // environment blocks
+  int ticket_chunk;   // fused steps per work item
+  int ticket_total;   // work items = groups * chunks
 };
 
 struct DynArgs {

@@ -179,6 +179,7 @@ struct StaticTopo {
   // per-lane list of the points in contact (gp_dynamics.cuh): kContactList = some body of the topology
   // uses it (the step kernel then stages the contact points in shared memory), contact_list = this body does
   static constexpr bool kContactList = Spec::contact_list(-1);
+  static constexpr bool kTickets = Spec::tickets();  // step kernel compiled with ticket mode (gp_kernels.cuh)
   GP_HD static constexpr bool contact_list(const MechParams&, int body, int /*n_points*/) { return Spec::contact_list(body); }
   // factorise H column by column inside the leaf-to-root pass (gp_dynamics.cuh): pays where the kernel
   // has registers to spare, i.e. everywhere but the 14-dof trees
@@ -252,6 +253,7 @@ struct DynTopo {
   static constexpr bool kBatchedSinCos = false;
   static constexpr bool kSprings = true;
   static constexpr bool kContactList = true;
+  static constexpr bool kTickets = true;
   // run-time topology: bodies with many points take the list (both loops exist once in the rolled body)
   GP_HD static bool contact_list(const MechParams&, int /*body*/, int n_points) { return n_points >= 4; }
   static constexpr bool kColumnsInPass2 = true;
@@ -292,6 +294,7 @@ struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
@@ -301,6 +304,7 @@ struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, co
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
@@ -310,6 +314,7 @@ struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
@@ -324,15 +329,17 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
   static constexpr int block_size() { return 256; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
   static const char* name() { return "floating_F"; }
-  static constexpr int min_blocks(int) { return 1; }
+  static constexpr int min_blocks(int) { return 4; }  // 128 registers: four 128-thread blocks per SM
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return true; }
+  static constexpr bool tickets() { return true; }  // rimless wheel, 256 K: +3 %
   static constexpr bool contact_list(int) { return true; }  // cube corners, rimless-wheel spokes
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
@@ -342,6 +349,7 @@ struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (c
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
@@ -351,6 +359,7 @@ struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(s
   static constexpr int block_size() { return 128; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
@@ -365,6 +374,7 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
   // literals save (profiles/r1_tuning.md)
   static constexpr bool batched_sincos() { return false; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return true; }  // 64 K environments = 1.73 waves: +12 %
   static constexpr bool contact_list(int) { return false; }  // one or two points per body: the list only costs registers (-22 %)
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
@@ -377,6 +387,7 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static constexpr int block_size() { return 256; }
   static constexpr bool batched_sincos() { return true; }
   static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return true; }  // 64 K environments = 1.73 waves: +12 %
   static constexpr bool contact_list(int body) { return body < 0 || body == 4 || body == 8; }  // the wheels (8 points on each rim)
 };
 

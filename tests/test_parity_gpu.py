@@ -743,3 +743,42 @@ def test_dynamics_against_independent_featherstone_derivation(name):
     ref = fs.Model(desc)
     want = np.array([fs.dynamics(ref, q[e], v[e], tau[e])["vdot"] for e in range(len(q))])
     assert rel_err(vdot, want) < TOL_DYN
+
+
+@pytest.mark.parametrize("name,n_copies,base_n,steps,dt", [
+    ("navbot_contact", 32, 2048, 37, 1.0 / 6000.0),     # 65536 envs: 256 blocks on 148 one-block SMs -> ticket mode
+    ("rimless_wheel", 64, 4096, 40, 1.0 / 600.0),       # 262144 envs, 2048 blocks on 592 slots -> ticket mode
+    ("quadruped", 33, 2000, 16, 1.0 / 3000.0),          # ragged: 66000 envs, last block partly filled
+])
+def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
+    """Batches whose blocks do not fill whole waves run in ticket mode (gp_kernels.cuh: the fused steps are
+    cut into chunks that a persistent grid draws from a counter, the state of an environment block travelling
+    through the q / v planes between chunks, possibly across SMs). The result must be what the plain mode
+    gives: copies of the same states are bitwise equal wherever they sit in the batch, equal to a small
+    batch (one wave, plain mode) of the same states bit for bit, and within parity of the oracle."""
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    q0, v0 = random_states(desc, base_n, seed=5, **kw)
+    small = MechanismState(mech, 256)
+    small.update(q0[:256], v0[:256])
+    small.step(dt, n_steps=steps)
+    qs, vs = small.state()
+    st = MechanismState(mech, base_n * n_copies)
+    st.update(np.tile(q0, (n_copies, 1)), np.tile(v0, (n_copies, 1)))
+    st.step(dt, n_steps=steps)
+    q1, v1 = st.state()
+    q1 = q1.reshape(n_copies, base_n, -1)
+    v1 = v1.reshape(n_copies, base_n, -1)
+    same = lambda a, b: np.array_equal(a, b, equal_nan=True)  # (a few deep-penetration states blow up, as in the reference)
+    assert all(same(q1[c], q1[0]) and same(v1[c], v1[0]) for c in range(n_copies))
+    assert same(q1[0][:256], qs) and same(v1[0][:256], vs)
+    assert_rollout_parity(oracle_of(desc), q0[:512], v0[:512], q1[0][:512], v1[0][:512], dt, steps)
+    # and through host buffers (simulate(): chunks on two streams, each with its own ticket scratch)
+    q_in = np.tile(q0, (n_copies, 1))
+    v_in = np.tile(v0, (n_copies, 1))
+    nsteps, q_out, v_out = st.simulate((steps - 0.5) * dt, dt, q_in, v_in)
+    assert nsteps == steps
+    q_out = q_out.reshape(n_copies, base_n, -1)
+    v_out = v_out.reshape(n_copies, base_n, -1)
+    assert all(same(q_out[c], q1[0]) and same(v_out[c], v1[0]) for c in range(n_copies))
