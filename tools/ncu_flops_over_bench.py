@@ -6,15 +6,17 @@ so the count of one early launch understates (or overstates) what the timed regi
 CSV log of
    ncu --metrics smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum -k regex:step_kernel
        --csv --log-file X.csv python bench.py --workload W --steps K --warmup 3 --no-cpu-baseline
-(three counters: one replay pass per launch) and divides the totals over the TIMED launches (the last K;
-bench.py's end-to-end leg launches smaller chunks afterwards and is excluded by grid size) by
-n_envs * inner * K.
-usage: python tools/ncu_flops_over_bench.py X.csv n_envs inner"""
+(three counters: one replay pass per launch) and divides the totals over the TIMED launches by
+n_envs * inner * K. bench.py launches W warm-up steps, then the K timed ones, then the chunks of its
+end-to-end leg: the timed launches are step-kernel launches W .. W+K-1 of the process.
+usage: python tools/ncu_flops_over_bench.py X.csv n_envs inner [K=40] [W=3]"""
 import csv
 import json
 import sys
 
 path, n_envs, inner = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+W = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 rows = []
 with open(path, newline="") as fh:
     lines = [l for l in fh if not l.startswith("==")]
@@ -29,11 +31,8 @@ for r in rd:
         if f"op_{op}_pred_on" in name:
             d[op] = val
 launches = [per_launch[k] for k in sorted(per_launch)]
-# the resident-state launches all have the full grid; the e2e chunks are smaller
-full = max(launches, key=lambda d: d.get("dfma", 0.0))["grid"]
-timed = [d for d in launches if d["grid"] == full]
-warm = 3
-timed = timed[warm:]
+timed = launches[W:W + K]
+assert len(timed) == K, (len(launches), K, W)
 tot = {op: sum(d.get(op, 0.0) for d in timed) for op in ("dfma", "dadd", "dmul")}
 env_steps = n_envs * inner * len(timed)
 per_launch_flop = [(2 * d.get("dfma", 0) + d.get("dadd", 0) + d.get("dmul", 0)) / (n_envs * inner) for d in timed]
