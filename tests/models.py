@@ -223,3 +223,40 @@ def cube_in_corner() -> Mechanism:
     n = np.array([1.0, 0.0, 0.2])
     m.add_halfspace(n / np.linalg.norm(n), -0.45, alpha=1.0, mu=0.3)
     return m
+
+
+def maximum_size_mechanism() -> MechanismDesc:
+    """Every limit of the C ABI at once (include/gorilla_b200.h GP_MAX_*): 16 bodies, 24 velocity dofs
+    (two floating joints, the second hanging off the first, + 12 single-dof joints + 2 fixed leaves),
+    32 contact points, 4 halfspaces."""
+    rng = np.random.default_rng(2026)
+    d = MechanismDesc()
+
+    def inertia():
+        m = float(rng.uniform(0.3, 1.5))
+        com = rng.uniform(-0.05, 0.05, size=3)
+        a = rng.normal(size=(3, 3))
+        return dict(moment=a @ a.T * 0.01 + np.eye(3) * 0.02 + m * (com @ com * np.eye(3) - np.outer(com, com)),
+                    cross_part=m * com, mass=m)
+
+    d.add_body(0, FLOATING, **inertia())
+    d.add_body(1, FLOATING, init_iso=iso((0.1, 0.0, 0.2)), **inertia())
+    for i in range(12):
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        parent = int(rng.integers(1, d.n_bodies + 1))
+        jt = PRISMATIC if i % 4 == 3 else REVOLUTE
+        d.add_body(parent, jt, axis=axis, init_iso=iso(rng.uniform(-0.2, 0.2, size=3), quat_from_scaled_axis(rng.normal(size=3) * 0.5)),
+                   spring=(40.0, 0.05) if jt == PRISMATIC else None, **inertia())
+    d.add_body(5, FIXED, init_iso=iso((0.0, 0.1, 0.0)), **inertia())
+    d.add_body(15, FIXED, init_iso=iso((0.05, 0.0, 0.0)), **inertia())
+    assert d.n_bodies == 16 and d.n_v == 24
+    for c in range(32):
+        d.add_contact_point(1 + c % 16, rng.uniform(-0.15, 0.15, size=3), k=float(rng.choice([50e3, 20e3])))
+    d.add_halfspace((0, 0, 1), -0.3)
+    n = np.array([0.2, 0.0, 1.0])
+    d.add_halfspace(n / np.linalg.norm(n), -0.35, alpha=1.0, mu=1.0)
+    n = np.array([0.0, -0.3, 1.0])
+    d.add_halfspace(n / np.linalg.norm(n), -0.4, alpha=0.5, mu=0.2)
+    d.add_halfspace((1, 0, 0), -0.6, alpha=0.9, mu=0.0)
+    return d

@@ -200,3 +200,41 @@ def test_bench_reference_arm_non_zero_ranks_exit_quietly():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_limits_of_the_abi():
+    """GP_MAX_* (include/gorilla_b200.h): the maximum-size mechanism is accepted, one more of anything is not."""
+    from tests import models
+    d = models.maximum_size_mechanism()
+    m = gp.Mechanism.from_desc(d)
+    assert m.kernel_variant == "generic" and m.desc().n_bodies == 16 and m.desc().n_v == 24
+    with pytest.raises(GorillaError) as e:
+        m.add_contact_point(1, (0, 0, 0))  # the 33rd contact point
+    assert e.value.code == _abi.GP_ERR_LIMIT
+    with pytest.raises(GorillaError) as e:
+        m.add_halfspace((0, 0, 1), 0.0)  # the 5th halfspace
+    assert e.value.code == _abi.GP_ERR_LIMIT
+    d17 = models.maximum_size_mechanism()
+    d17.add_body(1, gp.FIXED, moment=np.eye(3) * 0.01, mass=0.1)  # the 17th body
+    with pytest.raises(GorillaError) as e:
+        gp.Mechanism.from_desc(d17)
+    assert e.value.code == _abi.GP_ERR_LIMIT
+    d25 = gp.MechanismDesc()
+    for _ in range(4):
+        d25.add_body(0, gp.FLOATING, moment=np.eye(3), mass=1.0)
+    d25.add_body(1, gp.REVOLUTE, moment=np.eye(3), mass=1.0)  # the 25th dof
+    with pytest.raises(GorillaError) as e:
+        gp.Mechanism.from_desc(d25)
+    assert e.value.code == _abi.GP_ERR_LIMIT
+    # the oracle and the independent derivation agree on the maximum-size mechanism (CPU)
+    from oracle.binding import OracleMechanism
+    from tests import featherstone_ref as fs
+    from tests.test_oracle_independent import states
+    orc = OracleMechanism(m.desc())
+    ref = fs.Model(m.desc())
+    q, v, tau = states(m.desc(), 4, seed=1, q_range=0.5, t_jitter=0.2)
+    for e_ in range(4):
+        a = orc.dynamics(q[e_], v[e_], tau[e_], want="all")
+        b = fs.dynamics(ref, q[e_], v[e_], tau[e_])
+        assert np.abs(a["vdot"] - b["vdot"]).max() <= 1e-10 * max(1.0, np.abs(a["vdot"]).max())
+        assert np.abs(a["mass_matrix"] - b["mass_matrix"]).max() <= 1e-11 * np.abs(a["mass_matrix"]).max()

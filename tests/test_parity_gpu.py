@@ -782,3 +782,36 @@ def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
     q_out = q_out.reshape(n_copies, base_n, -1)
     v_out = v_out.reshape(n_copies, base_n, -1)
     assert all(same(q_out[c], q1[0]) and same(v_out[c], v1[0]) for c in range(n_copies))
+
+
+def test_maximum_size_mechanism():
+    """16 bodies / 24 dofs / 32 contact points / 4 halfspaces, all limits of the ABI at once, against the
+    oracle and against the independent derivation: dynamics, contact forces, one step of every integrator,
+    a fused rollout, and a ragged batch."""
+    from tests import featherstone_ref as fs
+    desc = models.maximum_size_mechanism()
+    mech = Mechanism.from_desc(desc)
+    assert mech.kernel_variant == "generic"
+    orc = oracle_of(mech.desc())
+    n = 333
+    q, v = random_states(desc, n, seed=8, t_jitter=0.2, rpy_jitter=0.6, q_range=0.5)
+    tau = np.random.default_rng(8).uniform(-1, 1, size=(n, desc.n_v))
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    vdot, cf = st.dynamics(tau=tau, contact_forces=True)
+    vdot_ref, cf_ref = orc.batch_dynamics(q, v, tau)
+    assert np.abs(cf_ref).max() > 0.0
+    assert rel_err(vdot, vdot_ref) < TOL_DYN
+    assert rel_err(cf, cf_ref, floor=1e-6) < TOL_DYN
+    ref = fs.Model(mech.desc())
+    want = np.array([fs.dynamics(ref, q[e], v[e], tau[e])["vdot"] for e in range(8)])
+    assert rel_err(vdot[:8], want) < TOL_DYN
+    for integ in (Integrator.SemiImplicitEuler, Integrator.RungeKutta2, Integrator.RungeKutta4):
+        st.update(q, v)
+        st.step(1e-4, tau=tau, integrator=integ)
+        q_ref, v_ref = orc.batch_rollout(q, v, 1e-4, 1, integrator=int(integ), tau=tau)
+        assert rel_err(st.q, q_ref) < TOL_STEP and rel_err(st.v, v_ref) < TOL_STEP
+    st.update(q, v)
+    st.step(1e-4, n_steps=50)
+    q1, v1 = st.state()
+    assert_rollout_parity(orc, q, v, q1, v1, 1e-4, 50)
