@@ -812,6 +812,6 @@ def test_maximum_size_mechanism():
         q_ref, v_ref = orc.batch_rollout(q, v, 1e-4, 1, integrator=int(integ), tau=tau)
         assert rel_err(st.q, q_ref) < TOL_STEP and rel_err(st.v, v_ref) < TOL_STEP
     st.update(q, v)
-    st.step(1e-4, n_steps=50)
+    st.step(1e-4, tau=tau, n_steps=50)
     q1, v1 = st.state()
-    assert_rollout_parity(orc, q, v, q1, v1, 1e-4, 50)
+    assert_rollout_parity(orc, q, v, q1, v1, 1e-4, 50, tau=tau)
