@@ -385,7 +385,7 @@ int simulate_pipelined(gp_batch* b, double* q_host, double* v_host, const double
   // a batch of at most two waves goes in one piece: cut in two, each half would be one (partly filled) wave
   // after the other, while the whole batch runs in ticket mode (gp_kernels.cuh) in 1.73 wave-times for 1.73
   // waves of work; that gains more than overlapping its copies (navbot 64 K: e2e +5 %, quadruped +11 %)
-  int n_chunks = n_waves <= 2 ? 1 : 4;
+  int n_chunks = (n_waves <= 2 && m->table->tickets) ? 1 : 4;
   if (const char* e = std::getenv("GP_PIPE_CHUNKS")) n_chunks = std::max(1, std::atoi(e));  // tuning only
   const long long chunk = wave * ((n_waves + n_chunks - 1) / n_chunks);
   const size_t per_env = (size_t)(nq + nv + (tau_host ? nv : 0));

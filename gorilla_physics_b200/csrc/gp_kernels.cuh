@@ -634,12 +634,12 @@ cudaError_t launch_energy(cudaStream_t s, const MechParams& P, const EnergyArgs&
 
 template <class Topo, class Spec>
 KernelTable make_static_table() {
-  return KernelTable{Spec::name(), Spec::data(), true, Topo::kBlockSize, Topo::kSprings, &launch_step<Topo>, &launch_dynamics<Topo>,
+  return KernelTable{Spec::name(), Spec::data(), true, Topo::kBlockSize, Topo::kSprings, Topo::kTickets, &launch_step<Topo>, &launch_dynamics<Topo>,
                      &launch_energy<Topo>};
 }
 template <class Topo>
 KernelTable make_generic_table() {
-  return KernelTable{"generic", TopoData{}, false, Topo::kBlockSize, true, &launch_step<Topo>, &launch_dynamics<Topo>,
+  return KernelTable{"generic", TopoData{}, false, Topo::kBlockSize, true, Topo::kTickets, &launch_step<Topo>, &launch_dynamics<Topo>,
                      &launch_energy<Topo>};
 }
 

@@ -88,6 +88,7 @@ struct KernelTable {
   bool is_static;
   int block_size;  // threads per block of the step kernels
   bool springs;    // the general-contact kernels implement SpringContact
+  bool tickets;    // the step kernels are compiled with ticket mode (StepArgs::tickets)
   cudaError_t (*step)(int contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
   cudaError_t (*dynamics)(int contact, cudaStream_t, const MechParams&, const DynArgs&);
   cudaError_t (*energy)(cudaStream_t, const MechParams&, const EnergyArgs&);
