@@ -538,14 +538,13 @@ inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n
 // environments are 1.73 waves of 256-thread blocks but 1.98 waves of 224-thread ones. These kernels are
 // latency-bound, a wave of 7 warps takes as long as a wave of 8: quadruped -13 %, navbot -5 %.)
 inline int sm_count() {
-  static int n_sm = 0;
-  if (n_sm == 0) {
+  // (every GPU of a box is the same part; initialised once, thread-safe)
+  static const int n_sm = [] {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n_sm = v;
-    else
-      n_sm = 148;
-  }
+      return v;
+    return 148;
+  }();
   return n_sm;
 }
 inline int step_block_for(long long n, int tuned) {

@@ -29,3 +29,73 @@ def reduce_diagnostics(sums, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return sums
+
+
+class ShardedMechanismState:
+    """The environments of one batch spread over several GPUs of the box FROM ONE PROCESS: one
+    `MechanismState` (its own device, stream and resident planes) per device, contiguous environment
+    ranges (`shard_range`), no exchange on the step path. This is how a single-process host (the
+    reference is one) drives the C ABI on a multi-GPU box; `bench.py` and the tests use the
+    process-per-GPU form with `torch.distributed` instead. `step` only enqueues (the devices run
+    concurrently); calls that move host data run one worker thread per device (ctypes releases the GIL).
+    """
+
+    def __init__(self, mechanism, n_envs: int, devices):
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .mechanism import MechanismState
+        self.devices = list(devices)
+        if not self.devices:
+            raise ValueError("no devices")
+        self.n_envs = int(n_envs)
+        self.ranges = [shard_range(self.n_envs, r, len(self.devices)) for r in range(len(self.devices))]
+        if any(hi <= lo for lo, hi in self.ranges):
+            raise ValueError(f"{n_envs} environments do not cover {len(self.devices)} devices")
+        self.shards = [MechanismState(mechanism, hi - lo, device=d) for (lo, hi), d in zip(self.ranges, self.devices)]
+        self.n_q, self.n_v = self.shards[0].n_q, self.shards[0].n_v
+        self._pool = ThreadPoolExecutor(max_workers=len(self.devices))
+
+    def _each(self, fn):
+        return list(self._pool.map(lambda a: fn(*a), [(s, lo, hi) for s, (lo, hi) in zip(self.shards, self.ranges)]))
+
+    def update(self, q, v):
+        import numpy as np
+        q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(self.n_envs, self.n_q))
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(self.n_envs, self.n_v))
+        self._each(lambda s, lo, hi: s.update(q[lo:hi], v[lo:hi]))
+
+    def step(self, dt, **kw):
+        for s in self.shards:  # asynchronous per device
+            s.step(dt, **kw)
+
+    def synchronize(self):
+        for s in self.shards:
+            s.synchronize()
+
+    def state(self):
+        import numpy as np
+        parts = self._each(lambda s, lo, hi: s.state())
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def simulate(self, final_time, dt, q, v, **kw):
+        """simulate() through host buffers on every device at once; q / v (float64, C-contiguous,
+        [n_envs, .]) are updated in place. Returns the number of steps."""
+        import numpy as np
+        if not (isinstance(q, np.ndarray) and q.flags.c_contiguous and q.dtype == np.float64):
+            raise ValueError("q must be a C-contiguous float64 array (it is updated in place)")
+        if not (isinstance(v, np.ndarray) and v.flags.c_contiguous and v.dtype == np.float64):
+            raise ValueError("v must be a C-contiguous float64 array (it is updated in place)")
+        q2, v2 = q.reshape(self.n_envs, self.n_q), v.reshape(self.n_envs, self.n_v)
+        done = self._each(lambda s, lo, hi: s.simulate(final_time, dt, q2[lo:hi], v2[lo:hi], **kw)[0])
+        return done[0]
+
+    def status(self):
+        import numpy as np
+        return np.concatenate(self._each(lambda s, lo, hi: s.status()))
+
+    def energy_sums(self):
+        """(sum KE, sum PE, sum spring energy) over every device: the end-of-rollout diagnostic; in one
+        process the "reduction" is a host-side sum of one triple per device."""
+        import numpy as np
+        parts = self._each(lambda s, lo, hi: tuple(float(np.sum(e)) for e in s.energies()))
+        return tuple(sum(p[k] for p in parts) for k in range(3))

@@ -238,3 +238,17 @@ def test_limits_of_the_abi():
         b = fs.dynamics(ref, q[e_], v[e_], tau[e_])
         assert np.abs(a["vdot"] - b["vdot"]).max() <= 1e-10 * max(1.0, np.abs(a["vdot"]).max())
         assert np.abs(a["mass_matrix"] - b["mass_matrix"]).max() <= 1e-11 * np.abs(a["mass_matrix"]).max()
+
+
+def test_sharded_state_fails_loudly_without_a_gpu_and_validates_its_ranges():
+    from gorilla_physics_b200 import ShardedMechanismState
+    mech = gp.Mechanism.from_model("double_pendulum")
+    with pytest.raises(ValueError):
+        ShardedMechanismState(mech, 8, devices=[])
+    with pytest.raises(ValueError):
+        ShardedMechanismState(mech, 2, devices=[0, 1, 2])  # fewer environments than devices
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(GorillaError) as e:  # no CPU path behind the product API
+            ShardedMechanismState(mech, 64, devices=[0, 1])
+        assert e.value.code == _abi.GP_ERR_NO_DEVICE

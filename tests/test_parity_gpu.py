@@ -815,3 +815,30 @@ def test_maximum_size_mechanism():
     st.step(1e-4, tau=tau, n_steps=50)
     q1, v1 = st.state()
     assert_rollout_parity(orc, q, v, q1, v1, 1e-4, 50, tau=tau)
+
+
+def test_sharded_state_from_one_process():
+    """ShardedMechanismState: contiguous environment ranges on several batches driven from ONE process
+    (here three shards on the same device: the logic, not the hardware). Same result as one batch."""
+    from gorilla_physics_b200 import ShardedMechanismState
+    mech = models.so101_with_contact()
+    desc = mech.desc()
+    n = 1000
+    q, v = random_states(desc, n, seed=21)
+    one = MechanismState(mech, n)
+    one.update(q, v)
+    one.step(1.0 / 6000.0, n_steps=40)
+    q1, v1 = one.state()
+    sh = ShardedMechanismState(mech, n, devices=[0, 0, 0])
+    assert [hi - lo for lo, hi in sh.ranges] == [333, 333, 334]
+    sh.update(q, v)
+    sh.step(1.0 / 6000.0, n_steps=40)
+    q2, v2 = sh.state()
+    assert np.array_equal(q1, q2) and np.array_equal(v1, v2)
+    qs, vs = q.copy(), v.copy()
+    assert sh.simulate(39.5 / 6000.0, 1.0 / 6000.0, qs, vs) == 40
+    assert np.array_equal(qs, q1) and np.array_equal(vs, v1)
+    assert not sh.status().any()
+    ke, pe, se = sh.energy_sums()
+    k1, p1, s1 = one.energies()
+    assert abs(ke - k1.sum()) <= 1e-9 * abs(k1.sum()) and abs(pe - p1.sum()) <= 1e-9 * abs(p1.sum())
