@@ -1,5 +1,7 @@
 #!/bin/bash
-# usage: ab_env.sh "<env assignment A>|<env assignment B>" workloads...
+# Developer tool (GPU box): A/B of run-time switches of ONE build (GP_NO_TICKETS=1, GP_PIPE_CHUNKS=n,
+# GP_STEP_BLOCK=n ...), two repetitions per workload -> gpurun_out/ab_env.txt
+#   tools/ab_env.sh "<env assignment A>|<env assignment B>" workloads...
 IFS='|' read -ra CFG <<< "$1"; shift
 : > gpurun_out/ab_env.txt
 for w in "$@"; do for rep in 1 2; do for cfg in "${CFG[@]}"; do
