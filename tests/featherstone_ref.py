@@ -227,3 +227,30 @@ def dynamics(model: Model, q, v, tau=None, gravity=GRAVITY):
             tau[model.voff[i]] += -model.spring_k[i] * (q[model.qoff[i]] - model.spring_l[i])
     vdot = np.linalg.solve(H, tau - bias) if nv else np.zeros(0)
     return {"vdot": vdot, "mass_matrix": H, "bias": bias, "contact_forces": cf}
+
+
+def potential_energy(model: Model, q, gravity=GRAVITY):
+    """true gravitational potential energy: sum over bodies of g * (m * origin_z + (R_world * mc)_z)
+    (the reference's gravitational_energy uses the frame-origin height only, mechanism.rs:352-362)"""
+    q = np.asarray(q, dtype=float)
+    Rw, pw, pe = [], [], 0.0
+    for i in range(model.nb):
+        R, t = model.joint_pose(i, q)
+        p = model.parent[i]
+        if p < 0:
+            Rw.append(R)
+            pw.append(t)
+        else:
+            Rw.append(Rw[p] @ R)
+            pw.append(pw[p] + Rw[p] @ t)
+        mass = model.I[i][3, 3]
+        mc = np.array([model.I[i][2, 4], model.I[i][0, 5], model.I[i][1, 3]])  # from skew(mc) in the upper-right block
+        pe += gravity * (mass * pw[i][2] + (Rw[i] @ mc)[2])
+    return pe
+
+
+def kinetic_energy(model: Model, q, v):
+    """1/2 v^T H v"""
+    H = dynamics(model, q, v)["mass_matrix"]
+    v = np.asarray(v, dtype=float)
+    return 0.5 * float(v @ H @ v)

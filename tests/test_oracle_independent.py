@@ -162,3 +162,38 @@ def test_counting_build_is_the_same_arithmetic():
     np.testing.assert_array_equal(got_v, want_v)
     per_step = sum(cnt) / (4 * 200)
     assert 5e3 < per_step < 2e4, per_step  # ~9e3 flop per SO-101 step in the reference's formulation
+
+
+@pytest.mark.parametrize("name", ["so101", "navbot", "quadruped_free", "double_pendulum", "hopper_1d_free"])
+def test_energy_is_conserved_along_oracle_rollouts(name):
+    """A physics pin that needs no second implementation of the dynamics: without contact and torques the
+    total energy KE + PE is constant along the true trajectory. The reference's Runge-Kutta 4 advances the
+    positions with the OLD velocities (integrators.rs:195-271, euler_step), so its energy error is first order
+    in dt: the drift at dt and dt/2 must be in the ratio 2, i.e. the Richardson-extrapolated drift
+    2 e(dt/2) - e(dt) vanishes. KE comes from the oracle's own kinetic_energy (inertia.rs:182-202) and,
+    independently, from 1/2 v^T H v of the Featherstone derivation; PE is the true potential energy of the
+    centres of mass (the reference's gravitational_energy uses frame origins)."""
+    if name == "quadruped_free":
+        desc = Mechanism.from_model("quadruped").desc()
+        kw = dict(base_t=(0, 0, 1.0), t_jitter=0.1, rpy_jitter=0.3)
+    elif name == "hopper_1d_free":
+        desc = Mechanism.from_model("hopper_1d").desc()
+        kw = dict(base_t=(0, 0, 1.0), t_jitter=0.1, rpy_jitter=0.3, q_range=0.2)
+    else:
+        factory, kw, _ = CASES[name]
+        desc = factory()
+    orc = OracleMechanism(desc)
+    ref = fs.Model(desc)
+    q, v, _ = states(desc, 3, seed=9, **kw)
+    horizon, dt = 0.05, 1e-4
+    for e in range(3):
+        ke0 = orc.kinetic_energy(q[e], v[e])
+        e0 = ke0 + fs.potential_energy(ref, q[e])
+        assert abs(ke0 - fs.kinetic_energy(ref, q[e], v[e])) <= 1e-12 * max(1.0, abs(e0))
+        drift = []
+        for h in (dt, dt / 2):
+            q1, v1 = orc.rollout(q[e], v[e], h, int(round(horizon / h)), integrator=2)
+            drift.append(orc.kinetic_energy(q1, v1) + fs.potential_energy(ref, q1) - e0)
+        scale = max(abs(e0), ke0, 1e-3)
+        assert abs(2.0 * drift[1] - drift[0]) <= 1e-7 * scale, (name, e, drift, scale)
+        assert abs(drift[1]) <= 1e-3 * scale
