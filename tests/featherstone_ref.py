@@ -254,3 +254,32 @@ def kinetic_energy(model: Model, q, v):
     H = dynamics(model, q, v)["mass_matrix"]
     v = np.asarray(v, dtype=float)
     return 0.5 * float(v @ H @ v)
+
+
+def semi_implicit_euler_step(model: Model, q, v, tau, dt):
+    """One step of the reference's semi-implicit Euler, written from its definition (SURVEY.md §8a I1,
+    integrators.rs:25-39, :276-319): v+ = v + vdot dt; scalar joints q+ = q + v+ dt; floating joints
+    quat+ = normalize(quat + 1/2 quat * (0, w+) dt) (w+ the NEW body-frame angular velocity),
+    t+ = t + R(quat) v_lin+ dt with the OLD rotation."""
+    q = np.asarray(q, dtype=float)
+    v = np.asarray(v, dtype=float)
+    vdot = dynamics(model, q, v, tau)["vdot"]
+    v1 = v + vdot * dt
+    q1 = q.copy()
+    for i in range(model.nb):
+        t = model.jtype[i]
+        qo, vo = model.qoff[i], model.voff[i]
+        if t in (REVOLUTE, PRISMATIC):
+            q1[qo] = q[qo] + v1[vo] * dt
+        elif t == FLOATING:
+            x, y, z, w = q[qo:qo + 4]
+            wx, wy, wz = v1[vo:vo + 3]
+            # Hamilton product quat * (wx, wy, wz, 0), halved
+            dq = 0.5 * np.array([w * wx + y * wz - z * wy,
+                                 w * wy + z * wx - x * wz,
+                                 w * wz + x * wy - y * wx,
+                                 -x * wx - y * wy - z * wz])
+            qn = q[qo:qo + 4] + dq * dt
+            q1[qo:qo + 4] = qn / np.linalg.norm(qn)
+            q1[qo + 4:qo + 7] = q[qo + 4:qo + 7] + quat_to_rot(x, y, z, w) @ v1[vo + 3:vo + 6] * dt
+    return q1, v1
