@@ -324,154 +324,154 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   int step_begin = 0, step_end = A.n_steps, chunk_index = 0;
   bool first_chunk = true, last_chunk = true;
   for (;;) {
-  if (TK && A.tickets) {
-    if (threadIdx.x == 0) s_ticket = atomicAdd(A.tickets, 1u);
-    __syncthreads();
-    const unsigned t = s_ticket;
-    if (t >= (unsigned)A.ticket_total) return;
-    chunk_index = (int)(t / (unsigned)A.ticket_groups);
-    group = (long long)(t - (unsigned)chunk_index * (unsigned)A.ticket_groups);
-    if (chunk_index > 0 && threadIdx.x == 0) {
-      const unsigned* done = A.tickets + 1 + group;
-      unsigned seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");
-        if (seen < (unsigned)chunk_index) __nanosleep(200);
-      } while (seen < (unsigned)chunk_index);
-      __threadfence();
+    if (TK && A.tickets) {
+      if (threadIdx.x == 0) s_ticket = atomicAdd(A.tickets, 1u);
+      __syncthreads();
+      const unsigned t = s_ticket;
+      if (t >= (unsigned)A.ticket_total) return;
+      chunk_index = (int)(t / (unsigned)A.ticket_groups);
+      group = (long long)(t - (unsigned)chunk_index * (unsigned)A.ticket_groups);
+      if (chunk_index > 0 && threadIdx.x == 0) {
+        const unsigned* done = A.tickets + 1 + group;
+        unsigned seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");
+          if (seen < (unsigned)chunk_index) __nanosleep(200);
+        } while (seen < (unsigned)chunk_index);
+        __threadfence();
+      }
+      __syncthreads();  // the predecessor's state is visible; s_ticket may be overwritten
+      step_begin = chunk_index * A.ticket_chunk;
+      step_end = min(step_begin + A.ticket_chunk, A.n_steps);
+      first_chunk = chunk_index == 0;
+      last_chunk = step_end == A.n_steps;
     }
-    __syncthreads();  // the predecessor's state is visible; s_ticket may be overwritten
-    step_begin = chunk_index * A.ticket_chunk;
-    step_end = min(step_begin + A.ticket_chunk, A.n_steps);
-    first_chunk = chunk_index == 0;
-    last_chunk = step_end == A.n_steps;
-  }
-  // threads past the end redo the last environment (and store nothing) so that the whole block
-  // can meet at the per-step barrier below
-  const long long env_raw = group * blockDim.x + threadIdx.x;
-  const bool active = env_raw < A.n;
-  const long long env = active ? env_raw : A.n - 1;
+    // threads past the end redo the last environment (and store nothing) so that the whole block
+    // can meet at the per-step barrier below
+    const long long env_raw = group * blockDim.x + threadIdx.x;
+    const bool active = env_raw < A.n;
+    const long long env = active ? env_raw : A.n - 1;
 
-  double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
-  if (A.q_aos_in && first_chunk) {
-    // one environment's values are contiguous: a warp reads one contiguous stretch, once per launch
+    double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
+    if (A.q_aos_in && first_chunk) {
+      // one environment's values are contiguous: a warp reads one contiguous stretch, once per launch
 #pragma unroll U
-    for (int k = 0; k < nq; ++k) q[k] = A.q_aos_in[env * nq + k];
+      for (int k = 0; k < nq; ++k) q[k] = A.q_aos_in[env * nq + k];
 #pragma unroll U
-    for (int k = 0; k < nv; ++k) v[k] = A.v_aos_in[env * nv + k];
-  } else {
-#pragma unroll U
-    // (ticket mode: another SM may have written the planes during this launch, so read them at L2)
-    for (int k = 0; k < nq; ++k) q[k] = TK ? __ldcg(A.q + (long long)k * A.ld + env) : A.q[(long long)k * A.ld + env];
-#pragma unroll U
-    for (int k = 0; k < nv; ++k) v[k] = TK ? __ldcg(A.v + (long long)k * A.ld + env) : A.v[(long long)k * A.ld + env];
-  }
-#pragma unroll U
-  for (int k = 0; k < nv; ++k) {
-#ifdef GP_ZERO_TAU  // tuning builds only: what would the registers that hold the torques be worth?
-    tau_in[k] = 0.0;
-#else
-    tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
-#endif
-    tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
-  }
-  unsigned status = 0u;
-  double cstate[2] = {0.0, 0.0};
-  if (A.ctrl_state) {
-    cstate[0] = TK ? __ldcg(A.ctrl_state + env) : A.ctrl_state[env];
-    cstate[1] = TK ? __ldcg(A.ctrl_state + A.ld + env) : A.ctrl_state[A.ld + env];
-  }
-  // (clones of the last environment in a partially filled block must not touch its spring-contact state)
-  DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
-  if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) none.cp_table = s_cp;
-
-#pragma unroll 1
-  for (int s = step_begin; s < step_end; ++s) {
-    if constexpr (GP_STEP_SYNC && Topo::kBlockSize >= 256) {
-    // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
-    // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
-    // then share instruction-cache lines instead of each streaming the whole body from L2
-    if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
-    }
-    controller_tau<Topo>(P, A, q, v, tau_in, tau, cstate);
-    if (INTEG == IntegSIE) {
-      // semi_implicit_euler, reference integrators.rs:25-39, :276-319
-      status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
-#pragma unroll U
-      for (int k = 0; k < nv; ++k) v[k] = v[k] + vdot[k] * A.dt;
-      advance_q<Topo>(P, q, v, A.dt, q);
+      for (int k = 0; k < nv; ++k) v[k] = A.v_aos_in[env * nv + k];
     } else {
-      // runge_kutta_2 / runge_kutta_4, reference integrators.rs:177-225 with euler_step :230-271
-      const bool rk4 = (A.integrator == GP_RUNGE_KUTTA_4);
-      const int n_stage = rk4 ? 4 : 2;
-      double q0[NQ], v0[NV], facc[NV];
 #pragma unroll U
-      for (int k = 0; k < nq; ++k) q0[k] = q[k];
+      // (ticket mode: another SM may have written the planes during this launch, so read them at L2)
+      for (int k = 0; k < nq; ++k) q[k] = TK ? __ldcg(A.q + (long long)k * A.ld + env) : A.q[(long long)k * A.ld + env];
 #pragma unroll U
-      for (int k = 0; k < nv; ++k) { v0[k] = v[k]; facc[k] = 0.0; }
+      for (int k = 0; k < nv; ++k) v[k] = TK ? __ldcg(A.v + (long long)k * A.ld + env) : A.v[(long long)k * A.ld + env];
+    }
+#pragma unroll U
+    for (int k = 0; k < nv; ++k) {
+#ifdef GP_ZERO_TAU  // tuning builds only: what would the registers that hold the torques be worth?
+      tau_in[k] = 0.0;
+#else
+      tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
+#endif
+      tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
+    }
+    unsigned status = 0u;
+    double cstate[2] = {0.0, 0.0};
+    if (A.ctrl_state) {
+      cstate[0] = TK ? __ldcg(A.ctrl_state + env) : A.ctrl_state[env];
+      cstate[1] = TK ? __ldcg(A.ctrl_state + A.ld + env) : A.ctrl_state[A.ld + env];
+    }
+    // (clones of the last environment in a partially filled block must not touch its spring-contact state)
+    DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
+    if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) none.cp_table = s_cp;
+
 #pragma unroll 1
-      for (int st = 0; st < n_stage; ++st) {
+    for (int s = step_begin; s < step_end; ++s) {
+      if constexpr (GP_STEP_SYNC && Topo::kBlockSize >= 256) {
+      // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
+      // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
+      // then share instruction-cache lines instead of each streaming the whole body from L2
+      if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
+      }
+      controller_tau<Topo>(P, A, q, v, tau_in, tau, cstate);
+      if (INTEG == IntegSIE) {
+        // semi_implicit_euler, reference integrators.rs:25-39, :276-319
         status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
-        if (st + 1 < n_stage) {
-          // RK4: f1 + 2 f2 + 2 f3 (+ f4 below), stage steps dt/2, dt/2, dt ; RK2: stage step dt/2
-          const double wgt = (st == 0) ? 1.0 : 2.0;
-          const double h = (rk4 && st == 2) ? A.dt : A.dt / 2.0;
 #pragma unroll U
-          for (int k = 0; k < nv; ++k) facc[k] = facc[k] + vdot[k] * wgt;
-          advance_q<Topo>(P, q0, v0, h, q);
+        for (int k = 0; k < nv; ++k) v[k] = v[k] + vdot[k] * A.dt;
+        advance_q<Topo>(P, q, v, A.dt, q);
+      } else {
+        // runge_kutta_2 / runge_kutta_4, reference integrators.rs:177-225 with euler_step :230-271
+        const bool rk4 = (A.integrator == GP_RUNGE_KUTTA_4);
+        const int n_stage = rk4 ? 4 : 2;
+        double q0[NQ], v0[NV], facc[NV];
 #pragma unroll U
-          for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * h;
+        for (int k = 0; k < nq; ++k) q0[k] = q[k];
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) { v0[k] = v[k]; facc[k] = 0.0; }
+#pragma unroll 1
+        for (int st = 0; st < n_stage; ++st) {
+          status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
+          if (st + 1 < n_stage) {
+            // RK4: f1 + 2 f2 + 2 f3 (+ f4 below), stage steps dt/2, dt/2, dt ; RK2: stage step dt/2
+            const double wgt = (st == 0) ? 1.0 : 2.0;
+            const double h = (rk4 && st == 2) ? A.dt : A.dt / 2.0;
+#pragma unroll U
+            for (int k = 0; k < nv; ++k) facc[k] = facc[k] + vdot[k] * wgt;
+            advance_q<Topo>(P, q0, v0, h, q);
+#pragma unroll U
+            for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * h;
+          }
+        }
+        if (rk4) {
+#pragma unroll U
+          for (int k = 0; k < nv; ++k) vdot[k] = (facc[k] + vdot[k]) / 6.0;
+        }
+        advance_q<Topo>(P, q0, v0, A.dt, q);
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * A.dt;
+      }
+      if (A.hist_q != nullptr && active) {  // (uniform test; history launches are bandwidth-bound anyway)
+        double* hq = A.hist_q + ((long long)s * A.hist_n + env) * nq;
+#pragma unroll U
+        for (int k = 0; k < nq; ++k) hq[k] = q[k];
+        if (A.hist_v != nullptr) {
+          double* hv = A.hist_v + ((long long)s * A.hist_n + env) * nv;
+#pragma unroll U
+          for (int k = 0; k < nv; ++k) hv[k] = v[k];
         }
       }
-      if (rk4) {
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) vdot[k] = (facc[k] + vdot[k]) / 6.0;
-      }
-      advance_q<Topo>(P, q0, v0, A.dt, q);
-#pragma unroll U
-      for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * A.dt;
     }
-    if (A.hist_q != nullptr && active) {  // (uniform test; history launches are bandwidth-bound anyway)
-      double* hq = A.hist_q + ((long long)s * A.hist_n + env) * nq;
-#pragma unroll U
-      for (int k = 0; k < nq; ++k) hq[k] = q[k];
-      if (A.hist_v != nullptr) {
-        double* hv = A.hist_v + ((long long)s * A.hist_n + env) * nv;
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) hv[k] = v[k];
-      }
-    }
-  }
 
-  if (active) {
-    if (A.ctrl_state) {
-      A.ctrl_state[env] = cstate[0];
-      A.ctrl_state[A.ld + env] = cstate[1];
+    if (active) {
+      if (A.ctrl_state) {
+        A.ctrl_state[env] = cstate[0];
+        A.ctrl_state[A.ld + env] = cstate[1];
+      }
+#pragma unroll U
+      for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
+      if (A.q_aos_out && last_chunk) {
+#pragma unroll U
+        for (int k = 0; k < nq; ++k) A.q_aos_out[env * nq + k] = q[k];
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) A.v_aos_out[env * nv + k] = v[k];
+      }
+      if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
+      if (status) {
+        if constexpr (TK) atomicOr(A.status + env, status);  // (at L2: an earlier chunk may have run on another SM)
+        else A.status[env] |= status;
+      }
     }
-#pragma unroll U
-    for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
-#pragma unroll U
-    for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
-    if (A.q_aos_out && last_chunk) {
-#pragma unroll U
-      for (int k = 0; k < nq; ++k) A.q_aos_out[env * nq + k] = q[k];
-#pragma unroll U
-      for (int k = 0; k < nv; ++k) A.v_aos_out[env * nv + k] = v[k];
+    if (!TK || !A.tickets) return;
+    // publish: every thread's stores, then the chunk count of this environment block
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = (unsigned)chunk_index + 1u;
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.tickets + 1 + group), "r"(done) : "memory");
     }
-    if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
-    if (status) {
-      if constexpr (TK) atomicOr(A.status + env, status);  // (at L2: an earlier chunk may have run on another SM)
-      else A.status[env] |= status;
-    }
-  }
-  if (!TK || !A.tickets) return;
-  // publish: every thread's stores, then the chunk count of this environment block
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = (unsigned)chunk_index + 1u;
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.tickets + 1 + group), "r"(done) : "memory");
-  }
   }  // next work item
 }
 
