@@ -107,13 +107,21 @@ const KernelTable* variant_quadruped();
 const KernelTable* variant_navbot();
 
 
-// every compiled variant, generic last
+const KernelTable* variant_custom();  // nullptr unless the library was built with CUSTOM_NB=... (gp_topology.cuh)
+
+// every compiled variant, generic last (a build-time custom specialisation goes first)
 inline const KernelTable* const* all_variants(int* n) {
-  static const KernelTable* v[] = {variant_pendulum(),  variant_double_pendulum(), variant_cart_pole(),
-                                   variant_so101(),     variant_floating(),        variant_hopper1d(),
-                                   variant_hopper(),    variant_quadruped(),       variant_navbot(),
-                                   variant_generic()};
-  *n = (int)(sizeof(v) / sizeof(v[0]));
+  static const KernelTable* v[12];
+  static const int count = [] {
+    const KernelTable* all[] = {variant_custom(),    variant_pendulum(), variant_double_pendulum(), variant_cart_pole(),
+                                variant_so101(),     variant_floating(), variant_hopper1d(),        variant_hopper(),
+                                variant_quadruped(), variant_navbot(),   variant_generic()};
+    int k = 0;
+    for (const KernelTable* t : all)
+      if (t) v[k++] = t;
+    return k;
+  }();
+  *n = count;
   return v;
 }
 

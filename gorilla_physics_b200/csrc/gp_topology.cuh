@@ -391,6 +391,26 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static constexpr bool contact_list(int body) { return body < 0 || body == 4 || body == 8; }  // the wheels (8 points on each rim)
 };
 
+// A specialisation for ONE more tree, chosen when the library is built:
+//   make CUSTOM_NB=4 CUSTOM_PARENTS=-1,0,1,2 CUSTOM_JOINTS=3,1,2,2 CUSTOM_AXES=0,0,0,0 CUSTOM_NAME=hopper2d_FRPP
+// (0-based parents, -1 = world; joint types 0 fixed / 1 revolute / 2 prismatic / 3 floating; axes 1 = exactly +z,
+// 0 = any; `python tools/custom_topo.py <model>` prints the line for a mechanism). The policies are the defaults
+// the shipped specs converged to: one 256-thread block per SM beyond three bodies, ticket mode there.
+#ifdef GP_CUSTOM_TOPO_NB
+struct SpecCustom {
+  static constexpr TopoData data() {
+    return {GP_CUSTOM_TOPO_NB, {GP_CUSTOM_TOPO_PARENTS}, {GP_CUSTOM_TOPO_JOINTS}, {GP_CUSTOM_TOPO_AXES}};
+  }
+  static const char* name() { return GP_CUSTOM_TOPO_NAME; }
+  static constexpr int min_blocks(int) { return 1; }
+  static constexpr int block_size() { return GP_CUSTOM_TOPO_NB <= 3 ? 128 : 256; }
+  static constexpr bool batched_sincos() { return true; }
+  static constexpr bool springs() { return false; }
+  static constexpr bool tickets() { return GP_CUSTOM_TOPO_NB > 3; }
+  static constexpr bool contact_list(int) { return false; }
+};
+#endif
+
 #undef GP_R
 #undef GP_P
 #undef GP_F

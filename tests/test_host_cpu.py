@@ -252,3 +252,26 @@ def test_sharded_state_fails_loudly_without_a_gpu_and_validates_its_ranges():
         with pytest.raises(GorillaError) as e:  # no CPU path behind the product API
             ShardedMechanismState(mech, 64, devices=[0, 1])
         assert e.value.code == _abi.GP_ERR_NO_DEVICE
+
+
+@pytest.mark.skipif(not os.environ.get("GP_TEST_SLOW"), reason="builds a second library (~70 s); GP_TEST_SLOW=1")
+def test_custom_topology_build_selects_its_own_variant(tmp_path):
+    """csrc/Makefile CUSTOM_* + gp_topology.cuh SpecCustom: a library built with one more specialisation picks it
+    for the matching tree and nothing else changes."""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "tools"))
+    from custom_topo import custom_topo_vars
+    params = [10, 1, 0.5, 1, 0.1, 0.5, 1, 0.1, 0.3, 1, 1, 0.3]
+    d = gp.Mechanism.from_model("hopper_2d", params).desc()
+    out = tmp_path / "libcustom.so"
+    cmd = ["make", "-C", str(root / "gorilla_physics_b200" / "csrc"), "-j8", f"BUILD={tmp_path}/obj", f"OUT={out}"]
+    cmd += custom_topo_vars(d, "hopper2d_FRPP").split()
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    code = ("import gorilla_physics_b200 as gp; "
+            f"print(gp.Mechanism.from_model('hopper_2d', {params}).kernel_variant, "
+            "gp.Mechanism.from_model('so101').kernel_variant, gp.Mechanism.from_model('cart').kernel_variant)")
+    res = subprocess.run([sys.executable, "-c", code], env={**os.environ, "GP_LIB_PATH": str(out)}, cwd=root,
+                         capture_output=True, text=True, check=True)
+    assert res.stdout.split() == ["hopper2d_FRPP", "so101_X6Rz", "generic"]
