@@ -7,13 +7,15 @@ import numpy as np
 
 from gorilla_physics_b200 import (FIXED, FLOATING, PRISMATIC, REVOLUTE, Mechanism, MechanismDesc, iso,
                                   quat_from_euler, quat_from_scaled_axis)
-from oracle.binding import OracleMechanism
 
 GRAVITY = 9.81
 PI = math.pi
 
 
-def oracle_of(mech_or_desc) -> OracleMechanism:
+def oracle_of(mech_or_desc):
+    # (imported here, not at module level: bench.py's own arm takes its mechanisms from this module and must
+    # not pull the oracle in; only its cpu_baseline / --impl reference legs may)
+    from oracle.binding import OracleMechanism
     desc = mech_or_desc.desc() if isinstance(mech_or_desc, Mechanism) else mech_or_desc
     return OracleMechanism(desc)
 
