@@ -6,7 +6,8 @@ one-for-all/gorilla-physics, executed by hand-written sm_100a CUDA kernels behin
 """
 from .desc import (FIXED, FLOATING, PRISMATIC, REVOLUTE, MechanismDesc, iso, iso_xyz_rpy, quat_from_axis_angle,
                    quat_from_euler, quat_from_scaled_axis)
-from .mechanism import Controller, Integrator, Mechanism, MechanismState, measure_fp64_peak, simulate, step
+from .mechanism import (Controller, Integrator, KernelMode, Mechanism, MechanismState, jit_available, jit_cache_dir,
+                        measure_fp64_peak, simulate, step)
 from .sharding import ShardedMechanismState, shard_range
 
 GRAVITY = 9.81  # reference src/lib.rs:39
@@ -14,5 +15,6 @@ GRAVITY = 9.81  # reference src/lib.rs:39
 __all__ = [
     "FIXED", "REVOLUTE", "PRISMATIC", "FLOATING", "MechanismDesc", "iso", "iso_xyz_rpy", "quat_from_euler",
     "quat_from_axis_angle", "quat_from_scaled_axis", "Mechanism", "MechanismState", "Integrator", "Controller",
-    "step", "simulate", "measure_fp64_peak", "GRAVITY", "ShardedMechanismState", "shard_range",
+    "step", "simulate", "measure_fp64_peak", "GRAVITY", "ShardedMechanismState", "shard_range", "KernelMode",
+    "jit_available", "jit_cache_dir",
 ]

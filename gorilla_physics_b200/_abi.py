@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 # GP_LIB_PATH lets a developer point at an experimental build of the same library
 LIB_PATH = Path(os.environ.get("GP_LIB_PATH", _HERE / "lib" / "libgorilla_b200.so"))
 
-GP_OK, GP_ERR_INVALID, GP_ERR_UNSUPPORTED, GP_ERR_NO_DEVICE, GP_ERR_CUDA, GP_ERR_LIMIT = range(6)
+GP_OK, GP_ERR_INVALID, GP_ERR_UNSUPPORTED, GP_ERR_NO_DEVICE, GP_ERR_CUDA, GP_ERR_LIMIT, GP_ERR_JIT = range(7)
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -79,6 +79,10 @@ SYMBOLS = {
     "gp_mechanism_n_spring_contacts": (C.c_int, [vp]),
     "gp_mechanism_supports": (C.c_int, [vp, ip]),
     "gp_mechanism_kernel_variant": (C.c_char_p, [vp]),
+    "gp_mechanism_set_kernel_mode": (C.c_int, [vp, C.c_int]),
+    "gp_jit_available": (C.c_int, []),
+    "gp_jit_cache_dir": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "gp_mechanism_precompile": (C.c_int, [vp, C.c_uint, C.POINTER(C.c_int)]),
     "gp_model_create": (C.c_int, [C.c_char_p, dp, C.c_int, C.POINTER(vp)]),
     "gp_batch_create": (C.c_int, [vp, C.c_int64, C.c_int, C.POINTER(vp)]),
     "gp_batch_destroy": (None, [vp]),
@@ -110,6 +114,7 @@ SYMBOLS = {
     "gp_batch_energy_sums_device": (C.c_int, [vp, vp]),
     "gp_batch_poses": (C.c_int, [vp, vp]),
     "gp_batch_status": (C.c_int, [vp, vp]),
+    "gp_batch_clear_status": (C.c_int, [vp]),
     "gp_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, dp]),
 }
 

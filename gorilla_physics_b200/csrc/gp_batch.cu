@@ -26,6 +26,7 @@ struct gp_batch {
   unsigned* status = nullptr;  // [ld]
   double* ctrl_state = nullptr;  // [2][ld] controller state (GP_CTRL_HOPPER_1D), allocated on first use
   double* sc_state = nullptr;    // [n_sc*8][ld] spring-contact state (mechanisms with spring contacts)
+  int n_sc = 0;                  // spring contacts sc_state was allocated for (refresh_batch)
   double* stage = nullptr;     // staging for AoS<->SoA and outputs
   size_t stage_bytes = 0;
   double* scratch = nullptr;   // SoA outputs of dynamics / energy
@@ -46,6 +47,17 @@ namespace {
 #define GP_CUDA(call)                                                               \
   do {                                                                              \
     cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return GP_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+// launches through the kernel table: a run-time-compiled table reports its own failures (message already set)
+#define GP_TABLE(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ == cudaErrorJitCompilationDisabled) return GP_ERR_JIT;                  \
     if (e__ != cudaSuccess) {                                                       \
       set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
       return GP_ERR_CUDA;                                                           \
@@ -231,13 +243,39 @@ int to_host_aos(gp_batch* b, const double* soa, double* host_aos, int K) {
   return GP_OK;
 }
 
+// The mechanism may have changed since the batch was created (add_halfspace / add_contact_point /
+// add_spring_contact bump gp_mechanism::revision; the reference mutates the MechanismState in place). Halfspaces
+// and contact points live in the kernel parameters, so they take effect by themselves; spring contacts carry
+// per-environment state in the batch, which is (re)allocated here in the unregistered state of
+// MechanismState::new whenever their number changed.
+int refresh_batch(gp_batch* b) {
+  const gp_mechanism* m = b->mech;
+  if (b->mech_revision == m->revision) return GP_OK;
+  if (m->n_sc() != b->n_sc) {
+    GP_CUDA(cudaStreamSynchronize(b->stream));
+    cudaFree(b->sc_state);
+    b->sc_state = nullptr;
+    b->n_sc = 0;
+    if (m->n_sc() > 0) {
+      GP_CUDA(cudaMalloc((void**)&b->sc_state, (size_t)kSpringState * m->n_sc() * b->ld * sizeof(double)));
+      init_spring_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->sc_state, b->ld, m->params);
+      GP_CUDA(cudaGetLastError());
+      GP_CUDA(cudaStreamSynchronize(b->stream));
+      b->launches++;
+      b->n_sc = m->n_sc();
+    }
+  }
+  b->mech_revision = m->revision;
+  return GP_OK;
+}
+
 int check_batch(gp_batch* b, const char* fn) {
   if (!b) {
     set_error("%s: null batch", fn);
     return GP_ERR_INVALID;
   }
   GP_CUDA(cudaSetDevice(b->device));
-  return GP_OK;
+  return refresh_batch(b);
 }
 
 // 0 = no contact work, 1 = exactly one halfspace, 2 = several (dynamics_core's CONTACT modes)
@@ -364,7 +402,7 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
       A.ticket_capacity = b->ticket_capacity;
     }
   }
-  GP_CUDA(m->table->step(contact_mode(m), ic, stream, m->params, A));
+  GP_TABLE(m->table->step(m->table, contact_mode(m), ic, stream, m->params, A));
   b->launches++;
   return GP_OK;
 }
@@ -395,6 +433,7 @@ int simulate_pipelined(gp_batch* b, double* q_host, double* v_host, const double
     if (rc) return rc;
   }
   b->tau_set = tau_host != nullptr;
+  GP_CUDA(cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream));  // new states: new episode
   GP_CUDA(cudaStreamSynchronize(b->stream));
   int slot = 0;
   for (long long env0 = 0; env0 < b->n; env0 += chunk, slot ^= 1) {
@@ -484,6 +523,7 @@ int gp_batch_create(const gp_mechanism* mech, int64_t n_envs, int device, gp_bat
       return fail(GP_ERR_CUDA);
     }
     init_spring_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->sc_state, b->ld, mech->params);
+    b->n_sc = mech->n_sc();
   }
   cudaMemsetAsync(b->tau, 0, nv * b->ld * sizeof(double), b->stream);
   cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream);
@@ -541,9 +581,18 @@ int gp_batch_sync(gp_batch* b) {
   return GP_OK;
 }
 
+int gp_batch_clear_status(gp_batch* b) {
+  int rc = check_batch(b, "gp_batch_clear_status");
+  if (rc) return rc;
+  GP_CUDA(cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream));
+  return GP_OK;
+}
+
 int gp_batch_set_state(gp_batch* b, const double* q_host, const double* v_host) {
   int rc = check_batch(b, "gp_batch_set_state");
   if (rc) return rc;
+  // new states start a new episode: the flags of the previous one do not carry over
+  if (q_host && v_host) GP_CUDA(cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream));
   if (q_host && (rc = to_device_soa(b, q_host, b->q, b->mech->n_q))) return rc;
   if (q_host && v_host) GP_CUDA(cudaStreamSynchronize(b->stream));  // staging buffer is reused
   if (v_host && (rc = to_device_soa(b, v_host, b->v, b->mech->n_v))) return rc;
@@ -576,7 +625,7 @@ int gp_batch_set_spring_contact_state(gp_batch* b, const double* state_host) {
   int rc = check_batch(b, "gp_batch_set_spring_contact_state");
   if (rc) return rc;
   const int ns = b->mech->n_sc();
-  if (ns == 0) return GP_OK;
+  if (ns == 0 || !b->sc_state) return GP_OK;
   if (!state_host) {
     init_spring_state_kernel<<<(unsigned)((b->ld + 255) / 256), 256, 0, b->stream>>>(b->sc_state, b->ld, b->mech->params);
     GP_CUDA(cudaGetLastError());
@@ -597,7 +646,7 @@ int gp_batch_get_spring_contact_state(gp_batch* b, double* state_host) {
     return GP_ERR_INVALID;
   }
   const int ns = b->mech->n_sc();
-  if (ns == 0) return GP_OK;
+  if (ns == 0 || !b->sc_state) return GP_OK;
   return to_host_aos(b, b->sc_state, state_host, kSpringState * ns);
 }
 
@@ -636,6 +685,7 @@ int gp_batch_randomize(gp_batch* b, uint64_t seed, const gp_state_dist* dist) {
     set_error("gp_batch_randomize: null distribution");
     return GP_ERR_INVALID;
   }
+  GP_CUDA(cudaMemsetAsync(b->status, 0, b->ld * sizeof(unsigned), b->stream));  // new episode
   randomize_kernel<<<(unsigned)((b->n + 255) / 256), 256, 0, b->stream>>>(b->q, b->v, b->n, b->ld,
                                                                           b->mech->params, seed, *dist);
   GP_CUDA(cudaGetLastError());
@@ -664,7 +714,7 @@ int gp_batch_dynamics(gp_batch* b, double* vdot_host, double* contact_force_host
   A.ld = b->ld;
   A.gravity = kGravity;
   A.sc_state = b->sc_state;  // dynamics_continuous advances the spring-contact state like the reference does
-  GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
+  GP_TABLE(m->table->dynamics(m->table, contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if ((rc = to_host_aos(b, A.vdot, vdot_host, nv))) return rc;
   if (contact_force_host && ncf) {
@@ -698,10 +748,11 @@ int gp_batch_free_velocity(gp_batch* b, double dt, int gravity_enabled, double* 
   A.gravity = gravity_enabled ? kGravity : 0.0;
   A.free_dt = dt;
   A.no_contact = 1;
+  A.armature = 1;
   if (dt == 0.0) {  // v + vdot * 0 = v: read the velocities back
     return to_host_aos(b, b->v, v_free_host, nv);
   }
-  GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
+  GP_TABLE(m->table->dynamics(m->table, contact_mode(m), b->stream, m->params, A));
   b->launches++;
   return to_host_aos(b, A.vdot, v_free_host, nv);
 }
@@ -725,7 +776,7 @@ int gp_batch_mass_matrix(gp_batch* b, double* mass_matrix_host, double* bias_hos
   A.ld = b->ld;
   A.gravity = kGravity;
   A.sc_state = b->sc_state;  // dynamics_continuous advances the spring-contact state like the reference does
-  GP_CUDA(m->table->dynamics(contact_mode(m), b->stream, m->params, A));
+  GP_TABLE(m->table->dynamics(m->table, contact_mode(m), b->stream, m->params, A));
   b->launches++;
   if (mass_matrix_host) {
     // nv*nv planes can exceed one tile's shared memory: move them nv planes (one row) at a time
@@ -837,7 +888,7 @@ static int run_energy(gp_batch* b, bool poses, double** ke, double** pe, double*
   A.poses = poses ? b->scratch + 3 * b->ld : nullptr;
   A.n = b->n;
   A.ld = b->ld;
-  GP_CUDA(m->table->energy(b->stream, m->params, A));
+  GP_TABLE(m->table->energy(m->table, b->stream, m->params, A));
   b->launches++;
   *ke = A.ke;
   *pe = A.pe;

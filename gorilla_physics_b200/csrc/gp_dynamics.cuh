@@ -35,6 +35,9 @@ struct DynOut {
   // per-lane hit list below reads them with a lane-dependent index, which shared memory serves in one
   // access where the constant bank would replay once per distinct address
   const double* cp_table = nullptr;
+  // add the joints' armature to the diagonal of H: Articulated::free_velocity only (the reference's
+  // MechanismState engine - mass_matrix, dynamics_continuous, step - never reads it; hybrid/articulated/mod.rs:247)
+  bool armature = false;
 };
 
 // Topologies whose bodies carry several contact points (Topo::kContactList) test all the points of a
@@ -669,13 +672,16 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       SV F;
       F.a = sym_mul_axis<Topo>(P, i, Ic.J);
       F.l = cross_axis<Topo>(P, i, Ic.c, -1.0);  // m*0 - c x a
-      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a) + P.armature[i];  // hybrid/articulated/mod.rs:247
+      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a);
+      if constexpr (DUMP) {
+        if (out.armature) H[hidx(vo, vo)] += P.armature[i];  // hybrid/articulated/mod.rs:247
+      }
       Fd[vo] = F;
     } else if (jt == JPrismatic) {
       SV F;
       F.a = cross_axis<Topo>(P, i, Ic.c, 1.0);  // J*0 + c x a
       F.l = axis_scaled<Topo>(P, i, Ic.m);
-      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.l) + P.armature[i];
+      H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.l);
       Fd[vo] = F;
     } else if (jt == JFloating) {
       // S = identity: the F columns are the columns of the 6x6 composite inertia

@@ -23,6 +23,7 @@ struct gp_mechanism {
   gp::MechParams params;
   const gp::KernelTable* table = nullptr;
   unsigned long long revision = 0;  // bumps on every change so batches can refresh
+  int kernel_mode = 0;              // gp_kernel_mode (GP_KERNEL_AUTO)
 
   int n_cp() const { return (int)cp_body.size(); }
   int n_hs() const { return (int)hs_alpha.size(); }

@@ -493,6 +493,7 @@ dynamics_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Dy
     tau[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
   }
   DynOut out{A.contact_force, A.mass_matrix, A.bias, A.ld, env, A.sc_state};
+  out.armature = A.armature != 0;
   if (A.contact_force)
     for (int c = 0; c < 3 * P.n_cp; ++c) A.contact_force[(long long)c * A.ld + env] = 0.0;
   unsigned status = A.no_contact ? dynamics_core<Topo, 0, true>(P, q, v, tau, vdot, out, A.gravity)
@@ -527,69 +528,16 @@ energy_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Ener
   if (A.spring) A.spring[env] = se;
 }
 
+#if !defined(__CUDACC_RTC__)  // host side: not part of a run-time compilation (gp_jit.cpp)
 // ---- launchers (table type in gp_launch.h) ------------------------------------------------
-inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
-
-// Threads per block of a step launch. The tuned size (one 256-thread block per SM for the big kernels)
-// assumes there are enough environments for every SM; a small batch (8 K environments is 32 such
-// blocks for 148 SMs) is cut into smaller blocks so that all SMs work, two warps on many SMs beating
-// eight warps on a few.
-// (Rejected, profiles/r1_tuning.md: evening out the last wave with slightly smaller blocks - 65536
-// environments are 1.73 waves of 256-thread blocks but 1.98 waves of 224-thread ones. These kernels are
-// latency-bound, a wave of 7 warps takes as long as a wave of 8: quadruped -13 %, navbot -5 %.)
-inline int sm_count() {
-  // (every GPU of a box is the same part; initialised once, thread-safe)
-  static const int n_sm = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      return v;
-    return 148;
-  }();
-  return n_sm;
-}
-inline int step_block_for(long long n, int tuned) {
-  const int n_sm = sm_count();
-  static const bool fixed = std::getenv("GP_STEP_FIXED_BLOCK") != nullptr;  // tuning only
-  static const char* forced = std::getenv("GP_STEP_BLOCK");                  // tuning only
-  if (forced) return std::atoi(forced);
-  int b = tuned;
-  while (!fixed && b > 32 && 4 * ((n + b - 1) / b) < 3 * n_sm) b /= 2;  // until 3/4 of the SMs have a block
-  return b;
-}
-
-// One step launch. Ticket mode (see step_kernel and gp_launch.h) when the blocks of the batch would leave
-// the last wave badly filled: the launch costs ceil(blocks / resident blocks) waves whatever the last one
-// holds, e.g. 256 blocks of a 9-body kernel on 148 one-block SMs = 2 waves for 1.73 waves of work. Cut into
-// 4 step chunks the same launch is 1024 work items = 6.92 rounds of a quarter of the time.
+// One step launch: block size, grid and ticket mode are planned by plan_step_launch (gp_launch.h), shared
+// with the run-time-compiled kernels of gp_jit.cpp.
 template <class Kernel>
 inline void launch_step_kernel(Kernel* kernel, int tuned_block, bool tickets_compiled_in, cudaStream_t s, const MechParams& P,
                                const StepArgs& A0) {
   StepArgs A = A0;
-  const int block = step_block_for(A.n, tuned_block);
-  const long long groups = grid_for(A.n, block);
-  long long grid = groups;
-  A.tickets = nullptr;
-  static const bool off = std::getenv("GP_NO_TICKETS") != nullptr;  // tuning only
-  if (!off && tickets_compiled_in && A.ticket_buf && A.n_steps >= 8 && groups + 1 <= A.ticket_capacity) {
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
-    const long long slots = (long long)occ * sm_count();
-    const long long waves = (groups + slots - 1) / slots;
-    if (groups > slots && (double)(waves * slots) > 1.08 * (double)groups) {
-      int chunk = (A.n_steps + 3) / 4;
-      chunk = (chunk + 3) / 4 * 4;  // a multiple of the kernel's barrier cadence
-      const int chunks = (A.n_steps + chunk - 1) / chunk;
-      if (chunks >= 2 && groups * chunks < 0x7fffffffLL &&
-          cudaMemsetAsync(A.ticket_buf, 0, (size_t)(1 + groups) * sizeof(unsigned), s) == cudaSuccess) {
-        A.tickets = A.ticket_buf;
-        A.ticket_groups = (int)groups;
-        A.ticket_chunk = chunk;
-        A.ticket_total = (int)(groups * chunks);
-        grid = groups < slots ? groups : slots;
-      }
-    }
-  }
-  kernel<<<(unsigned)grid, block, 0, s>>>(P, A);
+  const StepLaunchPlan plan = plan_step_launch((const void*)kernel, tuned_block, tickets_compiled_in, s, A);
+  kernel<<<plan.grid, plan.block, 0, s>>>(P, A);
 }
 
 // The Runge-Kutta step kernels of a topology live in their own translation unit (variants/*_rk.cu defines
@@ -609,7 +557,7 @@ cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, con
 #endif
 
 template <class Topo>
-cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
+cudaError_t launch_step(const KernelTable*, int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
   if (integ_class != IntegSIE) return launch_step_rk<Topo>(contact, s, P, A);
   auto go = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A); };
   if (contact == 0) go(&step_kernel<Topo, 0, IntegSIE>);
@@ -618,14 +566,14 @@ cudaError_t launch_step(int contact, int integ_class, cudaStream_t s, const Mech
   return cudaGetLastError();
 }
 template <class Topo>
-cudaError_t launch_dynamics(int contact, cudaStream_t s, const MechParams& P, const DynArgs& A) {
+cudaError_t launch_dynamics(const KernelTable*, int contact, cudaStream_t s, const MechParams& P, const DynArgs& A) {
   const dim3 g(grid_for(A.n)), b(kBlock);
   (void)contact;  // parity kernel: always the general contact mode
   dynamics_kernel<Topo, 2><<<g, b, 0, s>>>(P, A);
   return cudaGetLastError();
 }
 template <class Topo>
-cudaError_t launch_energy(cudaStream_t s, const MechParams& P, const EnergyArgs& A) {
+cudaError_t launch_energy(const KernelTable*, cudaStream_t s, const MechParams& P, const EnergyArgs& A) {
   const dim3 g(grid_for(A.n)), b(kBlock);
   energy_kernel<Topo><<<g, b, 0, s>>>(P, A);
   return cudaGetLastError();
@@ -641,5 +589,7 @@ KernelTable make_generic_table() {
   return KernelTable{"generic", TopoData{}, false, Topo::kBlockSize, true, Topo::kTickets, &launch_step<Topo>, &launch_dynamics<Topo>,
                      &launch_energy<Topo>};
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace gp

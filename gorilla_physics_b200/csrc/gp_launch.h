@@ -1,6 +1,9 @@
 // gp_launch.h — host-visible launch interface of the kernel variants (no device code).
 #pragma once
+#if !defined(__CUDACC_RTC__)
+#include <cstdlib>
 #include <cuda_runtime.h>
+#endif
 
 #include "gp_params.h"
 
@@ -69,6 +72,7 @@ struct DynArgs {
   double free_dt;       // != 0: vdot receives v + vdot * free_dt (Articulated::free_velocity)
   int no_contact;       // free_velocity ignores contact forces
   double* sc_state;     // [n_sc*8][ld] spring-contact state or nullptr
+  int armature;         // add the joint armature to H's diagonal (free_velocity; hybrid/articulated/mod.rs:247)
 };
 
 struct EnergyArgs {
@@ -81,6 +85,76 @@ struct EnergyArgs {
   long long n, ld;
 };
 
+#if !defined(__CUDACC_RTC__)  // host side: not part of a run-time compilation (gp_jit.cpp)
+// ---- launch planning (host) ---------------------------------------------------------------------
+inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+// Threads per block of a step launch. The tuned size (one 256-thread block per SM for the big kernels)
+// assumes there are enough environments for every SM; a small batch (8 K environments is 32 such
+// blocks for 148 SMs) is cut into smaller blocks so that all SMs work, two warps on many SMs beating
+// eight warps on a few.
+// (Rejected, profiles/r1_tuning.md: evening out the last wave with slightly smaller blocks - 65536
+// environments are 1.73 waves of 256-thread blocks but 1.98 waves of 224-thread ones. These kernels are
+// latency-bound, a wave of 7 warps takes as long as a wave of 8: quadruped -13 %, navbot -5 %.)
+inline int sm_count() {
+  // (every GPU of a box is the same part; initialised once, thread-safe)
+  static const int n_sm = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      return v;
+    return 148;
+  }();
+  return n_sm;
+}
+inline int step_block_for(long long n, int tuned) {
+  const int n_sm = sm_count();
+  static const bool fixed = std::getenv("GP_STEP_FIXED_BLOCK") != nullptr;  // tuning only
+  static const char* forced = std::getenv("GP_STEP_BLOCK");                  // tuning only
+  if (forced) return std::atoi(forced);
+  int b = tuned;
+  while (!fixed && b > 32 && 4 * ((n + b - 1) / b) < 3 * n_sm) b /= 2;  // until 3/4 of the SMs have a block
+  return b;
+}
+
+// One step launch. Ticket mode (see step_kernel and gp_launch.h) when the blocks of the batch would leave
+// the last wave badly filled: the launch costs ceil(blocks / resident blocks) waves whatever the last one
+// holds, e.g. 256 blocks of a 9-body kernel on 148 one-block SMs = 2 waves for 1.73 waves of work. Cut into
+// 4 step chunks the same launch is 1024 work items = 6.92 rounds of a quarter of the time.
+struct StepLaunchPlan {
+  unsigned grid;
+  int block;
+};
+// (kernel = the __global__ function's address, or a cudaKernel_t of a run-time-compiled kernel: the occupancy
+// query takes either. Fills in the ticket fields of A.)
+inline StepLaunchPlan plan_step_launch(const void* kernel, int tuned_block, bool tickets_compiled_in, cudaStream_t s, StepArgs& A) {
+  const int block = step_block_for(A.n, tuned_block);
+  const long long groups = grid_for(A.n, block);
+  long long grid = groups;
+  A.tickets = nullptr;
+  static const bool off = std::getenv("GP_NO_TICKETS") != nullptr;  // tuning only
+  if (!off && tickets_compiled_in && A.ticket_buf && A.n_steps >= 8 && groups + 1 <= A.ticket_capacity) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
+    const long long slots = (long long)occ * sm_count();
+    const long long waves = (groups + slots - 1) / slots;
+    if (groups > slots && (double)(waves * slots) > 1.08 * (double)groups) {
+      int chunk = (A.n_steps + 3) / 4;
+      chunk = (chunk + 3) / 4 * 4;  // a multiple of the kernel's barrier cadence
+      const int chunks = (A.n_steps + chunk - 1) / chunk;
+      if (chunks >= 2 && groups * chunks < 0x7fffffffLL &&
+          cudaMemsetAsync(A.ticket_buf, 0, (size_t)(1 + groups) * sizeof(unsigned), s) == cudaSuccess) {
+        A.tickets = A.ticket_buf;
+        A.ticket_groups = (int)groups;
+        A.ticket_chunk = chunk;
+        A.ticket_total = (int)(groups * chunks);
+        grid = groups < slots ? groups : slots;
+      }
+    }
+  }
+  return StepLaunchPlan{(unsigned)grid, block};
+}
+
+
 // ---- launch table -------------------------------------------------------------------------------
 struct KernelTable {
   const char* name;
@@ -89,9 +163,11 @@ struct KernelTable {
   int block_size;  // threads per block of the step kernels
   bool springs;    // the general-contact kernels implement SpringContact
   bool tickets;    // the step kernels are compiled with ticket mode (StepArgs::tickets)
-  cudaError_t (*step)(int contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
-  cudaError_t (*dynamics)(int contact, cudaStream_t, const MechParams&, const DynArgs&);
-  cudaError_t (*energy)(cudaStream_t, const MechParams&, const EnergyArgs&);
+  // (self = the table the pointer was taken from: the run-time-compiled tables of gp_jit.cpp keep their
+  // kernel handles behind it, the build-time variants ignore it)
+  cudaError_t (*step)(const KernelTable* self, int contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);
+  cudaError_t (*dynamics)(const KernelTable* self, int contact, cudaStream_t, const MechParams&, const DynArgs&);
+  cudaError_t (*energy)(const KernelTable* self, cudaStream_t, const MechParams&, const EnergyArgs&);
 };
 
 // defined one per translation unit under variants/
@@ -124,5 +200,7 @@ inline const KernelTable* const* all_variants(int* n) {
   *n = count;
   return v;
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace gp

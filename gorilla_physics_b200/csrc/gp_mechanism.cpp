@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "gp_host.h"
+#include "gp_jit.h"
 #include "gp_topology.cuh"
 
 namespace gp {
@@ -227,16 +228,32 @@ int finalize_mechanism(gp_mechanism* m) {
     for (int d = 0; d < 3; ++d) P.sc_dir[s][d] = m->sc_direction[3 * s + d];
   }
 
-  // kernel variant: first compiled specialisation whose signature matches, else generic
+  // kernel variant (gp_kernel_mode): a shipped specialisation whose signature matches; else one compiled
+  // at run time for this very tree (gp_jit.cpp); else the run-time-topology kernel.
   // (spring contacts: only kernels that implement them)
   int nvar = 0;
   const KernelTable* const* vars = all_variants(&nvar);
-  m->table = vars[nvar - 1];
-  for (int k = 0; k < nvar - 1; ++k)
-    if (topo_matches(vars[k]->topo, td) && (m->n_sc() == 0 || vars[k]->springs)) {
-      m->table = vars[k];
-      break;
+  const KernelTable* generic = vars[nvar - 1];
+  m->table = nullptr;
+  if (m->kernel_mode == GP_KERNEL_AUTO || m->kernel_mode == GP_KERNEL_SHIPPED) {
+    for (int k = 0; k < nvar - 1; ++k)
+      if (topo_matches(vars[k]->topo, td) && (m->n_sc() == 0 || vars[k]->springs)) {
+        m->table = vars[k];
+        break;
+      }
+  }
+  if (!m->table && (m->kernel_mode == GP_KERNEL_AUTO || m->kernel_mode == GP_KERNEL_JIT)) {
+    std::string why;
+    if (jit_available(&why)) {
+      m->table = jit_table(td, jit_policy_for(m, td));
+    } else if (m->kernel_mode == GP_KERNEL_JIT) {
+      set_error("GP_KERNEL_JIT: run-time specialisation is not available: %s", why.c_str());
+      m->table = generic;
+      m->revision++;
+      return GP_ERR_JIT;
     }
+  }
+  if (!m->table) m->table = generic;
   m->revision++;
   return GP_OK;
 }
@@ -279,6 +296,16 @@ int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
   if (!d->parent || !d->joint_type || !d->axis || !d->init_iso || !d->moment || !d->cross_part || !d->mass) {
     set_error("gp_mechanism_create: null array in description");
     return GP_ERR_INVALID;
+  }
+  if ((d->n_halfspaces > 0 && (!d->hs_point || !d->hs_normal || !d->hs_alpha || !d->hs_mu)) ||
+      (d->n_contact_points > 0 && (!d->cp_body || !d->cp_location || !d->cp_k)) ||
+      (d->n_spring_contacts > 0 && (!d->sc_body || !d->sc_l_rest || !d->sc_direction || !d->sc_k))) {
+    set_error("gp_mechanism_create: a count is > 0 but its arrays are null");
+    return GP_ERR_INVALID;
+  }
+  if (d->n_spring_contacts < 0 || d->n_spring_contacts > kMaxSC) {
+    set_error("n_spring_contacts=%d (max %d)", d->n_spring_contacts, kMaxSC);
+    return GP_ERR_LIMIT;
   }
   gp_mechanism* m = new gp_mechanism();
   m->nb = nb;
@@ -333,14 +360,22 @@ int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
     m->spring_k.push_back(sp && d->spring_k ? d->spring_k[i] : 0.0);
     m->spring_l.push_back(sp && d->spring_l ? d->spring_l[i] : 0.0);
     const double arm = d->armature ? d->armature[i] : 0.0;
-    if (!(arm >= 0.0) || (arm != 0.0 && jt != GP_JOINT_REVOLUTE && jt != GP_JOINT_PRISMATIC)) {
-      set_error("joint %d: armature must be >= 0 and only applies to revolute / prismatic joints", i + 1);
+    if (!(arm >= 0.0) || (arm != 0.0 && jt != GP_JOINT_REVOLUTE)) {
+      // reference joint/mod.rs:105-108: "armature is only supported on revolute joints"
+      set_error("joint %d: armature must be >= 0 and is only supported on revolute joints", i + 1);
       delete m;
       return GP_ERR_INVALID;
     }
     m->armature.push_back(arm);
   }
   for (int h = 0; h < d->n_halfspaces; ++h) {
+    const double* nn = d->hs_normal + 3 * h;
+    const double n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+    if (!(std::fabs(n2 - 1.0) < 1e-9)) {  // the reference takes a UnitVector3 (halfspace.rs:6-11)
+      set_error("halfspace %d: normal is not a unit vector (|n|^2 = %.17g)", h, n2);
+      delete m;
+      return GP_ERR_INVALID;
+    }
     m->hs_point.insert(m->hs_point.end(), d->hs_point + 3 * h, d->hs_point + 3 * h + 3);
     m->hs_normal.insert(m->hs_normal.end(), d->hs_normal + 3 * h, d->hs_normal + 3 * h + 3);
     m->hs_alpha.push_back(d->hs_alpha[h]);
@@ -404,6 +439,11 @@ int gp_mechanism_add_halfspace(gp_mechanism* m, const double point[3], const dou
                                double mu) {
   if (!m || !point || !normal) {
     set_error("gp_mechanism_add_halfspace: null argument");
+    return GP_ERR_INVALID;
+  }
+  const double hn2 = normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2];
+  if (!(std::fabs(hn2 - 1.0) < 1e-9)) {  // the reference takes a UnitVector3 (halfspace.rs:6-11)
+    set_error("halfspace normal is not a unit vector (|n|^2 = %.17g)", hn2);
     return GP_ERR_INVALID;
   }
   if (m->n_hs() >= kMaxHS) {
@@ -478,6 +518,45 @@ int gp_mechanism_supports(const gp_mechanism* m, int32_t* out) {
 
 const char* gp_mechanism_kernel_variant(const gp_mechanism* m) {
   return (m && m->table) ? m->table->name : "";
+}
+
+int gp_mechanism_set_kernel_mode(gp_mechanism* m, int mode) {
+  if (!m || mode < GP_KERNEL_AUTO || mode > GP_KERNEL_SHIPPED) {
+    set_error("gp_mechanism_set_kernel_mode: bad argument");
+    return GP_ERR_INVALID;
+  }
+  const int before = m->kernel_mode;
+  m->kernel_mode = mode;
+  const int rc = finalize_mechanism(m);
+  if (rc != GP_OK) {
+    m->kernel_mode = before;
+    const std::string msg = last_error();
+    finalize_mechanism(m);
+    set_error("%s", msg.c_str());
+  }
+  return rc;
+}
+
+int gp_jit_available(void) { return jit_available(nullptr) ? 1 : 0; }
+
+size_t gp_jit_cache_dir(char* buf, size_t len) {
+  const std::string d = jit_cache_dir();
+  if (buf && len > 0) {
+    const size_t n = d.size() < len - 1 ? d.size() : len - 1;
+    std::memcpy(buf, d.data(), n);
+    buf[n] = '\0';
+  }
+  return d.size();
+}
+
+int gp_mechanism_precompile(const gp_mechanism* m, unsigned kinds, int* n_compiled) {
+  if (!m || !m->table) {
+    set_error("gp_mechanism_precompile: null mechanism");
+    return GP_ERR_INVALID;
+  }
+  // (the contact mode a step launch of this mechanism uses: gp_batch.cu contact_mode)
+  const int contact = m->n_sc() > 0 ? 2 : ((m->n_cp() == 0 || m->n_hs() == 0) ? 0 : (m->n_hs() == 1 ? 1 : 2));
+  return jit_precompile(m->table, contact, kinds, n_compiled);
 }
 
 }  // extern "C"

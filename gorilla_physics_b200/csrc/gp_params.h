@@ -5,9 +5,14 @@
 // what MechanismState::new receives, reference src/mechanism.rs:62-148). Bodies are
 // 0-based here (body b = reference body id b+1, parent -1 = world).
 #pragma once
+#if defined(__CUDACC_RTC__)
+// run-time compilation (gp_jit.cpp): the public header travels with the embedded sources under its bare name
+#include "gorilla_b200.h"
+#else
 #include <cstdint>
 
 #include "../../include/gorilla_b200.h"
+#endif
 
 namespace gp {
 
@@ -73,7 +78,7 @@ struct MechParams {
   double mass[kMaxBodies];
   double spring_k[kMaxBodies];
   double spring_l[kMaxBodies];
-  double armature[kMaxBodies];  // added to the joint's own diagonal entry of H
+  double armature[kMaxBodies];  // added to the joint's own diagonal entry of H by free_velocity only
 
   // ---- constants of the composite-inertia pass, folded by gp_mechanism_create (gp_dynamics.cuh pass 2)
   // A child behind a revolute or fixed joint sits at a constant offset r and its subtree has a

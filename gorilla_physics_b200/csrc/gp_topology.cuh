@@ -391,23 +391,47 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static constexpr bool contact_list(int body) { return body < 0 || body == 4 || body == 8; }  // the wheels (8 points on each rim)
 };
 
-// A specialisation for ONE more tree, chosen when the library is built:
-//   make CUSTOM_NB=4 CUSTOM_PARENTS=-1,0,1,2 CUSTOM_JOINTS=3,1,2,2 CUSTOM_AXES=0,0,0,0 CUSTOM_NAME=hopper2d_FRPP
+// A specialisation for ONE more tree. Two users:
+//  * gp_jit.cpp compiles it at RUN time (NVRTC) for any mechanism no shipped spec matches: the macros below are
+//    the first lines of the translation unit it generates, the policies chosen from the mechanism itself
+//    (which bodies carry many contact points, spring contacts, size);
+//  * a library build with make variables, for deployments without NVRTC:
+//      make CUSTOM_NB=4 CUSTOM_PARENTS=-1,0,1,2 CUSTOM_JOINTS=3,1,2,2 CUSTOM_AXES=0,0,0,0 CUSTOM_NAME=hopper2d_FRPP
 // (0-based parents, -1 = world; joint types 0 fixed / 1 revolute / 2 prismatic / 3 floating; axes 1 = exactly +z,
-// 0 = any; `python tools/custom_topo.py <model>` prints the line for a mechanism). The policies are the defaults
-// the shipped specs converged to: one 256-thread block per SM beyond three bodies, ticket mode there.
+// 0 = any; `python tools/custom_topo.py <model>` prints the line for a mechanism). Policy defaults are what the
+// shipped specs converged to: one 256-thread block per SM beyond three bodies, ticket mode there.
 #ifdef GP_CUSTOM_TOPO_NB
+#ifndef GP_CUSTOM_BLOCK
+#define GP_CUSTOM_BLOCK (GP_CUSTOM_TOPO_NB <= 3 ? 128 : 256)
+#endif
+#ifndef GP_CUSTOM_MIN_BLOCKS
+#define GP_CUSTOM_MIN_BLOCKS 1
+#endif
+#ifndef GP_CUSTOM_SINCOS
+#define GP_CUSTOM_SINCOS true
+#endif
+#ifndef GP_CUSTOM_SPRINGS
+#define GP_CUSTOM_SPRINGS false
+#endif
+#ifndef GP_CUSTOM_TICKETS
+#define GP_CUSTOM_TICKETS (GP_CUSTOM_TOPO_NB > 3)
+#endif
+#ifndef GP_CUSTOM_CONTACT_LIST_MASK
+#define GP_CUSTOM_CONTACT_LIST_MASK 0u  // bit b: body b runs the per-lane list of points in contact
+#endif
 struct SpecCustom {
   static constexpr TopoData data() {
     return {GP_CUSTOM_TOPO_NB, {GP_CUSTOM_TOPO_PARENTS}, {GP_CUSTOM_TOPO_JOINTS}, {GP_CUSTOM_TOPO_AXES}};
   }
   static const char* name() { return GP_CUSTOM_TOPO_NAME; }
-  static constexpr int min_blocks(int) { return 1; }
-  static constexpr int block_size() { return GP_CUSTOM_TOPO_NB <= 3 ? 128 : 256; }
-  static constexpr bool batched_sincos() { return true; }
-  static constexpr bool springs() { return false; }
-  static constexpr bool tickets() { return GP_CUSTOM_TOPO_NB > 3; }
-  static constexpr bool contact_list(int) { return false; }
+  static constexpr int min_blocks(int) { return GP_CUSTOM_MIN_BLOCKS; }
+  static constexpr int block_size() { return GP_CUSTOM_BLOCK; }
+  static constexpr bool batched_sincos() { return GP_CUSTOM_SINCOS; }
+  static constexpr bool springs() { return GP_CUSTOM_SPRINGS; }
+  static constexpr bool tickets() { return GP_CUSTOM_TICKETS; }
+  static constexpr bool contact_list(int body) {
+    return body < 0 ? (GP_CUSTOM_CONTACT_LIST_MASK) != 0u : (((GP_CUSTOM_CONTACT_LIST_MASK) >> body) & 1u) != 0u;
+  }
 };
 #endif
 

@@ -48,6 +48,29 @@ class Controller(enum.IntEnum):
     PENDULUM_SWINGUP_BALANCE = 7     # reference control/mod.rs:98-105
 
 
+class KernelMode(enum.IntEnum):
+    """enum gp_kernel_mode: which device kernels a mechanism runs on."""
+    AUTO = 0      # shipped specialisation, else run-time-compiled (NVRTC), else generic
+    GENERIC = 1   # always the run-time-topology kernel
+    JIT = 2       # always run-time-compiled, even where a shipped specialisation matches
+    SHIPPED = 3   # shipped specialisation, else generic: never compile at run time
+
+
+# gp_mechanism_precompile kinds
+JIT_STEP_SIE, JIT_STEP_RK, JIT_DYNAMICS, JIT_ENERGY = 1, 2, 4, 8
+
+
+def jit_available() -> bool:
+    """NVRTC could be loaded (and GP_JIT is not 0): unknown trees get their own compiled kernels."""
+    return bool(lib().gp_jit_available())
+
+
+def jit_cache_dir() -> str:
+    buf = C.create_string_buffer(4096)
+    lib().gp_jit_cache_dir(buf, len(buf))
+    return buf.value.decode()
+
+
 def _f64(a, shape=None):
     a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
     return a.reshape(shape) if shape is not None else a
@@ -70,7 +93,7 @@ class Mechanism:
 
     # ---- construction -------------------------------------------------------
     @classmethod
-    def from_desc(cls, desc: MechanismDesc) -> "Mechanism":
+    def from_desc(cls, desc: MechanismDesc, kernel: "KernelMode | None" = None) -> "Mechanism":
         """MechanismState::new(treejoints, bodies), reference mechanism.rs:62."""
         keep = {
             "parent": np.ascontiguousarray(desc.parent, dtype=np.int32),
@@ -96,7 +119,10 @@ class Mechanism:
             setattr(d, name, arr.ctypes.data_as(ip if arr.dtype == np.int32 else dp))
         h = C.c_void_p()
         check(lib().gp_mechanism_create(C.byref(d), C.byref(h)))
-        return cls(h)
+        m = cls(h)
+        if kernel is not None:
+            m.set_kernel_mode(kernel)
+        return m
 
     @classmethod
     def from_model(cls, name: str, params: Sequence[float] = ()) -> "Mechanism":
@@ -115,6 +141,18 @@ class Mechanism:
                 self._h = None
         except Exception:
             pass
+
+    def set_kernel_mode(self, mode: "KernelMode") -> "Mechanism":
+        """gp_mechanism_set_kernel_mode: shipped / run-time-compiled / run-time-topology kernels."""
+        check(lib().gp_mechanism_set_kernel_mode(self._h, int(mode)))
+        return self
+
+    def precompile(self, kinds: int = JIT_STEP_SIE | JIT_DYNAMICS) -> int:
+        """Compile this mechanism's run-time-specialised kernels into the on-disk cache (needs no GPU).
+        Returns how many were not cached yet."""
+        n = C.c_int(0)
+        check(lib().gp_mechanism_precompile(self._h, int(kinds), C.byref(n)))
+        return n.value
 
     # ---- queries ---------------------------------------------------------------
     @property
@@ -404,6 +442,9 @@ class MechanismState:
         out = np.empty(self.n_envs, dtype=np.uint32)
         check(lib().gp_batch_status(self._h, _ptr(out)))
         return out
+
+    def clear_status(self):
+        check(lib().gp_batch_clear_status(self._h))
 
 
 # ---- free functions with the reference's names -----------------------------------------------

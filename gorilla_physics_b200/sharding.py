@@ -64,9 +64,22 @@ class ShardedMechanismState:
         v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(self.n_envs, self.n_v))
         self._each(lambda s, lo, hi: s.update(q[lo:hi], v[lo:hi]))
 
+    def _slice_kw(self, kw, lo, hi):
+        """per-environment keyword arguments (tau of shape [n_envs, n_v]) go to each shard as its own rows"""
+        import numpy as np
+        out = dict(kw)
+        tau = out.get("tau")
+        if tau is not None and not isinstance(tau, (int, np.integer)):
+            t = np.asarray(tau, dtype=np.float64)
+            if t.ndim == 2 and t.shape[0] == self.n_envs:
+                out["tau"] = np.ascontiguousarray(t[lo:hi])
+            elif t.size == self.n_envs * self.n_v and t.ndim == 1 and self.n_envs > 1:
+                out["tau"] = np.ascontiguousarray(t.reshape(self.n_envs, self.n_v)[lo:hi])
+        return out
+
     def step(self, dt, **kw):
-        for s in self.shards:  # asynchronous per device
-            s.step(dt, **kw)
+        for s, (lo, hi) in zip(self.shards, self.ranges):  # asynchronous per device
+            s.step(dt, **self._slice_kw(kw, lo, hi))
 
     def synchronize(self):
         for s in self.shards:
@@ -86,7 +99,7 @@ class ShardedMechanismState:
         if not (isinstance(v, np.ndarray) and v.flags.c_contiguous and v.dtype == np.float64):
             raise ValueError("v must be a C-contiguous float64 array (it is updated in place)")
         q2, v2 = q.reshape(self.n_envs, self.n_q), v.reshape(self.n_envs, self.n_v)
-        done = self._each(lambda s, lo, hi: s.simulate(final_time, dt, q2[lo:hi], v2[lo:hi], **kw)[0])
+        done = self._each(lambda s, lo, hi: s.simulate(final_time, dt, q2[lo:hi], v2[lo:hi], **self._slice_kw(kw, lo, hi))[0])
         return done[0]
 
     def status(self):

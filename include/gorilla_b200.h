@@ -63,7 +63,8 @@ enum gp_status_code {
   GP_ERR_UNSUPPORTED = 2, /* VelocityStepping / CCDVelocityStepping (SOCP path, out of scope) */
   GP_ERR_NO_DEVICE = 3,   /* no usable CUDA device: there is no CPU fallback */
   GP_ERR_CUDA = 4,        /* CUDA runtime error, see gp_last_error */
-  GP_ERR_LIMIT = 5        /* mechanism exceeds GP_MAX_* */
+  GP_ERR_LIMIT = 5,       /* mechanism exceeds GP_MAX_* */
+  GP_ERR_JIT = 6          /* run-time specialisation failed (NVRTC missing / compile or load error) */
 };
 
 /* enum Joint, src/joint/mod.rs:22-27 */
@@ -135,9 +136,10 @@ typedef struct gp_mechanism_desc {
   const double* hs_normal;   /* [NH][3] unit outward normal */
   const double* hs_alpha;    /* [NH] */
   const double* hs_mu;       /* [NH] */
-  const double* armature;    /* [NB] reflected drivetrain inertia added to the joint's own mass-matrix
-                                diagonal (revolute.rs:29; used by hybrid/articulated/mod.rs:247); may be
-                                NULL = zeros. Revolute / prismatic joints only. */
+  const double* armature;    /* [NB] reflected drivetrain inertia of revolute joints (revolute.rs:29, joint/mod.rs:96-108);
+                                may be NULL = zeros. As in the reference it enters ONLY gp_batch_free_velocity
+                                (Articulated::update_mass_matrix, hybrid/articulated/mod.rs:247): step, simulate,
+                                dynamics and mass_matrix ignore it. Non-zero on a non-revolute joint is an error. */
   int32_t n_spring_contacts;   /* SpringContact (contact.rs:74-94): ideal spring legs acting against halfspaces */
   const int32_t* sc_body;      /* [NS] body id (1-based) the leg is attached to (at the body-frame origin) */
   const double* sc_l_rest;     /* [NS] rest length */
@@ -176,11 +178,42 @@ int gp_mechanism_add_contact_point(gp_mechanism* mech, int32_t body, const doubl
  * kernels; Runge-Kutta integrators are refused for them like in the reference (simulate.rs:57-69). */
 int gp_mechanism_add_spring_contact(gp_mechanism* mech, int32_t body, double l_rest, const double direction[3],
                                     double k);
+/* (Mechanisms may be extended after batches were created from them, like the reference mutates a
+ * MechanismState in place: halfspaces and contact points take effect at the next call; a new spring contact
+ * re-creates the batch's spring-contact state, all legs unregistered as after MechanismState::new.) */
 int gp_mechanism_n_spring_contacts(const gp_mechanism* mech);
 /* supports[j-1] as a 0/1 row of length NB (mechanism.rs:118-125); out[(j-1)*NB + (i-1)] */
 int gp_mechanism_supports(const gp_mechanism* mech, int32_t* out);
-/* name of the device kernel specialisation this topology maps to ("generic" if none) */
+/* name of the device kernel specialisation this topology maps to: a shipped one ("so101_X6Rz", ...), a
+ * run-time-compiled one ("jit:<joint letters>"), or "generic" (run-time-topology kernel) */
 const char* gp_mechanism_kernel_variant(const gp_mechanism* mech);
+
+/* ---- run-time specialisation ----------------------------------------------------
+ * MechanismState::new accepts any joint tree (mechanism.rs:62-148). Trees the library ships no
+ * specialisation for get one compiled at run time: the mechanism's signature (parents, joint types,
+ * +z axes) and policies (contact points per body, spring contacts) become compile-time constants of
+ * the same kernel sources (embedded in the library), NVRTC compiles them for sm_100a when a kernel
+ * is first launched, and the cubin is cached on disk ($GP_JIT_CACHE, <library dir>/jit_cache,
+ * ~/.cache/gorilla_b200). NVRTC is loaded with dlopen ($GP_NVRTC_LIB, libnvrtc.so.12); without it, or
+ * with GP_JIT=0 in the environment, such trees run the run-time-topology kernel ("generic", several
+ * times slower). */
+enum gp_kernel_mode {
+  GP_KERNEL_AUTO = 0,    /* shipped specialisation, else run-time-compiled, else generic (default) */
+  GP_KERNEL_GENERIC = 1, /* always the run-time-topology kernel */
+  GP_KERNEL_JIT = 2,     /* always run-time-compiled, even where a shipped specialisation matches;
+                            GP_ERR_JIT when NVRTC is not available */
+  GP_KERNEL_SHIPPED = 3  /* shipped specialisation, else generic: never compile at run time */
+};
+int gp_mechanism_set_kernel_mode(gp_mechanism* mech, int mode);
+/* 1 when NVRTC could be loaded (and GP_JIT is not 0) */
+int gp_jit_available(void);
+/* directory compiled kernels are written to (copied into buf, NUL-terminated); returns its length */
+size_t gp_jit_cache_dir(char* buf, size_t len);
+/* Compile (into the cache, without loading: needs NO GPU) the kernels this mechanism would launch:
+ * kinds = bit mask of 1 step/SemiImplicitEuler, 2 step/Runge-Kutta, 4 dynamics (gp_batch_dynamics,
+ * _mass_matrix, _free_velocity), 8 energy/poses. n_compiled (may be NULL) receives the number of
+ * kernels that were not cached yet. A no-op for mechanisms on shipped or generic kernels. */
+int gp_mechanism_precompile(const gp_mechanism* mech, unsigned kinds, int* n_compiled);
 
 /* ---- model builders: src/helpers.rs, src/builders/mod.rs, navbot_builder.rs -----
  * name / params:
@@ -300,8 +333,12 @@ int gp_batch_energy(gp_batch* batch, double* ke_host, double* pe_host, double* s
 int gp_batch_energy_sums_device(gp_batch* batch, double* out_dev);
 /* poses(), mechanism.rs:403-417: body->world isometries, [n_envs][NB][7] (x,y,z,w,t) */
 int gp_batch_poses(gp_batch* batch, double* poses_host);
-/* per-environment status bits, [n_envs] */
+/* per-environment status bits, [n_envs]. Bits accumulate (OR) over steps; gp_batch_set_state with both q and
+ * v, gp_batch_randomize and gp_batch_simulate (which install new states) clear them, as does
+ * gp_batch_clear_status. Spring-contact and controller state are NOT reset by those calls: use
+ * gp_batch_set_spring_contact_state(NULL) / gp_batch_set_controller_state(NULL). */
 int gp_batch_status(gp_batch* batch, uint32_t* status_host);
+int gp_batch_clear_status(gp_batch* batch);
 
 /* ---- measurement helpers --------------------------------------------------------
  * FP64 FMA-chain microbenchmark on `device`: runs for about `seconds`, returns the

@@ -352,7 +352,9 @@ inline void mul_inertia(const M3& J, V3 c, double mass, V3 w, V3 v, V3& ang, V3&
 }
 
 // mechanism.rs:637-696 (+ :592-625, momentum.rs:17-47)
-void mass_matrix(const gpo_mechanism* m, Work& w) {
+// with_armature: Articulated::update_mass_matrix only (hybrid/articulated/mod.rs:199-269); MechanismState's
+// mass_matrix never reads the armature
+void mass_matrix(const gpo_mechanism* m, Work& w, bool with_armature = false) {
   const int nb = m->nb, n_v = m->n_v;
   for (int i = 0; i < n_v * n_v; ++i) w.M[i] = 0.0;
   for (int i = 1; i <= nb; ++i) {
@@ -393,11 +395,13 @@ void mass_matrix(const gpo_mechanism* m, Work& w) {
           w.M[(bi.voff + r) * n_v + (bj.voff + c)] = dot(Fang[r], Sj.ang[c]) + dot(Flin[r], Sj.lin[c]);
     }
   }
-  // armature on the joint's own diagonal entry (hybrid/articulated/mod.rs:247; zero by default, in which
-  // case this is exactly the reference's MechanismState mass matrix)
-  for (int i = 1; i <= nb; ++i) {
-    const Body& bi = m->bodies[i - 1];
-    if ((bi.jtype == J_REV || bi.jtype == J_PRIS) && bi.armature != 0.0) w.M[bi.voff * n_v + bi.voff] += bi.armature;
+  // armature on the joint's own diagonal entry (hybrid/articulated/mod.rs:247; revolute joints only,
+  // joint/mod.rs:96-108)
+  if (with_armature) {
+    for (int i = 1; i <= nb; ++i) {
+      const Body& bi = m->bodies[i - 1];
+      if (bi.jtype == J_REV && bi.armature != 0.0) w.M[bi.voff * n_v + bi.voff] += bi.armature;
+    }
   }
   // mirror the lower triangle (mechanism.rs:688-693)
   for (int i = 0; i < n_v; ++i)
@@ -1097,7 +1101,7 @@ int gpo_free_velocity(const gpo_mechanism* m, const double* q, const double* v, 
   Work w;
   bodies_to_root(m, q, w);
   body_twists(m, v, w);
-  mass_matrix(m, w);
+  mass_matrix(m, w, true);
   const int nb = m->nb, n = m->n_v;
   // bias accelerations: world-frame commutator of body twist and joint twist, summed down the tree
   SV bias[GPO_MAX_BODIES + 1];

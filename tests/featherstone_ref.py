@@ -221,8 +221,7 @@ def dynamics(model: Model, q, v, tau=None, gravity=GRAVITY):
                 H[oi:oi + k, oj:oj + kj] = F.T @ S[j]
                 H[oj:oj + kj, oi:oi + k] = S[j].T @ F
     for i in range(nb):
-        if model.jtype[i] in (REVOLUTE, PRISMATIC):
-            H[model.voff[i], model.voff[i]] += model.armature[i]
+        # (no armature here: MechanismState's dynamics never reads it, only hybrid::Articulated::free_velocity does)
         if model.jtype[i] == PRISMATIC and model.has_spring[i]:
             tau[model.voff[i]] += -model.spring_k[i] * (q[model.qoff[i]] - model.spring_l[i])
     vdot = np.linalg.solve(H, tau - bias) if nv else np.zeros(0)

@@ -82,13 +82,62 @@ def test_kernel_variant_selection():
     expect = {"pendulum": "pendulum_R", "double_pendulum": "double_pendulum_RR", "cart_pole": "cart_pole_PR",
               "so101": "so101_X6Rz", "cube": "floating_F", "ball": "floating_F", "rimless_wheel": "floating_F",
               "hopper": "hopper_FPR", "hopper_1d": "hopper1d_FPP", "quadruped": "quadruped_F8R",
-              "navbot": "navbot_F8Rz", "cart": "generic"}
+              "navbot": "navbot_F8Rz"}
     for name, variant in expect.items():
         assert gp.Mechanism.from_model(name).kernel_variant == variant
-    # an SO-101-shaped chain whose axes are not +z falls back to the run-time topology kernel
+    # trees without a shipped specialisation: compiled at run time for their own topology when NVRTC is
+    # there (gp_jit.cpp), else the run-time-topology kernel; the mode can be forced either way
+    unknown = "jit:P" if gp.jit_available() else "generic"
+    assert gp.Mechanism.from_model("cart").kernel_variant == unknown
+    # an SO-101-shaped chain whose axes are not all +z does not match the shipped so101 kernels
     d = gp.Mechanism.from_model("so101").desc()
     d._axis[3] = np.array([0.0, 1.0, 0.0])
-    assert gp.Mechanism.from_desc(d).kernel_variant == "generic"
+    assert gp.Mechanism.from_desc(d).kernel_variant == ("jit:XRRRRRR" if gp.jit_available() else "generic")
+    assert gp.Mechanism.from_desc(d, kernel=gp.KernelMode.GENERIC).kernel_variant == "generic"
+    assert gp.Mechanism.from_desc(d, kernel=gp.KernelMode.SHIPPED).kernel_variant == "generic"
+    m = gp.Mechanism.from_model("so101")
+    assert m.set_kernel_mode(gp.KernelMode.GENERIC).kernel_variant == "generic"
+    assert m.set_kernel_mode(gp.KernelMode.SHIPPED).kernel_variant == "so101_X6Rz"
+    if gp.jit_available():
+        assert m.set_kernel_mode(gp.KernelMode.JIT).kernel_variant == "jit:XRRRRRR"
+        # the mode survives later changes of the mechanism
+        m.add_halfspace((0, 0, 1), 0.0)
+        assert m.kernel_variant == "jit:XRRRRRR"
+    assert m.set_kernel_mode(gp.KernelMode.AUTO).kernel_variant == "so101_X6Rz"
+    with pytest.raises(GorillaError):
+        m.set_kernel_mode(17)
+
+
+def test_run_time_specialisation_compiles_without_a_gpu(tmp_path, monkeypatch):
+    """gp_mechanism_precompile: NVRTC turns the mechanism's signature + the embedded kernel sources into an
+    sm_100a cubin in the on-disk cache; a second request is a cache hit. Needs no GPU (loading does)."""
+    if not gp.jit_available():
+        pytest.skip("NVRTC not loadable here")
+    from gorilla_physics_b200.mechanism import JIT_DYNAMICS, JIT_ENERGY, JIT_STEP_SIE
+    monkeypatch.setenv("GP_JIT_CACHE", str(tmp_path))
+    assert gp.jit_cache_dir() == str(tmp_path)
+    d = gp.MechanismDesc()  # a tree no shipped spec covers: revolute - prismatic(spring) - revolute(+z)
+    d.add_body(0, gp.REVOLUTE, axis=(0, 1, 0), moment=np.eye(3) * 0.1, cross_part=(0, 0, -0.2), mass=1.0)
+    d.add_body(1, gp.PRISMATIC, axis=(1, 0, 0), moment=np.eye(3) * 0.05, mass=0.5, spring=(30.0, 0.1))
+    d.add_body(2, gp.REVOLUTE, axis=(0, 0, 1), init_iso=gp.iso((0.1, 0, 0)), moment=np.eye(3) * 0.02, mass=0.3)
+    d.add_contact_point(3, (0.0, 0.0, 0.1))
+    d.add_halfspace((0, 0, 1), -1.0)
+    m = gp.Mechanism.from_desc(d)
+    assert m.kernel_variant == "jit:RPR"
+    assert m.precompile(JIT_ENERGY) == 1
+    files = sorted(p.name for p in tmp_path.iterdir() if p.suffix == ".cubin")
+    assert len(files) == 1
+    blob = (tmp_path / files[0]).read_bytes()
+    assert blob.startswith(b"GPJIT1 _ZN2gp13energy_kernel") and b"\x7fELF" in blob[:200]
+    assert m.precompile(JIT_ENERGY) == 0  # cache hit
+    # shipped and generic kernels have nothing to compile
+    assert gp.Mechanism.from_model("so101").precompile(JIT_STEP_SIE | JIT_DYNAMICS) == 0
+    assert gp.Mechanism.from_desc(d, kernel=gp.KernelMode.GENERIC).precompile(JIT_ENERGY) == 0
+    # a different contact-point layout is a different specialisation only when the policy changes
+    for k in range(4):
+        d.add_contact_point(1, (0.0, 0.1 * k, 0.0))
+    m2 = gp.Mechanism.from_desc(d)  # body 1 now runs the per-lane contact list: a new kernel
+    assert m2.precompile(JIT_ENERGY) == 1
 
 
 def test_desc_roundtrip_and_contact_point_order():
@@ -207,7 +256,7 @@ def test_limits_of_the_abi():
     from tests import models
     d = models.maximum_size_mechanism()
     m = gp.Mechanism.from_desc(d)
-    assert m.kernel_variant == "generic" and m.desc().n_bodies == 16 and m.desc().n_v == 24
+    assert m.kernel_variant in ("generic", "jit:FFRRRPRRRPRRRPXX") and m.desc().n_bodies == 16 and m.desc().n_v == 24
     with pytest.raises(GorillaError) as e:
         m.add_contact_point(1, (0, 0, 0))  # the 33rd contact point
     assert e.value.code == _abi.GP_ERR_LIMIT

@@ -460,7 +460,8 @@ def test_armature_adds_to_the_joint_diagonal():  # hybrid/articulated/mod.rs:243
     o = oracle_of(d)
     inertia = m * l * l / 3.0
     torque_g = m * GRAVITY * l / 2.0
-    assert abs(o.dynamics([0.0], [0.0])[0] - torque_g / (inertia + arm)) < 1e-12
+    # MechanismState's dynamics_continuous never reads the armature (only hybrid::Articulated does)
+    assert abs(o.dynamics([0.0], [0.0])[0] - torque_g / inertia) < 1e-12
     assert abs(o.free_velocity([0.0], [0.0], 0.01)[0] - 0.01 * torque_g / (inertia + arm)) < 1e-12
     assert abs(o.free_velocity([0.0], [0.0], 0.01, gravity_enabled=False)[0]) < 1e-15
     # the product's host code carries the armature through the flat description

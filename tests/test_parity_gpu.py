@@ -504,10 +504,14 @@ def test_free_velocity_and_armature():
         ref = np.stack([orc.free_velocity(q[e], v[e], 1e-3, tau=tau[e], gravity_enabled=gravity) for e in range(n)])
         assert rel_err(vf, ref) < TOL_DYN
     np.testing.assert_array_equal(st.free_velocity(0.0), v)
-    # the armature also enters the regular step path (dynamics / step) consistently
+    # the armature does NOT enter MechanismState's own path (dynamics / step / mass_matrix), as in the reference:
+    # same accelerations as the mechanism without armature
     vdot = st.dynamics(tau=tau)
     vdot_ref, _ = orc.batch_dynamics(q, v, tau)
     assert rel_err(vdot, vdot_ref) < TOL_DYN
+    plain = MechanismState(Mechanism.from_model("so101"), n)
+    plain.update(q, v)
+    np.testing.assert_array_equal(plain.dynamics(tau=tau), vdot)
     # quadruped (floating base, generic axes)
     mech = Mechanism.from_model("quadruped")
     orc = oracle_of(mech)
