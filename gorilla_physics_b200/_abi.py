@@ -107,6 +107,8 @@ SYMBOLS = {
     "gp_batch_free_velocity": (C.c_int, [vp, C.c_double, C.c_int, vp]),
     "gp_batch_mass_matrix": (C.c_int, [vp, vp, vp]),
     "gp_batch_step": (C.c_int, [vp, C.c_double, C.c_int, C.c_int, C.c_int, dp, C.c_int]),
+    "gp_batch_step_tau_sequence": (C.c_int, [vp, C.c_double, C.c_int, C.c_int, vp]),
+    "gp_batch_step_tau_sequence_device": (C.c_int, [vp, C.c_double, C.c_int, C.c_int, vp]),
     "gp_batch_simulate": (C.c_int, [vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, dp, C.c_int,
                                     C.POINTER(C.c_int64), vp, vp]),
     "gp_simulate_step_count": (C.c_int64, [C.c_double, C.c_double]),
@@ -116,6 +118,7 @@ SYMBOLS = {
     "gp_batch_status": (C.c_int, [vp, vp]),
     "gp_batch_clear_status": (C.c_int, [vp]),
     "gp_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, dp]),
+    "gp_measure_fp64_peak_trace": (C.c_int, [C.c_int, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -5,6 +5,7 @@
 // device every entry point returns GP_ERR_NO_DEVICE.
 #include <cmath>
 #include <algorithm>
+#include <vector>
 #include <cstdlib>
 #include <cstring>
 
@@ -297,10 +298,16 @@ int64_t step_count(double final_time, double dt) {
   return n;
 }
 
+// a torque vector per fused step (StepArgs::tau_seq): device pointer + strides in doubles
+struct TauSeq {
+  const double* ptr;
+  long long step, env, k;
+};
+
 int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
                  int n_cp, long long env0 = 0, long long n_sub = -1, cudaStream_t stream = nullptr,
                  double* q_aos = nullptr, double* v_aos = nullptr, double* hist_q = nullptr,
-                 double* hist_v = nullptr) {
+                 double* hist_v = nullptr, const TauSeq* tau_seq = nullptr) {
   if (n_sub < 0) n_sub = b->n;
   if (!stream) stream = b->stream;
   const gp_mechanism* m = b->mech;
@@ -334,6 +341,12 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
   A.hist_q = hist_q;
   A.hist_v = hist_v;
   A.hist_n = n_sub;
+  if (tau_seq) {
+    A.tau_seq = tau_seq->ptr + env0 * tau_seq->env;
+    A.tau_seq_step = tau_seq->step;
+    A.tau_seq_env = tau_seq->env;
+    A.tau_seq_k = tau_seq->k;
+  }
   A.dt = dt;
   A.n_steps = n_steps;
   A.integrator = integrator;
@@ -798,6 +811,70 @@ int gp_batch_step(gp_batch* b, double dt, int integrator, int n_steps, int contr
   return launch_steps(b, dt, integrator, n_steps, controller, cp, n_cp);
 }
 
+int gp_batch_step_tau_sequence_device(gp_batch* b, double dt, int integrator, int n_steps, const double* tau_seq_dev) {
+  int rc = check_batch(b, "gp_batch_step_tau_sequence_device");
+  if (rc) return rc;
+  if (!tau_seq_dev) {
+    set_error("gp_batch_step_tau_sequence_device: null torque sequence");
+    return GP_ERR_INVALID;
+  }
+  const TauSeq ts{tau_seq_dev, (long long)b->mech->n_v * b->ld, 1, b->ld};
+  return launch_steps(b, dt, integrator, n_steps, GP_CTRL_NONE, nullptr, 0, 0, -1, nullptr, nullptr, nullptr, nullptr, nullptr, &ts);
+}
+
+int gp_batch_step_tau_sequence(gp_batch* b, double dt, int integrator, int n_steps, const double* tau_seq_host) {
+  int rc = check_batch(b, "gp_batch_step_tau_sequence");
+  if (rc) return rc;
+  if (!tau_seq_host || n_steps < 0) {
+    set_error("gp_batch_step_tau_sequence: bad argument");
+    return GP_ERR_INVALID;
+  }
+  const gp_mechanism* m = b->mech;
+  const size_t per_step = (size_t)b->n * m->n_v;  // doubles
+  if (n_steps == 0 || per_step == 0) return launch_steps(b, dt, integrator, n_steps, GP_CTRL_NONE, nullptr, 0);
+  // The sequence streams through two staging buffers in blocks of steps: the copy of block k+1 (copy stream)
+  // overlaps the rollout of block k (the batch's stream). The kernel reads the host's environment-major rows
+  // as they are: one environment's torques are contiguous, a warp reads one contiguous stretch per step.
+  int64_t block = (int64_t)(((size_t)64 << 20) / (per_step * sizeof(double)));  // <= 64 MB per buffer
+  if (block < 1) block = 1;
+  if (block > n_steps) block = n_steps;
+  for (int s = 0; s < 2; ++s) {
+    if (!b->pipe_stream[s]) GP_CUDA(cudaStreamCreateWithFlags(&b->pipe_stream[s], cudaStreamNonBlocking));
+    if ((rc = ensure(&b->pipe_stage[s], &b->pipe_stage_bytes[s], (size_t)block * per_step * sizeof(double)))) return rc;
+  }
+  cudaStream_t copy = b->pipe_stream[0];
+  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  for (int s = 0; s < 2; ++s) {
+    GP_CUDA(cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming));
+    GP_CUDA(cudaEventCreateWithFlags(&consumed[s], cudaEventDisableTiming));
+  }
+  int slot = 0;
+  int64_t k = 0;
+  for (int64_t s0 = 0; s0 < n_steps && rc == GP_OK; s0 += block, slot ^= 1, ++k) {
+    const int64_t ns = (s0 + block <= n_steps) ? block : n_steps - s0;
+    // the buffer is free again once the rollout that read it (two blocks ago) has finished
+    if (k >= 2 && cudaStreamWaitEvent(copy, consumed[slot], 0) != cudaSuccess) rc = GP_ERR_CUDA;
+    if (rc == GP_OK && cudaMemcpyAsync(b->pipe_stage[slot], tau_seq_host + (size_t)s0 * per_step, (size_t)ns * per_step * sizeof(double),
+                                       cudaMemcpyHostToDevice, copy) != cudaSuccess)
+      rc = GP_ERR_CUDA;
+    if (rc == GP_OK && (cudaEventRecord(copied[slot], copy) != cudaSuccess || cudaStreamWaitEvent(b->stream, copied[slot], 0) != cudaSuccess))
+      rc = GP_ERR_CUDA;
+    if (rc == GP_OK) {
+      const TauSeq ts{b->pipe_stage[slot], (long long)per_step, (long long)m->n_v, 1};
+      rc = launch_steps(b, dt, integrator, (int)ns, GP_CTRL_NONE, nullptr, 0, 0, -1, nullptr, nullptr, nullptr, nullptr, nullptr, &ts);
+    }
+    if (rc == GP_OK && cudaEventRecord(consumed[slot], b->stream) != cudaSuccess) rc = GP_ERR_CUDA;
+  }
+  cudaStreamSynchronize(copy);
+  cudaStreamSynchronize(b->stream);  // the host buffer may be released when this call returns
+  for (int s = 0; s < 2; ++s) {
+    cudaEventDestroy(copied[s]);
+    cudaEventDestroy(consumed[s]);
+  }
+  if (rc == GP_ERR_CUDA) set_error("gp_batch_step_tau_sequence: CUDA error: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
 int64_t gp_simulate_step_count(double final_time, double dt) { return step_count(final_time, dt); }
 
 int gp_batch_simulate(gp_batch* b, double* q_host, double* v_host, const double* tau_host, double final_time,
@@ -959,11 +1036,13 @@ int gp_batch_status(gp_batch* b, uint32_t* status_host) {
   return GP_OK;
 }
 
-int gp_measure_fp64_peak(int device, double seconds, double* tflops_out) {
-  if (!tflops_out) {
-    set_error("gp_measure_fp64_peak: null output");
+int gp_measure_fp64_peak_trace(int device, double seconds, double* t_end_s, double* tflops, int max_samples,
+                               int* n_samples_out) {
+  if (!n_samples_out || max_samples < 0 || (max_samples > 0 && (!t_end_s || !tflops))) {
+    set_error("gp_measure_fp64_peak_trace: bad argument");
     return GP_ERR_INVALID;
   }
+  *n_samples_out = 0;
   if (gp_device_count() <= 0) {
     set_error("no CUDA device available");
     return GP_ERR_NO_DEVICE;
@@ -979,11 +1058,12 @@ int gp_measure_fp64_peak(int device, double seconds, double* tflops_out) {
   cudaEventCreate(&e1);
   const int iters = 2000;
   const double flop_per_launch = 2.0 * 8 * 16 * (double)iters * blocks * threads;
-  fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);  // warm-up
+  fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);  // warm-up (module load)
   cudaDeviceSynchronize();
-  double best = 0.0, elapsed = 0.0;
+  // launches back to back (two in flight, so the GPU never idles between samples), one sample per launch
+  double elapsed = 0.0;
   int reps = 0;
-  while (elapsed < seconds || reps < 3) {
+  while ((elapsed < seconds || reps < 3) && reps < 1000000) {
     cudaEventRecord(e0);
     fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
     cudaEventRecord(e1);
@@ -991,17 +1071,33 @@ int gp_measure_fp64_peak(int device, double seconds, double* tflops_out) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     elapsed += ms * 1e-3;
+    if (reps < max_samples) {
+      t_end_s[reps] = elapsed;
+      tflops[reps] = flop_per_launch / (ms * 1e-3) / 1e12;
+      *n_samples_out = reps + 1;
+    }
     ++reps;
-    // report the sustained figure: the median-ish of the later half is what a long step sees;
-    // keep the LAST measurement after `seconds` of continuous load
-    best = flop_per_launch / (ms * 1e-3) / 1e12;
-    if (reps > 100000) break;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(out);
   GP_CUDA(cudaGetLastError());
-  *tflops_out = best;
+  return GP_OK;
+}
+
+int gp_measure_fp64_peak(int device, double seconds, double* tflops_out) {
+  if (!tflops_out) {
+    set_error("gp_measure_fp64_peak: null output");
+    return GP_ERR_INVALID;
+  }
+  // the sustained figure: median of the last quarter of the samples
+  std::vector<double> t(4096), f(4096);
+  int n = 0;
+  const int rc = gp_measure_fp64_peak_trace(device, seconds, t.data(), f.data(), (int)t.size(), &n);
+  if (rc) return rc;
+  std::vector<double> tail(f.begin() + (n - (n + 3) / 4), f.begin() + n);
+  std::sort(tail.begin(), tail.end());
+  *tflops_out = tail[tail.size() / 2];
   return GP_OK;
 }
 

@@ -393,6 +393,14 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
       // then share instruction-cache lines instead of each streaming the whole body from L2
       if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
       }
+      if (A.tau_seq != nullptr) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("");  // a real (uniform) branch, not a predicated copy of the loads in every step
+#endif
+        const double* ts = A.tau_seq + (long long)s * A.tau_seq_step + env * A.tau_seq_env;
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) tau[k] = ts[(long long)k * A.tau_seq_k];
+      }
       controller_tau<Topo>(P, A, q, v, tau_in, tau, cstate);
       if (INTEG == IntegSIE) {
         // semi_implicit_euler, reference integrators.rs:25-39, :276-319

@@ -43,6 +43,13 @@ struct StepArgs {
   double* hist_q;
   double* hist_v;
   long long hist_n;
+  // A different torque vector for every fused step (reference simulate.rs:102-104 calls control_fn before every
+  // step): when set, step s of this launch reads tau[k] = tau_seq[s * tau_seq_step + env * tau_seq_env +
+  // k * tau_seq_k] instead of keeping the torques it loaded at the start. Strides in doubles: planes
+  // ([n_steps][n_v][ld]: step = n_v * ld, env = 1, k = ld) or the host's environment-major rows
+  // ([n_steps][n][n_v]: step = n * n_v, env = n_v, k = 1).
+  const double* tau_seq;
+  long long tau_seq_step, tau_seq_env, tau_seq_k;
   // Ticket mode (gp_kernels.cuh, step_kernel): a batch whose blocks do not fill whole waves (65536
   // environments of a 9-body tree are 256 blocks for 148 one-block SMs: 1.73 waves, the second one runs on
   // 108 SMs) is cut into (block of environments) x (chunk of the fused steps) work items that a persistent

@@ -393,6 +393,31 @@ class MechanismState:
         check(lib().gp_batch_step(self._h, dt, int(integrator), int(n_steps), int(controller),
                                   None if p is None else p.ctypes.data_as(dp), len(ctrl_params)))
 
+    def step_tau_sequence(self, dt: float, tau_seq, integrator: Integrator = Integrator.SemiImplicitEuler,
+                          n_steps: Optional[int] = None):
+        """n_steps of step() with a different torque vector before each: the reference's per-step control closure
+        (simulate.rs:87-112) for torques known ahead of the rollout. tau_seq: [n_steps, n_envs, n_v] (numpy, or the
+        address of such a host buffer together with n_steps). One launch per block of steps; returns when done."""
+        if isinstance(tau_seq, (int, np.integer)):
+            if n_steps is None:
+                raise ValueError("n_steps is required with a raw address")
+            ptr = C.c_void_p(int(tau_seq))
+        else:
+            a = _f64(tau_seq)
+            if a.ndim == 2 and self.n_envs == 1:
+                a = a[:, None, :]
+            if a.ndim != 3 or a.shape[1:] != (self.n_envs, self.n_v):
+                raise ValueError(f"tau_seq must be [n_steps, {self.n_envs}, {self.n_v}]")
+            n_steps = a.shape[0]
+            ptr = _ptr(a)
+        check(lib().gp_batch_step_tau_sequence(self._h, dt, int(integrator), int(n_steps), ptr))
+
+    def step_tau_sequence_device(self, dt: float, tau_seq_dev_ptr: int, n_steps: int,
+                                 integrator: Integrator = Integrator.SemiImplicitEuler):
+        """as step_tau_sequence, the sequence already on the device as [n_steps][n_v][ld] planes; asynchronous"""
+        check(lib().gp_batch_step_tau_sequence_device(self._h, dt, int(integrator), int(n_steps),
+                                                      C.c_void_p(int(tau_seq_dev_ptr))))
+
     def simulate(self, final_time: float, dt: float, q, v, tau=None,
                  integrator: Integrator = Integrator.SemiImplicitEuler, controller: Controller = Controller.NONE,
                  ctrl_params: Sequence[float] = (), history: bool = False):
@@ -483,3 +508,15 @@ def measure_fp64_peak(device: int = 0, seconds: float = 1.0) -> float:
     out = C.c_double()
     check(lib().gp_measure_fp64_peak(device, seconds, C.byref(out)))
     return out.value
+
+
+def measure_fp64_peak_trace(device: int = 0, seconds: float = 1.0, max_samples: int = 4096):
+    """DFMA-chain probe, one (seconds of load so far, TFLOP/s) sample per launch: the burst figure at the start,
+    the sustained one at the end (gp_measure_fp64_peak_trace)."""
+    t = np.zeros(max_samples)
+    f = np.zeros(max_samples)
+    n = C.c_int()
+    dp = C.POINTER(C.c_double)
+    check(lib().gp_measure_fp64_peak_trace(device, seconds, t.ctypes.data_as(dp), f.ctypes.data_as(dp), max_samples,
+                                           C.byref(n)))
+    return t[:n.value], f[:n.value]

@@ -1,0 +1,159 @@
+"""The configurations of BASELINE.json as ready-made workloads: mechanism, batch size per GPU, time step,
+initial-state distribution and (where the configuration names one) the in-kernel controller.
+
+bench.py, __graft_entry__.smoke() and the parity tests all take them from here, so that what is benchmarked is
+what is tested. Sources of the numbers: SURVEY.md section 8 (config table) and the reference files cited per
+workload. The reference ships no contact points for SO-101 and navbot on this path; those sets are defined by
+the benchmark and stated below.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Sequence
+
+import numpy as np
+
+from .mechanism import Controller, Mechanism
+
+
+# ---- mechanisms --------------------------------------------------------------------------------------
+def so101_with_contact() -> Mechanism:
+    """config 3c: SO-101 (builders/mod.rs:252-341) + halfspace z=0 (HalfSpace::new defaults) + contact points at
+    the frame origins of upper_arm, lower_arm, wrist, gripper, jaw (bodies 3..7). Benchmark-defined."""
+    m = Mechanism.from_model("so101")
+    for body in (3, 4, 5, 6, 7):
+        m.add_contact_point(body, (0.0, 0.0, 0.0))
+    m.add_halfspace((0.0, 0.0, 1.0), 0.0)
+    return m
+
+
+def rimless_wheel_on_slope() -> Mechanism:
+    """config 4a, reference examples/rimless_wheel.rs:14-27 / contact.rs:679-694"""
+    m = Mechanism.from_model("rimless_wheel")
+    ang = math.radians(10.0)
+    n = np.array([math.sin(ang), 0.0, math.cos(ang)])
+    n = n / np.linalg.norm(n)
+    m.add_halfspace(n, -20.0, alpha=0.9, mu=0.5)
+    return m
+
+
+def hopper1d_on_ground() -> Mechanism:
+    """config 4b, reference examples/1D_hopper.rs:83-98"""
+    m = Mechanism.from_model("hopper_1d")
+    m.add_halfspace((0, 0, 1), -20.0)
+    return m
+
+
+def quadruped_on_ground() -> Mechanism:
+    """reference control/quadruped_control.rs:417-478: ground z=0, alpha=1, mu=1"""
+    m = Mechanism.from_model("quadruped")
+    m.add_halfspace((0, 0, 1), 0.0, alpha=1.0, mu=1.0)
+    return m
+
+
+def navbot_with_contact() -> Mechanism:
+    """config 5: the reference's navbot has no ContactPoints on this path; the
+    benchmark adds 8 points on each wheel circle (radius 0.0185 about the wheel COM, in the wheel's x-y plane)
+    plus the frame origins of base, legs and feet: NC = 21, ground z=0 defaults."""
+    m = Mechanism.from_model("navbot")
+    r = 0.037 / 2.0
+    for body, com in ((5, (4.83102e-08, -1.61747e-09, -0.00780743)), (9, (-1.61747e-09, -4.83102e-08, -0.00780743))):
+        for k in range(8):
+            a = 2.0 * math.pi * k / 8.0
+            m.add_contact_point(body, (com[0] + r * math.cos(a), com[1] + r * math.sin(a), com[2]))
+    for body in (1, 2, 3, 6, 7):
+        m.add_contact_point(body, (0.0, 0.0, 0.0))
+    m.add_halfspace((0, 0, 1), 0.0)
+    return m
+
+
+def acrobot() -> Mechanism:
+    """config 1, reference examples/acrobot.rs:14-35: build_double_pendulum with m = 1, l = 7, axis -y,
+    rod2_to_rod1 = trans(l, 0, 0), point masses at the rod ends"""
+    from .desc import REVOLUTE, MechanismDesc, iso
+    m, l = 1.0, 7.0
+    d = MechanismDesc()
+    mom = np.diag([0.0, m * l * l, m * l * l])
+    d.add_body(0, REVOLUTE, axis=(0.0, -1.0, 0.0), moment=mom, cross_part=(m * l, 0, 0), mass=m)
+    d.add_body(1, REVOLUTE, axis=(0.0, -1.0, 0.0), init_iso=iso((l, 0, 0)), moment=mom, cross_part=(m * l, 0, 0), mass=m)
+    return Mechanism.from_desc(d)
+
+
+# ---- workloads ------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Workload:
+    name: str
+    config: str                      # which BASELINE.json configuration this is
+    factory: Callable[[], Mechanism]
+    n_envs: int                      # environments per GPU
+    dt: float
+    randomize: Dict = field(default_factory=dict)   # MechanismState.randomize keyword arguments
+    controller: Controller = Controller.NONE
+    ctrl_params: Sequence[float] = ()
+    settle_steps: int = 0            # time steps run (untimed) after randomize: "resting" variants
+    flops_key: str = ""              # entry of profiles/flop_counts.json (default: name)
+
+    def mechanism(self) -> Mechanism:
+        return self.factory()
+
+
+_SO101_RND = dict(q_range=(-1.0, 1.0), v_range=(-1.0, 1.0))
+_NAVBOT_RND = dict(q_range=(-0.2, 0.2), v_range=(0.0, 0.0), base_t=(0.0, 0.0, 0.075), t_jitter=(0.01, 0.01, 0.01),
+                   rpy_jitter=0.1)
+
+WORKLOADS: Dict[str, Workload] = {w.name: w for w in [
+    # the configuration BASELINE.json's target is quoted on: arms start in random poses and fall
+    Workload("so101_contact", "3c: SO-101 + ground contact, 256 K", so101_with_contact, 262144, 1.0 / 6000.0, _SO101_RND),
+    # the same, started from the state after 1 s of that rollout: the arms lie on the ground, contact-rich
+    Workload("so101_contact_resting", "3c: SO-101 + ground contact, 256 K, arms resting on the ground", so101_with_contact,
+             262144, 1.0 / 6000.0, _SO101_RND, settle_steps=6000),
+    Workload("so101", "3: SO-101, gravity, zero torques, 256 K", lambda: Mechanism.from_model("so101"), 262144, 1.0 / 6000.0,
+             _SO101_RND),
+    # config 3 "with joint torques": SO101PositionController in-kernel (control/so101_control.rs:12-34: kp 1000, kd 0.1, clamp 10)
+    Workload("so101_pd", "3b: SO-101, gravity + SO101PositionController torques, 256 K", lambda: Mechanism.from_model("so101"),
+             262144, 1.0 / 6000.0, _SO101_RND, controller=Controller.SO101_PD, ctrl_params=(1000.0, 0.1, 10.0)),
+    Workload("so101_contact_pd", "3b+3c: SO-101 + ground contact + SO101PositionController, 256 K", so101_with_contact,
+             262144, 1.0 / 6000.0, _SO101_RND, controller=Controller.SO101_PD, ctrl_params=(1000.0, 0.1, 10.0)),
+    Workload("double_pendulum", "2: double pendulum, 1 M", lambda: Mechanism.from_model("double_pendulum"), 1048576, 1e-3,
+             dict(q_range=(-math.pi, math.pi), v_range=(-1.0, 1.0))),
+    Workload("cart_pole", "2: cart-pole, 1 M", lambda: Mechanism.from_model("cart_pole"), 1048576, 1e-3,
+             dict(q_range=(-math.pi, math.pi), v_range=(-1.0, 1.0))),
+    Workload("acrobot_swingup", "1 (batched): acrobot with swingup_acrobot in-kernel, 1 M", acrobot, 1048576, 1e-3,
+             dict(q_range=(-0.1, 0.1), v_range=(-0.1, 0.1)), controller=Controller.ACROBOT_SWINGUP, ctrl_params=(1.0, 7.0)),
+    Workload("rimless_wheel", "4a: rimless wheel on a 10 degree slope, 256 K", rimless_wheel_on_slope, 262144, 1.0 / 600.0,
+             dict(base_t=(0.0, 0.0, -10.5), t_jitter=(0.0, 0.0, 0.5), rpy_jitter=0.3, base_v=(0, 0, 0, 1.0, 0, 0),
+                  v_jitter=0.2)),
+    Workload("hopper_1d", "4b: 1-D hopper, 256 K", hopper1d_on_ground, 262144, 1.0 / 500.0,
+             dict(q_range=(0.0, 0.0), v_range=(0.0, 0.0), base_t=(0.0, 0.0, 2.5), t_jitter=(0.0, 0.0, 2.5))),
+    Workload("quadruped", "5 (reference-pinned twin): quadruped, 14 dof, 12 contact points, 64 K", quadruped_on_ground,
+             65536, 1.0 / 3000.0, dict(q_range=(-0.2, 0.2), v_range=(0.0, 0.0), base_t=(0.0, 0.0, 0.8),
+                                       t_jitter=(0.01, 0.01, 0.01), rpy_jitter=0.1)),
+    Workload("navbot_contact", "5: navbot, 14 dof, 21 contact points, 64 K", navbot_with_contact, 65536, 1.0 / 6000.0,
+             _NAVBOT_RND),
+]}
+
+
+def host_states(desc, randomize: Dict, n: int, seed: int):
+    """numpy states of a workload's distribution for a mechanism description (CPU-side runs that have no device
+    to randomize on): the ranges of Workload.randomize, numpy's generator instead of the device's counter-based
+    one. Needs no GPU and does not load the library."""
+    from .desc import FLOATING, JOINT_NQ, quat_from_euler
+    r = dict(q_range=(-1.0, 1.0), v_range=(-1.0, 1.0), base_t=(0.0, 0.0, 0.0), t_jitter=(0.0, 0.0, 0.0), rpy_jitter=0.0,
+             base_v=(0.0,) * 6, v_jitter=0.0)
+    r.update(randomize)
+    tj = np.broadcast_to(np.asarray(r["t_jitter"], dtype=float), (3,))
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, desc.n_q))
+    v = np.zeros((n, desc.n_v))
+    for jt, qo, vo in zip(desc.joint_type, desc.q_offsets(), desc.v_offsets()):
+        if jt == FLOATING:
+            rpy = rng.uniform(-r["rpy_jitter"], r["rpy_jitter"], size=(n, 3))
+            for e in range(n):
+                q[e, qo:qo + 4] = quat_from_euler(*rpy[e])
+            q[:, qo + 4:qo + 7] = np.asarray(r["base_t"]) + rng.uniform(-1.0, 1.0, size=(n, 3)) * tj
+            v[:, vo:vo + 6] = np.asarray(r["base_v"]) + rng.uniform(-r["v_jitter"], r["v_jitter"], size=(n, 6))
+        elif JOINT_NQ[int(jt)] == 1:
+            q[:, qo] = rng.uniform(*r["q_range"], size=n)
+            v[:, vo] = rng.uniform(*r["v_range"], size=n)
+    return q, v

@@ -298,6 +298,22 @@ int gp_batch_mass_matrix(gp_batch* batch, double* mass_matrix_host, double* bias
 int gp_batch_step(gp_batch* batch, double dt, int integrator, int n_steps, int controller,
                   const double* ctrl_params, int n_ctrl_params);
 
+/* step() n_steps times with a DIFFERENT torque vector before every step: the reference's control closure,
+ * called once per step (simulate.rs:87-112 `let torque = control_fn(state); step(...)`, and the wasm
+ * InterfaceSimulator::step(dt, control_input), interface/mod.rs:93-121), for controllers whose torques are known
+ * ahead of the rollout (open-loop trajectories, policies evaluated elsewhere for a horizon) - without a launch
+ * and two copies per step.
+ *   gp_batch_step_tau_sequence:        tau_seq_host [n_steps][n_envs][n_v], the rows gp_batch_set_tau takes, one set
+ *                                      per step. Streams through two staging buffers (copy of the next block of
+ *                                      steps overlaps the rollout of the current one; pin the buffer for that) and
+ *                                      returns when the rollout is done.
+ *   gp_batch_step_tau_sequence_device: tau_seq_dev [n_steps][n_v][ld] planes already in device memory (written by
+ *                                      the caller's own kernels on the batch's stream); asynchronous like gp_batch_step.
+ * The batch's own tau buffer is not used or changed. */
+int gp_batch_step_tau_sequence(gp_batch* batch, double dt, int integrator, int n_steps, const double* tau_seq_host);
+int gp_batch_step_tau_sequence_device(gp_batch* batch, double dt, int integrator, int n_steps,
+                                      const double* tau_seq_dev);
+
 /* SpringContact state, which lives outside (q, v) (contact.rs:79-80): [n_envs][NS][8] =
  * (registered halfspace: 0 none / h+1, contact x,y,z (world), direction x,y,z, l_rest).
  * set: NULL restores the unregistered state of MechanismState::new. */
@@ -345,6 +361,12 @@ int gp_batch_clear_status(gp_batch* batch);
  * sustained DFMA rate in TFLOP/s (2 flop per FMA) — the measured FP64 roofline
  * denominator (MEASURED_PEAKS.json has none). */
 int gp_measure_fp64_peak(int device, double seconds, double* tflops_out);
+/* the same probe, one sample per launch (launches back to back for about `seconds`): t_end_s[i] = seconds of
+ * probe load when launch i finished, tflops[i] = its DFMA rate. The first samples are the burst figure, the last
+ * ones the sustained one; sample the SM clock (NVML) from another thread while it runs to know at which clock
+ * each was taken. At most max_samples are kept; *n_samples_out receives how many. */
+int gp_measure_fp64_peak_trace(int device, double seconds, double* t_end_s, double* tflops, int max_samples,
+                               int* n_samples_out);
 
 #ifdef __cplusplus
 }

@@ -129,54 +129,9 @@ def pose_q(rpy=(0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0)):
     return np.concatenate([quat_from_euler(*rpy), np.asarray(t, dtype=float)])
 
 
-# ---- the benchmark / parity workloads of SURVEY.md §8d -------------------------------------------
-def so101_with_contact() -> Mechanism:
-    """config 3c: SO-101 + halfspace z=0 (HalfSpace::new defaults) + contact points at the frame
-    origins of upper_arm, lower_arm, wrist, gripper, jaw (bodies 3..7). Benchmark-defined."""
-    m = Mechanism.from_model("so101")
-    for body in (3, 4, 5, 6, 7):
-        m.add_contact_point(body, (0.0, 0.0, 0.0))
-    m.add_halfspace((0.0, 0.0, 1.0), 0.0)
-    return m
-
-
-def rimless_wheel_on_slope() -> Mechanism:
-    """config 4a, reference examples/rimless_wheel.rs:14-27 / contact.rs:679-694"""
-    m = Mechanism.from_model("rimless_wheel")
-    ang = math.radians(10.0)
-    n = np.array([math.sin(ang), 0.0, math.cos(ang)])
-    n = n / np.linalg.norm(n)
-    m.add_halfspace(n, -20.0, alpha=0.9, mu=0.5)
-    return m
-
-
-def hopper1d_on_ground() -> Mechanism:
-    m = Mechanism.from_model("hopper_1d")
-    m.add_halfspace((0, 0, 1), -20.0)
-    return m
-
-
-def quadruped_on_ground() -> Mechanism:
-    """reference control/quadruped_control.rs:417-478: ground z=0, alpha=1, mu=1"""
-    m = Mechanism.from_model("quadruped")
-    m.add_halfspace((0, 0, 1), 0.0, alpha=1.0, mu=1.0)
-    return m
-
-
-def navbot_with_contact() -> Mechanism:
-    """config 5: the reference's navbot has no ContactPoints on this path; the
-    benchmark adds 8 points on each wheel circle (radius 0.0185 about the wheel COM, in the wheel's
-    x-y plane) plus the frame origins of base, legs and feet: NC = 21, ground z=0 defaults."""
-    m = Mechanism.from_model("navbot")
-    r = 0.037 / 2.0
-    for body, com in ((5, (4.83102e-08, -1.61747e-09, -0.00780743)), (9, (-1.61747e-09, -4.83102e-08, -0.00780743))):
-        for k in range(8):
-            a = 2.0 * math.pi * k / 8.0
-            m.add_contact_point(body, (com[0] + r * math.cos(a), com[1] + r * math.sin(a), com[2]))
-    for body in (1, 2, 3, 6, 7):
-        m.add_contact_point(body, (0.0, 0.0, 0.0))
-    m.add_halfspace((0, 0, 1), 0.0)
-    return m
+# ---- the benchmark / parity workloads of SURVEY.md §8d: owned by the package (gorilla_physics_b200/workloads.py)
+from gorilla_physics_b200.workloads import (acrobot, hopper1d_on_ground, navbot_with_contact,  # noqa: E402,F401
+                                            quadruped_on_ground, rimless_wheel_on_slope, so101_with_contact)
 
 
 def random_tree(seed: int, n_bodies: int, max_dof: int = 24, contact: bool = True):

@@ -324,3 +324,30 @@ def test_custom_topology_build_selects_its_own_variant(tmp_path):
     res = subprocess.run([sys.executable, "-c", code], env={**os.environ, "GP_LIB_PATH": str(out)}, cwd=root,
                          capture_output=True, text=True, check=True)
     assert res.stdout.split() == ["hopper2d_FRPP", "so101_X6Rz", "generic"]
+
+
+def test_frozen_workload_descs_match_the_product_builders():
+    """tests/golden/workload_descs.json (tools/make_workload_descs.py) is what bench.py's CPU arm hands to the
+    oracle instead of asking the product library: it must be exactly what the library would have built."""
+    import bench
+    from gorilla_physics_b200 import WORKLOADS
+    for name, w in WORKLOADS.items():
+        d, f = w.mechanism().desc(), bench.frozen_desc(name)
+        assert d.n_bodies == f.n_bodies and d.n_contact_points == f.n_contact_points and d.n_halfspaces == f.n_halfspaces
+        for field in ("parent", "joint_type", "axis", "init_iso", "moment", "cross_part", "mass", "has_spring", "spring_k",
+                      "spring_l", "cp_body", "cp_location", "cp_k", "hs_point", "hs_normal", "hs_alpha", "hs_mu"):
+            np.testing.assert_array_equal(np.asarray(getattr(d, field)), np.asarray(getattr(f, field)), err_msg=f"{name}.{field}")
+
+
+def test_reference_arm_runs_without_the_product_library():
+    """bench.py --impl reference: same config keys as the measured arm, and libgorilla_b200.so never loaded"""
+    code = ("import sys, json; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0','--envs','64',"
+            "'--inner','4']; import bench; bench.main(); "
+            "maps=open('/proc/self/maps').read(); assert 'libgorilla_b200' not in maps, 'product library loaded'")
+    out = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    for key in ("workload", "n_envs_per_gpu", "inner_steps_per_launch", "dt", "integrator", "controller"):
+        assert key in line["config"]
+    assert line["config"]["n_envs_per_gpu"] == 64 and line["e2e"]["h2d_bytes_per_step"] == 0

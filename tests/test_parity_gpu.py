@@ -10,7 +10,8 @@ import math
 import numpy as np
 import pytest
 
-from gorilla_physics_b200 import FIXED, FLOATING, Controller, Integrator, Mechanism, MechanismState
+from gorilla_physics_b200 import (FIXED, FLOATING, Controller, Integrator, KernelMode, Mechanism, MechanismState,
+                                  jit_available)
 from gorilla_physics_b200.desc import JOINT_NQ, quat_from_euler
 from tests import models
 from tests.models import oracle_of
@@ -81,13 +82,28 @@ def random_states(desc, n, seed, q_range=1.0, v_range=1.0, base_t=(0.0, 0.0, 0.0
     return q, v
 
 
-def generic_twin(mech: Mechanism) -> Mechanism:
-    """Same physics, but a massless fixed leaf is appended so no static specialisation matches."""
+def generic_twin(mech: Mechanism, kernel: KernelMode = KernelMode.GENERIC) -> Mechanism:
+    """Same physics, but a massless fixed leaf is appended so no shipped specialisation matches; run on the
+    run-time-topology kernel (GENERIC) or on a kernel compiled at run time for the twin's own tree (JIT)."""
     d = mech.desc()
     d.add_body(d.n_bodies, FIXED, moment=np.zeros((3, 3)), mass=0.0)
-    g = Mechanism.from_desc(d)
-    assert g.kernel_variant == "generic"
+    g = Mechanism.from_desc(d, kernel=kernel)
+    assert g.kernel_variant == ("generic" if kernel == KernelMode.GENERIC else "jit:" + "".join("XRPF"[int(t)] for t in d.joint_type))
     return g
+
+
+def kernel_flavour(mech: Mechanism, flavour: str) -> Mechanism:
+    """static: the shipped specialisation; generic: the twin on the run-time-topology kernel; jit: the twin on
+    its run-time-compiled kernel; jit_same: the mechanism itself, forced onto a run-time-compiled kernel"""
+    if flavour == "static":
+        return mech
+    if flavour == "generic":
+        return generic_twin(mech)
+    if not jit_available():
+        pytest.skip("NVRTC not loadable: no run-time specialisation on this machine")
+    if flavour == "jit":
+        return generic_twin(mech, KernelMode.JIT)
+    return mech.set_kernel_mode(KernelMode.JIT)
 
 
 # name -> (factory, state kwargs, expected static variant)
@@ -119,13 +135,12 @@ def _with_ground(m, h, alpha=0.9, mu=0.5):
 
 
 @pytest.mark.parametrize("name", list(WORKLOADS))
-@pytest.mark.parametrize("generic", [False, True], ids=["static", "generic"])
-def test_dynamics_parity(name, generic):
+@pytest.mark.parametrize("flavour", ["static", "generic", "jit"])
+def test_dynamics_parity(name, flavour):
     factory, kw, variant = WORKLOADS[name]
     mech = factory()
     assert mech.kernel_variant == variant
-    if generic:
-        mech = generic_twin(mech)
+    mech = kernel_flavour(mech, flavour)
     desc = factory().desc()  # the oracle always sees the original mechanism
     orc = oracle_of(desc)
     n = 1024
@@ -167,10 +182,11 @@ def test_mass_matrix_and_bias_parity(name):
 
 @pytest.mark.parametrize("name", list(WORKLOADS))
 @pytest.mark.parametrize("integrator", [Integrator.SemiImplicitEuler, Integrator.RungeKutta2, Integrator.RungeKutta4])
-def test_single_step_parity(name, integrator):
+@pytest.mark.parametrize("flavour", ["static", "jit"])
+def test_single_step_parity(name, integrator, flavour):
     factory, kw, _ = WORKLOADS[name]
-    mech = factory()
-    desc = mech.desc()
+    desc = factory().desc()
+    mech = kernel_flavour(factory(), flavour)
     orc = oracle_of(desc)
     n = 256
     q, v = random_states(desc, n, seed=4321, **kw)
@@ -188,11 +204,12 @@ def test_single_step_parity(name, integrator):
     ("double_pendulum", 1e-3, 1000), ("cart_pole", 1e-3, 1000), ("so101", 1.0 / 6000.0, 1000),
     ("so101_contact", 1.0 / 6000.0, 1000), ("navbot_contact", 1.0 / 6000.0, 600), ("hopper", 5e-4, 500),
 ])
-def test_rollout_parity_fused_steps(name, dt, steps):
+@pytest.mark.parametrize("flavour", ["static", "jit"])
+def test_rollout_parity_fused_steps(name, dt, steps, flavour):
     """n_steps fused in one launch == the oracle stepping one by one (short horizon, 1e-8)."""
     factory, kw, _ = WORKLOADS[name]
-    mech = factory()
-    desc = mech.desc()
+    desc = factory().desc()
+    mech = kernel_flavour(factory(), flavour)
     orc = oracle_of(desc)
     n = 128
     q, v = random_states(desc, n, seed=2024, v_range=0.5, **kw)
@@ -342,9 +359,23 @@ def test_status_flags_nan_and_singular():
 def test_random_trees_on_the_runtime_topology_kernel(seed):
     """Random trees (floating joints hanging off bodies, fixed joints mid-chain, springs, one or two
     halfspaces, up to 16 bodies / 24 dof) through the generic kernel: dynamics, forces, one step."""
-    nb = int(np.random.default_rng(1000 + seed).integers(1, 17))
+    _random_tree_case(seed, int(np.random.default_rng(1000 + seed).integers(1, 17)), KernelMode.GENERIC)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_trees_on_run_time_compiled_kernels(seed):
+    """The same kind of random tree (1-8 bodies here: each one costs three NVRTC compilations unless
+    tools/warm_jit_cache.py already put them in the cache) on a kernel compiled for that very tree."""
+    if not jit_available():
+        pytest.skip("NVRTC not loadable: no run-time specialisation on this machine")
+    _random_tree_case(seed, 1 + (3 * seed + 2) % 8, KernelMode.AUTO)
+
+
+def _random_tree_case(seed, nb, kernel):
     desc = models.random_tree(1000 + seed, nb)
-    mech = Mechanism.from_desc(desc)
+    mech = Mechanism.from_desc(desc, kernel=kernel)
+    assert mech.kernel_variant.startswith("generic" if kernel == KernelMode.GENERIC else ("jit:", "pendulum", "floating",
+                                                                                         "double_pendulum", "cart_pole", "hopper"))
     orc = oracle_of(mech.desc())
     if desc.n_v == 0:
         pytest.skip("no degrees of freedom drawn")
@@ -365,8 +396,12 @@ def test_random_trees_on_the_runtime_topology_kernel(seed):
 
 
 def test_two_halfspaces_contact_mode():
-    """cube wedged between ground and a tilted wall: the multi-halfspace step kernels (static + generic)"""
-    for mech in (models.cube_in_corner(), generic_twin(models.cube_in_corner())):
+    """cube wedged between ground and a tilted wall: the multi-halfspace step kernels (static, generic and,
+    where NVRTC is there, run-time-compiled)"""
+    flavours = [models.cube_in_corner(), generic_twin(models.cube_in_corner())]
+    if jit_available():
+        flavours.append(generic_twin(models.cube_in_corner(), KernelMode.JIT))
+    for mech in flavours:
         desc = models.cube_in_corner().desc()
         orc = oracle_of(desc)
         n = 512
@@ -509,7 +544,10 @@ def test_free_velocity_and_armature():
     vdot = st.dynamics(tau=tau)
     vdot_ref, _ = orc.batch_dynamics(q, v, tau)
     assert rel_err(vdot, vdot_ref) < TOL_DYN
-    plain = MechanismState(Mechanism.from_model("so101"), n)
+    bare = mech.desc()
+    for i in range(bare.n_bodies):
+        bare._armature[i] = 0.0
+    plain = MechanismState(Mechanism.from_desc(bare), n)
     plain.update(q, v)
     np.testing.assert_array_equal(plain.dynamics(tau=tau), vdot)
     # quadruped (floating base, generic axes)
@@ -523,8 +561,8 @@ def test_free_velocity_and_armature():
     assert rel_err(vf, ref) < TOL_DYN
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["static", "generic"])
-def test_spring_contact_slip_matches_oracle(generic):
+@pytest.mark.parametrize("flavour", ["static", "generic", "jit"])
+def test_spring_contact_slip_matches_oracle(flavour):
     """SpringContact (reference contact.rs:74-94, :133-186): the stateful SLIP leg. Many hoppers with
     different launch speeds, stepped on the GPU and in the oracle, the apex logic of SLIP_hopping
     (contact.rs:878-889) applied on the host to both; state AND spring-contact state must agree.
@@ -533,8 +571,8 @@ def test_spring_contact_slip_matches_oracle(generic):
     mech.add_halfspace((0, 0, 1), -0.3)
     assert mech.kernel_variant == "floating_F" and mech.n_spring_contacts == 1
     orc = oracle_of(mech)
-    if generic:
-        mech = generic_twin(mech)
+    if flavour != "static":
+        mech = kernel_flavour(mech, flavour)
         assert mech.n_spring_contacts == 1 and mech.n_halfspaces == 1
     a = math.radians(45.0)
     direction = np.array([math.sin(a), 0.0, -math.cos(a)])
@@ -788,14 +826,17 @@ def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
     assert all(same(q_out[c], q1[0]) and same(v_out[c], v1[0]) for c in range(n_copies))
 
 
-def test_maximum_size_mechanism():
+@pytest.mark.parametrize("kernel", [KernelMode.GENERIC, KernelMode.JIT], ids=["generic", "jit"])
+def test_maximum_size_mechanism(kernel):
     """16 bodies / 24 dofs / 32 contact points / 4 halfspaces, all limits of the ABI at once, against the
     oracle and against the independent derivation: dynamics, contact forces, one step of every integrator,
-    a fused rollout, and a ragged batch."""
+    a fused rollout, and a ragged batch. On the run-time-topology kernel and on a kernel compiled for this tree."""
     from tests import featherstone_ref as fs
     desc = models.maximum_size_mechanism()
-    mech = Mechanism.from_desc(desc)
-    assert mech.kernel_variant == "generic"
+    if kernel == KernelMode.JIT and not jit_available():
+        pytest.skip("NVRTC not loadable: no run-time specialisation on this machine")
+    mech = Mechanism.from_desc(desc, kernel=kernel)
+    assert mech.kernel_variant == ("generic" if kernel == KernelMode.GENERIC else "jit:FFRRRPRRRPRRRPXX")
     orc = oracle_of(mech.desc())
     n = 333
     q, v = random_states(desc, n, seed=8, t_jitter=0.2, rpy_jitter=0.6, q_range=0.5)
@@ -846,3 +887,52 @@ def test_sharded_state_from_one_process():
     ke, pe, se = sh.energy_sums()
     k1, p1, s1 = one.energies()
     assert abs(ke - k1.sum()) <= 1e-9 * abs(k1.sum()) and abs(pe - p1.sum()) <= 1e-9 * abs(p1.sum())
+
+
+@pytest.mark.parametrize("name,dt,steps", [("so101_contact", 1.0 / 6000.0, 48), ("navbot_contact", 1.0 / 6000.0, 40),
+                                           ("cart_pole", 1e-3, 64)])
+def test_torque_sequence_is_the_per_step_control_closure(name, dt, steps):
+    """gp_batch_step_tau_sequence: one torque vector per fused step (reference simulate.rs:87-112, control_fn
+    before every step). Against (1) set_tau + step(1) repeated on the GPU, bitwise, (2) the oracle stepped one
+    step at a time with the same torques, and (3) the device-resident [n_steps][n_v][ld] plane form, bitwise."""
+    import torch
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 301  # ragged: ld = 320
+    q, v = random_states(desc, n, seed=77, v_range=0.3, **kw)
+    rng = np.random.default_rng(5)
+    tau_seq = rng.uniform(-0.5, 0.5, size=(steps, n, desc.n_v))
+    # (1) launch per step
+    a = MechanismState(mech, n)
+    a.update(q, v)
+    for s in range(steps):
+        a.step(dt, tau=tau_seq[s], n_steps=1)
+    qa, va = a.state()
+    # the sequence in one call (host rows, streamed)
+    b = MechanismState(mech, n)
+    b.update(q, v)
+    b.set_tau(np.full((n, desc.n_v), 123.0))  # must be ignored by the sequence and left alone
+    b.step_tau_sequence(dt, tau_seq)
+    qb, vb = b.state()
+    assert np.array_equal(qa, qb) and np.array_equal(va, vb)
+    # (2) oracle
+    qo, vo = q.copy(), v.copy()
+    for s in range(steps):
+        qo, vo = orc.batch_rollout(qo, vo, dt, 1, tau=tau_seq[s])
+    assert rel_err(qb, qo) < 1e-9 and rel_err(vb, vo, floor=1e-3) < 1e-7
+    # (3) planes on the device
+    c = MechanismState(mech, n)
+    c.update(q, v)
+    planes = np.zeros((steps, desc.n_v, c.ld))
+    planes[:, :, :n] = tau_seq.transpose(0, 2, 1)
+    dev = torch.from_numpy(planes).cuda()
+    torch.cuda.synchronize()
+    c.step_tau_sequence_device(dt, dev.data_ptr(), steps)
+    qc, vc = c.state()
+    assert np.array_equal(qa, qc) and np.array_equal(va, vc)
+    # the batch's own torques were not touched: one more plain step uses them
+    b.step(dt, n_steps=1)
+    a.step(dt, tau=np.full((n, desc.n_v), 123.0), n_steps=1)
+    assert np.array_equal(a.q, b.q)

@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""Developer tool (GPU box): what the run-time-topology ("generic") kernel costs against the static
-specialisation of the same mechanism.   python tools/bench_generic.py [workload ...]"""
+"""Developer tool (GPU box): the static specialisation of a mechanism against its twin (a massless fixed leaf
+appended, so that no shipped specialisation matches) on the run-time-topology ("generic") kernel and on a kernel
+compiled at run time for the twin's tree (NVRTC, gp_jit.cpp).   python tools/bench_generic.py [workload ...]
+One JSON line per (workload, flavour) -> stdout."""
+import json
 import sys
 import time
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
-import bench  # noqa: E402
-from gorilla_physics_b200 import MechanismState  # noqa: E402
+from gorilla_physics_b200 import WORKLOADS, KernelMode, MechanismState, jit_available  # noqa: E402
 from tests.test_parity_gpu import generic_twin  # noqa: E402
 
 for w in sys.argv[1:] or ["so101_contact", "navbot_contact", "double_pendulum"]:
-    n, dt, rnd = bench.WORKLOADS[w]
-    n = min(n, 65536)
-    for label, mech in (("static", bench.make_mechanism(w)), ("generic", generic_twin(bench.make_mechanism(w)))):
+    wl = WORKLOADS[w]
+    n, dt, rnd = min(wl.n_envs, 65536), wl.dt, wl.randomize
+    flavours = [("static", wl.mechanism()), ("generic", generic_twin(wl.mechanism()))]
+    if jit_available():
+        flavours.append(("jit", generic_twin(wl.mechanism(), KernelMode.JIT)))
+    base = None
+    for label, mech in flavours:
         st = MechanismState(mech, n)
         st.randomize(1, **rnd)
         st.step(dt, n_steps=32)
@@ -24,4 +30,7 @@ for w in sys.argv[1:] or ["so101_contact", "navbot_contact", "double_pendulum"]:
             st.step(dt, n_steps=64)
         st.synchronize()
         el = time.perf_counter() - t0
-        print(f"{w:16s} {label:8s} {mech.kernel_variant:20s} {n * 64 * 5 / el:.3e} env-steps/s")
+        rate = n * 64 * 5 / el
+        base = base or rate
+        print(json.dumps({"workload": w, "n_envs": n, "flavour": label, "kernel": mech.kernel_variant,
+                          "env_steps_per_sec": rate, "static_over_this": base / rate}), flush=True)

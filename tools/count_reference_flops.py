@@ -35,7 +35,7 @@ def main():
     real.gpc_read_counters.argtypes = [C.POINTER(C.c_longlong)]
     binding._lib = binding.configure(_Proxy(real))  # OracleMechanism now drives the counting build
 
-    import bench  # workload table and mechanisms of the benchmark
+    from gorilla_physics_b200 import WORKLOADS  # workload table and mechanisms of the benchmark
     from tests.test_parity_gpu import random_states
 
     executed = json.loads((ROOT / "profiles" / "flop_counts.json").read_text())
@@ -53,8 +53,11 @@ def main():
                    "bytes = (n_q + n_v) * 8 read + written per environment per LAUNCH (state stays in registers across "
                    "the fused steps); per env-step = / 128 fused steps.",
            "workloads": {}}
-    for name, (n_envs, dt, _) in bench.WORKLOADS.items():
-        mech = bench.make_mechanism(name)
+    for name, wl in WORKLOADS.items():
+        if wl.controller.name != "NONE" or wl.settle_steps:
+            continue  # the count is per mechanism: variants of a counted workload add nothing
+        n_envs, dt = wl.n_envs, wl.dt
+        mech = wl.mechanism()
         desc = mech.desc()
         orc = binding.OracleMechanism(desc)
         n, steps = 16, 2000
