@@ -262,6 +262,18 @@ def parity_sample(workload, inner, q0, v0, vdot0, q1, v1):
         out["vdot_rel_err_max"] = float((np.abs(vdot0 - ref) / scale).max())
         comp = np.abs(vdot0 - ref) / np.maximum(np.abs(ref), 1e-3 * scale)
         out["vdot_componentwise_rel_err_max"] = float(comp.max())
+    # one time step (controller included) from the same states, on a small batch of its own: north_star's per-step bar
+    from gorilla_physics_b200 import Integrator, MechanismState
+    one = MechanismState(w.mechanism(), len(q0))
+    one.update(q0, v0)
+    one.step(w.dt, integrator=Integrator.SemiImplicitEuler, n_steps=1, controller=w.controller, ctrl_params=tuple(w.ctrl_params))
+    qg, vg = one.state()
+    q1r, v1r = orc.batch_rollout(q0, v0, w.dt, 1, controller=int(w.controller), params=tuple(w.ctrl_params))
+
+    def rel(a, b):
+        return float((np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-9)).max())
+    out["one_step_rel_err_max"] = {"q": rel(qg, q1r), "v": rel(vg, v1r)}
+    del one
     qr, vr = orc.batch_rollout(q0, v0, w.dt, inner, controller=int(w.controller), params=tuple(w.ctrl_params))
     qp, vp = orc.batch_rollout(q0 * (1.0 + 1e-15), v0 * (1.0 - 1e-15), w.dt, inner, controller=int(w.controller),
                                params=tuple(w.ctrl_params))
@@ -322,8 +334,9 @@ def main():
                     help="environments over ALL GPUs, split evenly: strong scaling (overrides --envs)")
     ap.add_argument("--sustain", type=float, default=2.0,
                     help="repeat the timed block until this many seconds of kernel time (0: only the K steps)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "jit", "generic"],
-                    help="jit: run the mechanism on a kernel compiled at run time for its tree (NVRTC)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "jit", "generic", "jit_twin", "generic_twin"],
+                    help="jit: run the mechanism on a kernel compiled at run time for its tree (NVRTC); *_twin: the "
+                         "same physics with a massless fixed leaf appended, so that no shipped specialisation matches")
     ap.add_argument("--per-step-control", action="store_true",
                     help="also measure the per-step torque paths (launch per step; streamed torque sequence)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -358,7 +371,12 @@ def main():
         scaling = "strong"
     inner = args.inner
     mech = w.mechanism()
-    if args.kernel == "jit":
+    if args.kernel in ("jit_twin", "generic_twin"):
+        from gorilla_physics_b200 import FIXED, Mechanism
+        d = mech.desc()
+        d.add_body(d.n_bodies, FIXED, moment=np.zeros((3, 3)), mass=0.0)
+        mech = Mechanism.from_desc(d, kernel=KernelMode.JIT if args.kernel == "jit_twin" else KernelMode.GENERIC)
+    elif args.kernel == "jit":
         mech.set_kernel_mode(KernelMode.JIT)
     elif args.kernel == "generic":
         mech.set_kernel_mode(KernelMode.GENERIC)

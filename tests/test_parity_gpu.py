@@ -936,3 +936,48 @@ def test_torque_sequence_is_the_per_step_control_closure(name, dt, steps):
     b.step(dt, n_steps=1)
     a.step(dt, tau=np.full((n, desc.n_v), 123.0), n_steps=1)
     assert np.array_equal(a.q, b.q)
+
+
+def test_config1_acrobot_swingup_30s():
+    """BASELINE.json config 1 (reference examples/acrobot.rs:14-65): the acrobot from rest, swingup_acrobot
+    evaluated before every step (in-kernel here), SemiImplicitEuler, dt = 1e-3, 30 s, every state recorded.
+    The reference's check is the energy trace KE + double_pendulum_potential_energy2 (energy.rs:19-26) climbing
+    to m g (l + 2 l). Against the oracle's one-step-at-a-time rollout:
+      * q, v over the first 2 s (2000 steps): 1e-6 absolute (the swing-up is chaotic: bounded horizon);
+      * the energy trace over the whole 30 s: 1e-6 relative to the target energy, or within 100x of the oracle's
+        own sensitivity to a 1e-15 perturbation of the initial state where that is larger;
+      * the outcome of the example: the energy ends nearer to the target than it started, as in the oracle."""
+    m, l = 1.0, 7.0
+    mech = models.acrobot()
+    assert mech.kernel_variant == "double_pendulum_RR"
+    orc = oracle_of(mech)
+    steps = 30000
+    st = MechanismState(mech, 1)
+    q0, v0 = np.zeros((1, 2)), np.zeros((1, 2))
+    n, hq, hv = st.simulate(30.0, 1e-3, q0.copy(), v0.copy(), controller=Controller.ACROBOT_SWINGUP, ctrl_params=(m, l),
+                            history=True)
+    assert n == steps and hq.shape == (steps + 1, 1, 2)
+    hq, hv = hq[:, 0], hv[:, 0]
+    _, _, rq, rv = orc.rollout(q0[0], v0[0], 1e-3, steps, controller=int(Controller.ACROBOT_SWINGUP), params=(m, l), history=True)
+    # (the example starts from q = v = 0, which a relative perturbation leaves alone: perturb the first state
+    # reached, by 1e-15 absolute, the size of one rounding error of the O(1) quantities of a step)
+    _, _, pq, pv = orc.rollout(rq[1] + 1e-15, rv[1] - 1e-15, 1e-3, steps - 1,
+                               controller=int(Controller.ACROBOT_SWINGUP), params=(m, l), history=True)
+    assert np.abs(hq[:2001] - rq[:2001]).max() < 1e-6 and np.abs(hv[:2001] - rv[:2001]).max() < 1e-6
+
+    def energy(qq, vv):
+        ke = np.array([orc.kinetic_energy(a, b) for a, b in zip(qq[::50], vv[::50])])
+        pe = m * 9.81 * (l * np.sin(qq[::50, 0]) + (l * np.sin(qq[::50, 0]) + l * np.sin(qq[::50, 0] + qq[::50, 1])))
+        return ke + pe
+    target = m * 9.81 * 3.0 * l
+    e_gpu, e_ref = energy(hq, hv), energy(rq, rv)
+    e_pert = energy(np.vstack([rq[:1], pq]), np.vstack([rv[:1], pv]))
+    err = np.abs(e_gpu - e_ref) / target
+    sens = np.abs(e_pert - e_ref) / target
+    bound = np.maximum(1e-6, 100.0 * np.maximum.accumulate(sens))
+    print(f"acrobot 30 s: energy error max {err.max():.2e} (first 2 s {err[:41].max():.2e}), oracle sensitivity max {sens.max():.2e}; "
+          f"|q err| at 2 s {np.abs(hq[2000] - rq[2000]).max():.2e}, 10 s {np.abs(hq[10000] - rq[10000]).max():.2e}, "
+          f"30 s {np.abs(hq[-1] - rq[-1]).max():.2e}")
+    assert (err <= bound).all(), (float(err.max()), float(bound.min()))
+    assert err[:41].max() < 1e-6
+    assert abs(e_gpu[0]) < 1e-12 and abs(e_gpu[-1] - target) < abs(e_gpu[0] - target)

@@ -13,12 +13,12 @@ for w in ${W:-so101_contact so101 double_pendulum cart_pole rimless_wheel hopper
   # FP64 work averaged over the launches the bench times (tools/ncu_flops_over_bench.py)
   ncu --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum \
       --clock-control none -k regex:step_kernel --csv --log-file gpurun_out/${R}_${w}_flops.csv \
-      python bench.py --workload $w --steps 40 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+      python bench.py --workload $w --steps 40 --warmup 3 --no-cpu-baseline --sustain 0 > /dev/null 2>&1
   python tools/ncu_flops_over_bench.py gpurun_out/${R}_${w}_flops.csv ${N[$w]} 128 > gpurun_out/profile_${R}_${w}_flops_over_bench.json
   rm -f gpurun_out/${R}_${w}_flops.csv
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/profile_${R}_launches.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/profile_${R}_launches.log 2>&1
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --sustain 0 > gpurun_out/profile_${R}_launches.log 2>&1
 python - <<PY
 import json, glob
 out = {"_how": "ncu --set full + smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum on one step-kernel launch of \`python bench.py --workload W --inner 64 --steps 3 --warmup 3\` (tools/refresh_profiles.sh on the GPU box, B200); flop = 2*dfma + dadd + dmul; per env-step = / (n_envs * 64) -> flop_per_env_step_one_launch. flop_per_env_step (what bench.py uses) = the same three counters summed over the 40 timed launches of \`python bench.py --workload W\` (defaults: 40 x 128 steps after 3 warm-up launches) / (n_envs * 128 * 40), i.e. averaged over the trajectory the bench times (tools/ncu_flops_over_bench.py). Per-workload summaries: profiles/${R}_<workload>_step_kernel.json (tools/ncu_summary.py)",
