@@ -554,12 +554,18 @@ def main():
         del tau_seq, dev
 
     # ---- optional end-of-rollout diagnostic reduction (the only collective; outside the timed region)
-    sums = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")
-    st.energy_sums_device(sums.data_ptr())
-    st.synchronize()
+    #      inside the library: gp_batch_reduce_diagnostics = four sums on the device + ncclAllReduce on the batch's
+    #      stream; torch.distributed only carries the communicator's 128-byte id to the other ranks
+    comm = None
     if world > 1:
-        dist.all_reduce(sums)
-    flagged = int(sums[3].item())
+        from gorilla_physics_b200 import Communicator
+        ident = [Communicator.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        comm = Communicator(rank, world, ident[0], local_rank)
+    sums = st.reduce_diagnostics(comm)
+    if comm is not None:
+        comm.close()
+    flagged = int(sums[3])
 
     # ---- roofline of the step kernel
     peak = fp64_peak_report(local_rank) if rank == 0 else {}
@@ -603,7 +609,8 @@ def main():
                 "parallelism": f"env-sharded x{world}, no collective on the step path",
                 "l2": "192 MB flush written before every timed launch (outside the event pair)",
                 "contact_active": {"start": contact_start, "end": contact_end},
-                "flagged_envs": flagged}),
+                "flagged_envs": flagged,
+                "diagnostic_sums_all_ranks": {"kinetic": float(sums[0]), "potential": float(sums[1]), "spring": float(sums[2])}}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "steps": e2e_steps, "api": "gp_batch_simulate (pinned host q,v in/out)"},

@@ -117,6 +117,25 @@ SYMBOLS = {
     "gp_batch_poses": (C.c_int, [vp, vp]),
     "gp_batch_status": (C.c_int, [vp, vp]),
     "gp_batch_clear_status": (C.c_int, [vp]),
+    "gp_sharded_create": (C.c_int, [vp, C.c_int64, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+    "gp_sharded_destroy": (None, [vp]),
+    "gp_sharded_n_shards": (C.c_int, [vp]),
+    "gp_sharded_n_envs": (C.c_int64, [vp]),
+    "gp_sharded_shard": (vp, [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gp_sharded_set_state": (C.c_int, [vp, vp, vp]),
+    "gp_sharded_get_state": (C.c_int, [vp, vp, vp]),
+    "gp_sharded_set_tau": (C.c_int, [vp, vp]),
+    "gp_sharded_step": (C.c_int, [vp, C.c_double, C.c_int, C.c_int, C.c_int, dp, C.c_int]),
+    "gp_sharded_sync": (C.c_int, [vp]),
+    "gp_sharded_simulate": (C.c_int, [vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, dp, C.c_int,
+                                      C.POINTER(C.c_int64)]),
+    "gp_sharded_status": (C.c_int, [vp, vp]),
+    "gp_sharded_energy_sums": (C.c_int, [vp, dp]),
+    "gp_nccl_available": (C.c_int, []),
+    "gp_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "gp_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(vp)]),
+    "gp_comm_destroy": (None, [vp]),
+    "gp_batch_reduce_diagnostics": (C.c_int, [vp, vp, dp]),
     "gp_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, dp]),
     "gp_measure_fp64_peak_trace": (C.c_int, [C.c_int, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int)]),
 }

@@ -247,12 +247,27 @@ class MechanismState:
         check(lib().gp_batch_create(mechanism._h, self.n_envs, device, C.byref(h)))
         self._h = h
         self.device = device
+        self._owned = True
+
+    @classmethod
+    def _borrowed(cls, mechanism: Mechanism, handle, owner) -> "MechanismState":
+        """view of a gp_batch that something else owns (a shard of a gp_sharded): never destroyed from here;
+        `owner` is kept alive as long as the view is"""
+        st = cls.__new__(cls)
+        st.mechanism = mechanism
+        st._h = C.c_void_p(handle)
+        st.n_envs = int(lib().gp_batch_n_envs(st._h))
+        st.n_q, st.n_v = mechanism.n_q, mechanism.n_v
+        st.device = int(lib().gp_batch_device(st._h))
+        st._owned = False
+        st._owner = owner
+        return st
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and getattr(self, "_owned", False):
                 lib().gp_batch_destroy(self._h)
-                self._h = None
+            self._h = None
         except Exception:
             pass
 
@@ -455,6 +470,14 @@ class MechanismState:
     def spring_energy(self):
         return self.energies()[2]
 
+    def reduce_diagnostics(self, comm: "Optional[Communicator]" = None) -> np.ndarray:
+        """[sum KE, sum PE, sum spring energy, flagged environments] of this batch, all-reduced over the ranks of
+        `comm` inside the library (NCCL on the batch's stream, gp_batch_reduce_diagnostics); without a
+        communicator: this batch's own sums. The path's only exchange, end of rollout."""
+        out = np.zeros(4)
+        check(lib().gp_batch_reduce_diagnostics(self._h, comm._h if comm is not None else None, out.ctypes.data_as(dp)))
+        return out
+
     def energy_sums_device(self, out_dev_ptr: int):
         check(lib().gp_batch_energy_sums_device(self._h, C.c_void_p(int(out_dev_ptr))))
 
@@ -520,3 +543,37 @@ def measure_fp64_peak_trace(device: int = 0, seconds: float = 1.0, max_samples: 
     check(lib().gp_measure_fp64_peak_trace(device, seconds, t.ctypes.data_as(dp), f.ctypes.data_as(dp), max_samples,
                                            C.byref(n)))
     return t[:n.value], f[:n.value]
+
+
+def nccl_available() -> bool:
+    return bool(lib().gp_nccl_available())
+
+
+class Communicator:
+    """NCCL communicator owned by the library (gp_comm_*), one rank per GPU. Rank 0 calls
+    Communicator.unique_id() and hands the 128 bytes to the other ranks by its own means."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().gp_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, rank: int, world: int, unique_id: bytes, device: int):
+        if len(unique_id) != 128:
+            raise ValueError("the unique id is 128 bytes")
+        h = C.c_void_p()
+        check(lib().gp_comm_create(int(rank), int(world), C.create_string_buffer(unique_id, 128), int(device), C.byref(h)))
+        self._h = h
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gp_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

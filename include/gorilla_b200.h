@@ -356,6 +356,51 @@ int gp_batch_poses(gp_batch* batch, double* poses_host);
 int gp_batch_status(gp_batch* batch, uint32_t* status_host);
 int gp_batch_clear_status(gp_batch* batch);
 
+/* ---- several GPUs from one process ---------------------------------------------------
+ * The reference is one process; on a multi-GPU box its MechanismState batch is spread over the devices as
+ * contiguous environment ranges (shard g owns [g*N/G, (g+1)*N/G)), each with its own resident planes and
+ * stream. Nothing is exchanged on the step path (environments are independent).
+ * gp_sharded_step only enqueues, so the devices run concurrently; calls that move host data
+ * (set/get_state, set_tau, simulate, status) run one worker thread per device. Host buffers are the same
+ * env-major arrays as for gp_batch_*, over ALL n_envs environments. Every shard stays reachable as a plain
+ * batch handle - borrowed, do not destroy it - for everything else the single-device ABI offers. */
+typedef struct gp_sharded gp_sharded; /* opaque */
+int gp_sharded_create(const gp_mechanism* mech, int64_t n_envs, const int* device_ids, int n_devices,
+                      gp_sharded** out);
+void gp_sharded_destroy(gp_sharded* sb);
+int gp_sharded_n_shards(const gp_sharded* sb);
+int64_t gp_sharded_n_envs(const gp_sharded* sb);
+gp_batch* gp_sharded_shard(gp_sharded* sb, int shard, int64_t* env_lo, int64_t* env_hi);
+int gp_sharded_set_state(gp_sharded* sb, const double* q_host, const double* v_host);
+int gp_sharded_get_state(gp_sharded* sb, double* q_host, double* v_host);
+int gp_sharded_set_tau(gp_sharded* sb, const double* tau_host);
+int gp_sharded_step(gp_sharded* sb, double dt, int integrator, int n_steps, int controller,
+                    const double* ctrl_params, int n_ctrl_params);
+int gp_sharded_sync(gp_sharded* sb);
+int gp_sharded_simulate(gp_sharded* sb, double* q_host, double* v_host, const double* tau_host,
+                        double final_time, double dt, int integrator, int controller,
+                        const double* ctrl_params, int n_ctrl_params, int64_t* n_steps_out);
+int gp_sharded_status(gp_sharded* sb, uint32_t* status_host);
+/* out[0..3] = sum KE, sum PE, sum spring energy, flagged environments over every shard (summed on the host
+ * in shard order: the in-process form of the end-of-rollout reduction) */
+int gp_sharded_energy_sums(gp_sharded* sb, double out[4]);
+
+/* ---- end-of-rollout diagnostic reduction across processes (one rank per GPU) -------------
+ * The only exchange the path has (BASELINE.json north_star: "NCCL is used only for an optional end-of-rollout
+ * energy/diagnostic reduction"). NCCL is loaded with dlopen ($GP_NCCL_LIB, libnccl.so.2); the library does not
+ * link it. Rank 0 makes an id with gp_comm_unique_id and hands it to the other ranks by whatever means the
+ * host has (file, socket, MPI, torch.distributed); every rank then calls gp_comm_create (collective).
+ * gp_batch_reduce_diagnostics writes this batch's four sums on the device (gp_batch_energy_sums_device),
+ * all-reduces them in place on the batch's stream (ncclAllReduce, sum) and copies the result to out_host;
+ * comm == NULL (or a world of one) skips the all-reduce: this batch's own sums. */
+#define GP_COMM_ID_BYTES 128
+typedef struct gp_comm gp_comm; /* opaque */
+int gp_nccl_available(void);
+int gp_comm_unique_id(char id_out[GP_COMM_ID_BYTES]);
+int gp_comm_create(int rank, int world, const char id[GP_COMM_ID_BYTES], int device, gp_comm** out);
+void gp_comm_destroy(gp_comm* comm);
+int gp_batch_reduce_diagnostics(gp_batch* batch, gp_comm* comm, double out_host[4]);
+
 /* ---- measurement helpers --------------------------------------------------------
  * FP64 FMA-chain microbenchmark on `device`: runs for about `seconds`, returns the
  * sustained DFMA rate in TFLOP/s (2 flop per FMA) — the measured FP64 roofline

@@ -887,6 +887,83 @@ def test_sharded_state_from_one_process():
     ke, pe, se = sh.energy_sums()
     k1, p1, s1 = one.energies()
     assert abs(ke - k1.sum()) <= 1e-9 * abs(k1.sum()) and abs(pe - p1.sum()) <= 1e-9 * abs(p1.sum())
+    # the single-batch form of the diagnostic (no communicator: this batch's own sums)
+    d = one.reduce_diagnostics()
+    assert abs(d[0] - k1.sum()) <= 1e-9 * abs(k1.sum()) and abs(d[1] - p1.sum()) <= 1e-9 * abs(p1.sum()) and d[3] == 0
+    # per-environment torques reach the right shard and row
+    tau = np.random.default_rng(3).uniform(-0.3, 0.3, size=(n, desc.n_v))
+    one.update(q, v)
+    one.step(1.0 / 6000.0, tau=tau, n_steps=25)
+    sh.update(q, v)
+    sh.step(1.0 / 6000.0, tau=tau, n_steps=25)
+    assert np.array_equal(one.state()[0], sh.state()[0]) and np.array_equal(one.state()[1], sh.state()[1])
+    qs, vs = q.copy(), v.copy()
+    sh.simulate(24.5 / 6000.0, 1.0 / 6000.0, qs, vs, tau=tau)
+    assert np.array_equal(qs, one.state()[0]) and np.array_equal(vs, one.state()[1])
+    # the shards remain plain batches
+    assert sum(s.n_envs for s in sh.shards) == n and sh.shards[1].state()[0].shape == (333, desc.n_q)
+
+
+_NCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from gorilla_physics_b200 import Communicator, MechanismState, shard_range
+from gorilla_physics_b200.workloads import so101_with_contact
+from tests.test_parity_gpu import random_states
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte id
+ident = [Communicator.unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ident, src=0)
+comm = Communicator(rank, world, ident[0], rank)
+mech = so101_with_contact(); desc = mech.desc()
+n = 4001
+q, v = random_states(desc, n, seed=9)
+lo, hi = shard_range(n, rank, world)
+st = MechanismState(mech, hi - lo, device=rank)
+st.update(q[lo:hi], v[lo:hi])
+st.step(1.0 / 6000.0, n_steps=64)        # no communication on the step path
+total = st.reduce_diagnostics(comm)      # the only exchange: NCCL all-reduce of 4 doubles inside the library
+mine = st.reduce_diagnostics()
+parts = [None] * world
+dist.all_gather_object(parts, mine.tolist())
+want = np.sum(np.asarray(parts), axis=0)
+assert np.allclose(total, want, rtol=1e-12, atol=0), (total, want)
+if rank == 0:
+    one = MechanismState(mech, n, device=0)
+    one.update(q, v); one.step(1.0 / 6000.0, n_steps=64)
+    ke, pe, se = one.energies()
+    assert abs(total[0] - ke.sum()) <= 1e-9 * abs(ke.sum()) and abs(total[1] - pe.sum()) <= 1e-9 * abs(pe.sum())
+    print("nccl-ok", total.tolist())
+comm.close()
+dist.destroy_process_group()
+"""
+
+
+def test_diagnostic_reduction_over_nccl_two_ranks(tmp_path):
+    """One rank per GPU: states sharded, no exchange on the step path, and the end-of-rollout diagnostic
+    all-reduced by the library itself (gp_comm_* + gp_batch_reduce_diagnostics, NCCL through dlopen).
+    Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    from gorilla_physics_b200 import nccl_available
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if not nccl_available():
+        pytest.skip("NCCL not loadable")
+    root = str(Path(__file__).resolve().parent.parent)
+    script = tmp_path / "worker.py"
+    script.write_text(_NCCL_WORKER.format(root=root))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "nccl-ok" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
 
 
 @pytest.mark.parametrize("name,dt,steps", [("so101_contact", 1.0 / 6000.0, 48), ("navbot_contact", 1.0 / 6000.0, 40),
