@@ -351,3 +351,15 @@ def test_reference_arm_runs_without_the_product_library():
     for key in ("workload", "n_envs_per_gpu", "inner_steps_per_launch", "dt", "integrator", "controller"):
         assert key in line["config"]
     assert line["config"]["n_envs_per_gpu"] == 64 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_integration_md_binds_every_declared_symbol():
+    """INTEGRATION.md's Rust `extern "C"` block is tools/gen_rust_ffi.py's output for the current header: no
+    exported function is missing from the binding a maintainer would add, and no `unimplemented!()` is left."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import gen_rust_ffi
+    text = (ROOT / "INTEGRATION.md").read_text()
+    assert gen_rust_ffi.rust_block() in text
+    assert "unimplemented!" not in text
+    names = set(re.findall(r"pub fn (gp_[a-z0-9_]+)\(", text))
+    assert names == set(_abi.SYMBOLS)
