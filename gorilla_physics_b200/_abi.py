@@ -94,6 +94,7 @@ SYMBOLS = {
     "gp_batch_tau_device": (vp, [vp]),
     "gp_batch_stream": (vp, [vp]),
     "gp_batch_sync": (C.c_int, [vp]),
+    "gp_batch_step_lanes": (C.c_int, [vp]),
     "gp_batch_launch_count": (C.c_int64, [vp]),
     "gp_batch_set_state": (C.c_int, [vp, vp, vp]),
     "gp_batch_get_state": (C.c_int, [vp, vp, vp]),

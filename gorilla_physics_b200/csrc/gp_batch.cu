@@ -585,6 +585,12 @@ double* gp_batch_tau_device(gp_batch* b) {
   return b->tau;
 }
 void* gp_batch_stream(gp_batch* b) { return b ? (void*)b->stream : nullptr; }
+int gp_batch_step_lanes(const gp_batch* b) {
+  if (!b || !b->mech || !b->mech->table) return 0;
+  const KernelTable* t = b->mech->table;
+  return (t->lanes_sie == 2 && use_pairs(b->n, t->block_size)) ? 2 : 1;
+}
+
 int64_t gp_batch_launch_count(const gp_batch* b) { return b ? b->launches : 0; }
 
 int gp_batch_sync(gp_batch* b) {

@@ -38,7 +38,33 @@ struct DynOut {
   // add the joints' armature to the diagonal of H: Articulated::free_velocity only (the reference's
   // MechanismState engine - mass_matrix, dynamics_continuous, step - never reads it; hybrid/articulated/mod.rs:247)
   bool armature = false;
+  // warp-pair mapping (StaticTopo<Spec, SIDE>, gp_topology.cuh): this pair's exchange buffer in shared memory,
+  // [2 halves][kXchSlots][32 lanes], and the id of the pair's 64-thread named barrier
+  double* xch = nullptr;
+  int bar_id = 0;
 };
+
+// doubles one half hands to the other per time step: root composite inertia (10) + root force (6), then the
+// root block of H (<= 21) + the root's part of the right-hand side (<= 6)
+constexpr int kXchSlotsA = 16, kXchSlotsB = 27, kXchSlots = kXchSlotsA + kXchSlotsB;
+
+// vals += the other half's vals, elementwise (IEEE addition commutes, so both halves end up with the same bits).
+// Each slot range is written once per time step; the other range's barrier sits between two uses of a range.
+template <int SIDE, int N>
+GP_D void pair_exchange_sum(const DynOut& out, int slot0, double (&vals)[N]) {
+#if defined(__CUDA_ARCH__)
+  const int lane = (int)(threadIdx.x & 31u);
+  double* mine = out.xch + ((SIDE * kXchSlots + slot0) * 32 + lane);
+  const double* theirs = out.xch + (((SIDE ^ 1) * kXchSlots + slot0) * 32 + lane);
+#pragma unroll
+  for (int k = 0; k < N; ++k) mine[k * 32] = vals[k];
+  asm volatile("bar.sync %0, 64;" ::"r"(out.bar_id) : "memory");
+#pragma unroll
+  for (int k = 0; k < N; ++k) vals[k] += theirs[k * 32];
+#else
+  (void)out; (void)slot0; (void)vals;
+#endif
+}
 
 // Topologies whose bodies carry several contact points (Topo::kContactList) test all the points of a
 // body first (three FMAs and a compare per point, warp-uniform) and then run the force law over a
@@ -374,6 +400,9 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     // kinematics of this body and its force, and the (independent) force of this body and kinematics
     // of the next share one basic block for the instruction scheduler.
     V3 ka = v3z(), kl = v3z();  // minus the contact wrench on this body
+    // (warp pairs: both halves carry the root's kinematics and contact planes for their children; its own
+    // contact and force are half 0's business)
+    constexpr bool kOwnForce = Topo::owns_body(ic_of<decltype(ii)>::value);
     if constexpr (CONTACT != 0) {
       M3 Rwi;
       if constexpr (WORLD) {  // body -> world rotation (reference mechanism.rs:153-170), parity output only
@@ -393,7 +422,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
         }
       }
       // point-vs-halfspace contact (reference contact.rs:103-128)
-      const int c0 = P.cp_begin[i], c1 = P.cp_begin[i + 1];
+      const int c0 = P.cp_begin[i], c1 = kOwnForce ? P.cp_begin[i + 1] : P.cp_begin[i];
       // one contact point against every halfspace: adds minus its wrench to (ka, kl)
       auto point_contact = [&](int c, V3 loc, double kc) {
         V3 fb = v3z();
@@ -485,7 +514,9 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     const V3 ci = ld3(P.mc[i]);
     const double mi = P.mass[i];
     SV f;
-    if (!moving_parent && jt == JRevolute) {
+    if constexpr (!kOwnForce) {
+      f = svz();
+    } else if (!moving_parent && jt == JRevolute) {
       // w = axis qd, no linear velocity, no angular acceleration: the velocity-product terms are
       // qd^2 times constants folded on the host (gp_params.h ne_a, ne_l)
       const double qd2 = v[vo] * v[vo];
@@ -578,7 +609,10 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
   // start from the body's own inertia plus the constant part of what its children add (gp_params.h)
   for_bodies<Topo>(P, [&](auto ii) {
     const int i = ii;
-    if (Topo::has_children(P, i)) Iacc[i] = RBI{lds3(P.Jacc0[i]), ld3(P.cacc0[i]), P.msub[i]};
+    if (Topo::has_children(P, i)) {
+      if constexpr (Topo::owns_body(ic_of<decltype(ii)>::value)) Iacc[i] = RBI{lds3(P.Jacc0[i]), ld3(P.cacc0[i]), P.msub[i]};
+      else Iacc[i] = RBI{S3{0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, v3z(), 0.0};  // (half 1's root: only what its own children add)
+    }
   });
 
   // Sparse L^T D L factorisation of H (Cholesky family, unit lower-triangular L, no pivoting; entries
@@ -638,6 +672,18 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     const int jt = Topo::jtype(P, i);
     const int vo = Topo::voff(P, i);
 
+    if constexpr (Topo::kSided) {
+      if constexpr (ic_of<decltype(ii)>::value == 0) {
+        // the root: what the two halves' children have added to its composite inertia and force meets here
+        RBI& I0 = Iacc[0];
+        SV& f0 = frc[0];
+        double x[kXchSlotsA] = {I0.J.xx, I0.J.xy, I0.J.xz, I0.J.yy, I0.J.yz, I0.J.zz, I0.c.x, I0.c.y, I0.c.z, I0.m,
+                                f0.a.x, f0.a.y, f0.a.z, f0.l.x, f0.l.y, f0.l.z};
+        pair_exchange_sum<Topo::kSide>(out, 0, x);
+        I0 = RBI{S3{x[0], x[1], x[2], x[3], x[4], x[5]}, V3{x[6], x[7], x[8]}, x[9]};
+        f0 = SV{V3{x[10], x[11], x[12]}, V3{x[13], x[14], x[15]}};
+      }
+    }
     // composite rigid-body inertia of the subtree rooted at i (reference mechanism.rs:606-625)
     RBI Ic;
     if (Topo::has_children(P, i)) Ic = Iacc[i];
@@ -760,6 +806,71 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
 
   if constexpr (kColumnsInPass2) {
     if constexpr (DUMP) for_dofs_reverse<Topo>(P, finish_column);
+  } else if constexpr (Topo::kSided) {
+    // Warp pairs: the same right-looking factorisation, each half eliminating the dofs of its own bodies. Their
+    // updates of the root block of H and of the root's right-hand side are sums over eliminated dofs, so half 0
+    // accumulates them on top of the block itself, half 1 on top of zeros, and the two meet before the root's own
+    // dofs are eliminated (by both halves alike). Everything below the root is local to a half.
+    constexpr int RNV = Topo::kRootNV;
+    for_bodies<Topo>(P, [&](auto ii) {
+      const int i = ii;
+      const int jt = Topo::jtype(P, i);
+      const int vo = Topo::voff(P, i);
+      constexpr bool own = Topo::owns_body(ic_of<decltype(ii)>::value);
+      if (jt == JRevolute) b[vo] = own ? tau[vo] - b[vo] : 0.0;
+      else if (jt == JPrismatic) {
+        double t = tau[vo];
+        if (P.has_spring[i]) t += -P.spring_k[i] * (q[Topo::qoff(P, i)] - P.spring_l[i]);
+        b[vo] = own ? t - b[vo] : 0.0;
+      } else if (jt == JFloating) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) b[vo + k] = own ? tau[vo + k] - b[vo + k] : 0.0;
+      }
+    });
+    if constexpr (Topo::kSide == 1) {
+#pragma unroll
+      for (int e = 0; e < RNV * (RNV + 1) / 2; ++e) H[e] = 0.0;  // (the root block is the head of the packed triangle)
+    }
+    auto eliminate = [&](auto kk) {
+      const int k = kk;
+      const double d = H[hidx(k, k)];
+      if (!(d > 0.0)) status |= kEnvNotSPD;
+      const double invd = gp_rcp(d);
+#pragma unroll U
+      for (int i2 = 0; i2 < Topo::lim(k, NV); ++i2) {
+        const int i = k - 1 - i2;
+        if (i >= 0 && Topo::dof_anc(P, i, k)) {
+          const double a = H[hidx(k, i)] * invd;
+#pragma unroll U
+          for (int j = 0; j < Topo::lim(i + 1, NV); ++j)
+            if (j <= i && Topo::dof_anc(P, j, k)) H[hidx(i, j)] -= a * H[hidx(k, j)];
+          H[hidx(k, i)] = a;
+        }
+      }
+      H[hidx(k, k)] = invd;
+      // x = L^-T rhs, the part of dof k
+#pragma unroll U
+      for (int j = 0; j < Topo::lim(k, NV); ++j)
+        if (j < k && Topo::dof_anc(P, j, k)) b[j] -= H[hidx(k, j)] * b[k];
+    };
+    for_dofs_reverse<Topo>(P, [&](auto kk) {
+      if constexpr (ic_of<decltype(kk)>::value >= RNV) eliminate(kk);
+    });
+    if constexpr (RNV > 0) {
+      double x[RNV * (RNV + 1) / 2 + RNV];
+#pragma unroll
+      for (int e = 0; e < RNV * (RNV + 1) / 2; ++e) x[e] = H[e];
+#pragma unroll
+      for (int e = 0; e < RNV; ++e) x[RNV * (RNV + 1) / 2 + e] = b[e];
+      pair_exchange_sum<Topo::kSide>(out, kXchSlotsA, x);
+#pragma unroll
+      for (int e = 0; e < RNV * (RNV + 1) / 2; ++e) H[e] = x[e];
+#pragma unroll
+      for (int e = 0; e < RNV; ++e) b[e] = x[RNV * (RNV + 1) / 2 + e];
+    }
+    for_dofs_reverse<Topo>(P, [&](auto kk) {
+      if constexpr (ic_of<decltype(kk)>::value < RNV) eliminate(kk);
+    });
   } else {
     // the same factorisation, right-looking and after the pass: eliminate the deepest dof first and
     // update the entries of its ancestors in place; then x = L^-T rhs

@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -64,12 +65,19 @@ const Nvrtc& nvrtc() {
     Nvrtc n;
     std::vector<std::string> candidates;
     if (const char* e = std::getenv("GP_NVRTC_LIB")) candidates.push_back(e);
-    candidates.push_back("libnvrtc.so.12");
-    candidates.push_back("libnvrtc.so");
+    // The toolkit's own copy first, by full path: a bare soname resolves to whatever copy the process already holds
+    // (a Python process that imported torch holds torch's bundled NVRTC, an older release), and the compiler
+    // version is part of the cache key - kernels compiled ahead of time (gp_mechanism_precompile) would never be
+    // found again.
     for (const char* var : {"CUDA_HOME", "CUDA_PATH"})
-      if (const char* e = std::getenv(var)) candidates.push_back(std::string(e) + "/lib64/libnvrtc.so");
+      if (const char* e = std::getenv(var)) {
+        candidates.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+        candidates.push_back(std::string(e) + "/lib64/libnvrtc.so");
+      }
     candidates.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
     candidates.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+    candidates.push_back("libnvrtc.so.12");
+    candidates.push_back("libnvrtc.so");
     for (const std::string& c : candidates) {
       n.handle = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
       if (n.handle) {
@@ -211,18 +219,22 @@ struct Slot {
   cudaLibrary_t library = nullptr;
   bool failed = false;
   std::string error;
+  std::atomic<bool> smem_set[64] = {};  // per device: dynamic shared memory limit raised (warp-pair kernels)
 };
 
 struct JitTable : KernelTable {
   std::string defines;  // the SpecCustom macros: first lines of every translation unit of this table
   std::string label;    // storage behind KernelTable::name
   std::mutex mu;
-  Slot step_slot[3][2], dynamics_slot, energy_slot;
+  Slot step_slot[3][2][3], dynamics_slot, energy_slot;  // [contact][integrator class][plain / warp pairs / torque sequence]
 };
 
-std::string step_expr(int contact, int integ) {
-  char buf[128];
-  snprintf(buf, sizeof(buf), "&gp::step_kernel<gp::StaticTopo<gp::SpecCustom>, %d, %d>", contact, integ);
+// flavour of a semi-implicit-Euler step kernel: 0 plain, 1 warp pairs, 2 reads a torque sequence (the Runge-Kutta
+// kernels have one flavour, which reads it)
+std::string step_expr(int contact, int integ, int flavour) {
+  char buf[160];
+  snprintf(buf, sizeof(buf), "&gp::step_kernel<gp::StaticTopo<gp::SpecCustom>, %d, %d, %s, %s>", contact, integ,
+           flavour == 1 ? "true" : "false", (integ != 0 || flavour == 2) ? "true" : "false");
   return buf;
 }
 const char* const kDynamicsExpr = "&gp::dynamics_kernel<gp::StaticTopo<gp::SpecCustom>, 2>";
@@ -377,11 +389,25 @@ cudaError_t jit_step(const KernelTable* self, int contact, int integ_class, cuda
   JitTable* t = const_cast<JitTable*>(static_cast<const JitTable*>(self));
   const int c = contact < 0 ? 0 : (contact > 2 ? 2 : contact), ic = integ_class == IntegSIE ? 0 : 1;
   cudaKernel_t k = nullptr;
-  if (get_kernel(t, t->step_slot[c][ic], step_expr(c, ic), &k) != GP_OK) return kJitFailed;
+  const bool tauseq = ic == 0 && A0.tau_seq != nullptr;
+  const bool pairs = ic == 0 && !tauseq && t->lanes_sie == 2 && use_pairs(A0.n, t->block_size);
+  const int flavour = ic != 0 ? 0 : (tauseq ? 2 : (pairs ? 1 : 0));
+  if (get_kernel(t, t->step_slot[c][ic][flavour], step_expr(c, ic, flavour), &k) != GP_OK) return kJitFailed;
   StepArgs A = A0;
-  const StepLaunchPlan plan = plan_step_launch((const void*)k, t->block_size, t->tickets, s, A);
+  const int lanes = pairs ? 2 : 1;
+  if (lanes == 2) {
+    // exchange buffers of the warp pairs: more than the 48 KB a kernel gets without asking (per kernel and device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Slot& slot = t->step_slot[c][ic][1];
+    if (dev >= 0 && dev < 64 && !slot.smem_set[dev].load(std::memory_order_acquire)) {
+      cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dynamic_smem(t->block_size, 2));
+      slot.smem_set[dev].store(true, std::memory_order_release);
+    }
+  }
+  const StepLaunchPlan plan = plan_step_launch((const void*)k, t->block_size, t->tickets, s, A, lanes);
   void* args[] = {(void*)&P, (void*)&A};
-  return cudaLaunchKernel((const void*)k, dim3(plan.grid), dim3((unsigned)plan.block), args, 0, s);
+  return cudaLaunchKernel((const void*)k, dim3(plan.grid), dim3((unsigned)plan.block), args, plan.smem, s);
 }
 
 cudaError_t jit_dynamics(const KernelTable* self, int /*contact*/, cudaStream_t s, const MechParams& P, const DynArgs& A) {
@@ -417,10 +443,10 @@ std::string defines_of(const TopoData& td, const JitPolicy& pol) {
            "#define GP_CUSTOM_TOPO_NB %d\n#define GP_CUSTOM_TOPO_PARENTS %s\n#define GP_CUSTOM_TOPO_JOINTS %s\n"
            "#define GP_CUSTOM_TOPO_AXES %s\n#define GP_CUSTOM_TOPO_NAME \"jit\"\n#define GP_CUSTOM_BLOCK %d\n"
            "#define GP_CUSTOM_MIN_BLOCKS %d\n#define GP_CUSTOM_SINCOS %s\n#define GP_CUSTOM_SPRINGS %s\n"
-           "#define GP_CUSTOM_TICKETS %s\n#define GP_CUSTOM_CONTACT_LIST_MASK 0x%xu\n",
+           "#define GP_CUSTOM_TICKETS %s\n#define GP_CUSTOM_CONTACT_LIST_MASK 0x%xu\n#define GP_CUSTOM_SIDE_MASK 0x%xu\n",
            td.nb, parents.c_str(), joints.c_str(), axes.c_str(), pol.block_size, pol.min_blocks,
            pol.batched_sincos ? "true" : "false", pol.springs ? "true" : "false", pol.tickets ? "true" : "false",
-           pol.contact_list_mask);
+           pol.contact_list_mask, pol.side_mask);
   return buf;
 }
 
@@ -459,6 +485,40 @@ JitPolicy jit_policy_for(const gp_mechanism* m, const TopoData& td) {
   for (int i = 0; i < td.nb; ++i)
     if (td.jtype[i] == JRevolute && td.axis[i] == AxAny) general_revolute++;
   p.batched_sincos = general_revolute < 8;
+  // Warp pairs (gp_topology.cuh): big trees whose root (body 0, the only child of the world) carries at least two
+  // child subtrees are cut at the root into two halves of about equal size, one warp each: half the live state
+  // per thread where a thread per environment spills (the 9-body trees). Whole subtrees go to a half, largest
+  // first onto the lighter half.
+  static const bool no_sides = std::getenv("GP_JIT_NO_SIDES") != nullptr;  // tuning only
+  int nv_total = 0, roots = 0;
+  for (int i = 0; i < td.nb; ++i) {
+    nv_total += joint_nv(td.jtype[i]);
+    if (td.parent[i] < 0) roots++;
+  }
+  if (!no_sides && !p.springs && roots == 1 && td.parent[0] < 0 && td.nb >= 7 && nv_total >= 12) {
+    std::vector<int> top(td.nb, -1), weight(td.nb, 0);  // child subtree of the root a body belongs to, dofs per subtree
+    for (int i = 1; i < td.nb; ++i) {
+      top[i] = td.parent[i] == 0 ? i : top[td.parent[i]];
+      weight[top[i]] += 1 + joint_nv(td.jtype[i]);
+    }
+    std::vector<int> subtrees;
+    for (int i = 1; i < td.nb; ++i)
+      if (top[i] == i) subtrees.push_back(i);
+    if (subtrees.size() >= 2) {
+      std::sort(subtrees.begin(), subtrees.end(), [&](int a, int b) { return weight[a] != weight[b] ? weight[a] > weight[b] : a < b; });
+      int load[2] = {0, 0};
+      unsigned mask = 0u;
+      for (int sroot : subtrees) {
+        const int half = load[1] < load[0] ? 1 : 0;
+        load[half] += weight[sroot];
+        if (half == 1)
+          for (int i = 1; i < td.nb; ++i)
+            if (top[i] == sroot) mask |= 1u << i;
+      }
+      // worth it only when the halves are balanced: the heavier one sets the pace
+      if (mask != 0u && 3 * std::min(load[0], load[1]) >= 2 * std::max(load[0], load[1])) p.side_mask = mask;
+    }
+  }
   return p;
 }
 
@@ -480,6 +540,7 @@ const KernelTable* jit_table(const TopoData& td, const JitPolicy& pol) {
   t->block_size = pol.block_size;
   t->springs = pol.springs;
   t->tickets = pol.tickets;
+  t->lanes_sie = pol.side_mask != 0u ? 2 : 1;
   t->step = &jit_step;
   t->dynamics = &jit_dynamics;
   t->energy = &jit_energy;
@@ -496,8 +557,12 @@ int jit_precompile(const KernelTable* table, int contact, unsigned kinds, int* n
   const JitTable* t = static_cast<const JitTable*>(table);
   const int c = contact < 0 ? 0 : (contact > 2 ? 2 : contact);
   std::vector<std::string> exprs;
-  if (kinds & JitStepSIE) exprs.push_back(step_expr(c, 0));
-  if (kinds & JitStepRK) exprs.push_back(step_expr(c, 1));
+  if (kinds & JitStepSIE) {
+    exprs.push_back(step_expr(c, 0, 0));
+    if (t->lanes_sie == 2) exprs.push_back(step_expr(c, 0, 1));  // small batches run warp pairs
+  }
+  if (kinds & JitStepRK) exprs.push_back(step_expr(c, 1, 0));
+  if (kinds & JitStepTauSeq) exprs.push_back(step_expr(c, 0, 2));
   if (kinds & JitDynamics) exprs.push_back(kDynamicsExpr);
   if (kinds & JitEnergy) exprs.push_back(kEnergyExpr);
   for (const std::string& e : exprs) {

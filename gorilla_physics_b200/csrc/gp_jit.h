@@ -26,10 +26,11 @@ struct JitPolicy {
   bool springs = false;      // SpringContact legs compiled into the general-contact kernels
   bool tickets = true;       // step kernels compiled with ticket mode
   unsigned contact_list_mask = 0u;  // bit b: body b runs the per-lane list of points in contact
+  unsigned side_mask = 0u;  // warp-pair mapping: bit b = body b belongs to half 1 (0: thread per environment)
 };
 
 // which kernels of a table (bit mask; gp_mechanism_precompile)
-enum JitKind : unsigned { JitStepSIE = 1u, JitStepRK = 2u, JitDynamics = 4u, JitEnergy = 8u };
+enum JitKind : unsigned { JitStepSIE = 1u, JitStepRK = 2u, JitDynamics = 4u, JitEnergy = 8u, JitStepTauSeq = 16u };
 
 // is NVRTC loadable in this process? (`why` receives the reason when not)
 bool jit_available(std::string* why = nullptr);

@@ -291,12 +291,169 @@ constexpr int step_min_blocks() {
 #ifndef GP_STEP_SYNC_EVERY
 #define GP_STEP_SYNC_EVERY 4  // barrier every so many time steps (power of two); profiles/r1_tuning.md
 #endif
-template <class Topo, int CONTACT, int INTEG>
+// The work of one thread for one work item (a block of environments x a range of the fused steps): load the state,
+// run the steps in registers, store it. T is the topology as this thread sees it: the whole tree, or - warp-pair
+// mapping, gp_topology.cuh - one half of it (the paired warp runs the other half on the same environments).
+template <class T, int CONTACT, int INTEG, bool TK, bool TAUSEQ>
+GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env, const bool active, const int step_begin,
+                    const int step_end, const bool first_chunk, const bool last_chunk, const double* s_cp, double* xch,
+                    const int bar_id) {
+  constexpr int NQ = T::NQ, NV = T::NV;
+  constexpr int U = T::kUnroll;
+  const int nq = T::nq(P), nv = T::nv(P);
+  double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
+  if (A.q_aos_in && first_chunk) {
+    // one environment's values are contiguous: a warp reads one contiguous stretch, once per launch
+    for_q_entries<T>(P, [&](auto kk) { const int k = kk; q[k] = A.q_aos_in[env * nq + k]; });
+    for_v_entries<T>(P, [&](auto kk) { const int k = kk; v[k] = A.v_aos_in[env * nv + k]; });
+  } else {
+    // (ticket mode: another SM may have written the planes during this launch, so read them at L2)
+    for_q_entries<T>(P, [&](auto kk) {
+      const int k = kk;
+      q[k] = TK ? __ldcg(A.q + (long long)k * A.ld + env) : A.q[(long long)k * A.ld + env];
+    });
+    for_v_entries<T>(P, [&](auto kk) {
+      const int k = kk;
+      v[k] = TK ? __ldcg(A.v + (long long)k * A.ld + env) : A.v[(long long)k * A.ld + env];
+    });
+  }
+  for_v_entries<T>(P, [&](auto kk) {
+    const int k = kk;
+#ifdef GP_ZERO_TAU  // tuning builds only: what would the registers that hold the torques be worth?
+    tau_in[k] = 0.0;
+#else
+    tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
+#endif
+    tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
+  });
+  unsigned status = 0u;
+  double cstate[2] = {0.0, 0.0};
+  if (A.ctrl_state) {
+    cstate[0] = TK ? __ldcg(A.ctrl_state + env) : A.ctrl_state[env];
+    cstate[1] = TK ? __ldcg(A.ctrl_state + A.ld + env) : A.ctrl_state[A.ld + env];
+  }
+  // (clones of the last environment in a partially filled block must not touch its spring-contact state)
+  DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
+  if constexpr (CONTACT != 0 && GP_CONTACT_LIST && T::kContactList) none.cp_table = s_cp;
+  none.xch = xch;
+  none.bar_id = bar_id;
+
+#pragma unroll 1
+  for (int s = step_begin; s < step_end; ++s) {
+    if constexpr (GP_STEP_SYNC && T::kBlockSize >= 256) {
+      // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
+      // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
+      // then share instruction-cache lines instead of each streaming the whole body from L2
+      if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
+    }
+    // a torque vector per time step (gp_batch_step_tau_sequence): its own instantiation of the semi-implicit-Euler
+    // kernels - carried as a run-time branch by the plain rollout it cost the navbot kernel 5.5 % (spills), the
+    // SO-101 one 1 % (profiles/r2_tuning.md)
+    if constexpr (TAUSEQ) {
+      if (A.tau_seq != nullptr) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("");  // a real (uniform) branch, not a predicated copy of the loads in every step
+#endif
+        const double* ts = A.tau_seq + (long long)s * A.tau_seq_step + env * A.tau_seq_env;
+        for_v_entries<T>(P, [&](auto kk) { const int k = kk; tau[k] = ts[(long long)k * A.tau_seq_k]; });
+      }
+    }
+    controller_tau<T>(P, A, q, v, tau_in, tau, cstate);
+    if (INTEG == IntegSIE) {
+      // semi_implicit_euler, reference integrators.rs:25-39, :276-319
+      status |= dynamics_core<T, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
+      for_v_entries<T>(P, [&](auto kk) { const int k = kk; v[k] = v[k] + vdot[k] * A.dt; });
+      advance_q<T>(P, q, v, A.dt, q);
+    } else {
+      // runge_kutta_2 / runge_kutta_4, reference integrators.rs:177-225 with euler_step :230-271
+      const bool rk4 = (A.integrator == GP_RUNGE_KUTTA_4);
+      const int n_stage = rk4 ? 4 : 2;
+      double q0[NQ], v0[NV], facc[NV];
+#pragma unroll U
+      for (int k = 0; k < nq; ++k) q0[k] = q[k];
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) { v0[k] = v[k]; facc[k] = 0.0; }
+#pragma unroll 1
+      for (int st = 0; st < n_stage; ++st) {
+        status |= dynamics_core<T, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
+        if (st + 1 < n_stage) {
+          // RK4: f1 + 2 f2 + 2 f3 (+ f4 below), stage steps dt/2, dt/2, dt ; RK2: stage step dt/2
+          const double wgt = (st == 0) ? 1.0 : 2.0;
+          const double h = (rk4 && st == 2) ? A.dt : A.dt / 2.0;
+#pragma unroll U
+          for (int k = 0; k < nv; ++k) facc[k] = facc[k] + vdot[k] * wgt;
+          advance_q<T>(P, q0, v0, h, q);
+#pragma unroll U
+          for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * h;
+        }
+      }
+      if (rk4) {
+#pragma unroll U
+        for (int k = 0; k < nv; ++k) vdot[k] = (facc[k] + vdot[k]) / 6.0;
+      }
+      advance_q<T>(P, q0, v0, A.dt, q);
+#pragma unroll U
+      for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * A.dt;
+    }
+    if (A.hist_q != nullptr && active) {  // (uniform test; history launches are bandwidth-bound anyway)
+      double* hq = A.hist_q + ((long long)s * A.hist_n + env) * nq;
+      for_q_entries<T>(P, [&](auto kk) {
+        const int k = kk;
+        if (T::owns_q(ic_of<decltype(kk)>::value)) hq[k] = q[k];
+      });
+      if (A.hist_v != nullptr) {
+        double* hv = A.hist_v + ((long long)s * A.hist_n + env) * nv;
+        for_v_entries<T>(P, [&](auto kk) {
+          const int k = kk;
+          if (T::owns_dof(ic_of<decltype(kk)>::value)) hv[k] = v[k];
+        });
+      }
+    }
+  }
+
+  if (active) {
+    if (A.ctrl_state && T::kSide <= 0) {
+      A.ctrl_state[env] = cstate[0];
+      A.ctrl_state[A.ld + env] = cstate[1];
+    }
+    bool finite = true;
+    for_q_entries<T>(P, [&](auto kk) {
+      const int k = kk;
+      if (T::owns_q(ic_of<decltype(kk)>::value)) {
+        A.q[(long long)k * A.ld + env] = q[k];
+        if (A.q_aos_out && last_chunk) A.q_aos_out[env * nq + k] = q[k];
+        finite = finite && isfinite(q[k]);
+      }
+    });
+    for_v_entries<T>(P, [&](auto kk) {
+      const int k = kk;
+      if (T::owns_dof(ic_of<decltype(kk)>::value)) {
+        A.v[(long long)k * A.ld + env] = v[k];
+        if (A.q_aos_out && last_chunk) A.v_aos_out[env * nv + k] = v[k];
+        finite = finite && isfinite(v[k]);
+      }
+    });
+    if (!finite) status |= kEnvNaN;
+    if (status) {
+      // (at L2: an earlier chunk may have run on another SM; the other half of a warp pair writes the same word)
+      if constexpr (TK || T::kSided) atomicOr(A.status + env, status);
+      else A.status[env] |= status;
+    }
+  }
+}
+
+// PAIRS: two warps per 32 environments, half the tree each (gp_topology.cuh; topologies that declare halves,
+// Spec::side_mask, semi-implicit Euler). Both mappings of such a topology are compiled and the launcher picks per
+// launch (use_pairs, gp_launch.h): a batch that fills the GPU runs a thread per environment (the halves duplicate
+// the root's work, about 15 % more instructions in total), a small one - the latency-bound regime, e.g. 8 K
+// environments per GPU when 64 K are spread over 8 GPUs - runs pairs: twice the warps, each with 0.58 of the
+// instruction stream (navbot 8 K: +33 %, profiles/r2_tuning.md).
+// TAUSEQ: the kernel reads StepArgs::tau_seq (a torque vector per time step). The Runge-Kutta kernels always do;
+// the semi-implicit-Euler ones exist with and without (the launcher picks the one a launch needs).
+template <class Topo, int CONTACT, int INTEG, bool PAIRS = false, bool TAUSEQ = (INTEG != IntegSIE)>
 __global__ void __launch_bounds__(Topo::kBlockSize, (step_min_blocks<Topo, CONTACT>()))
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
-  constexpr int NQ = Topo::NQ, NV = Topo::NV;
-  constexpr int U = Topo::kUnroll;
-  const int nq = Topo::nq(P), nv = Topo::nv(P);
+  static_assert(!PAIRS || (Topo::kHasSides && INTEG == IntegSIE && !TAUSEQ), "warp pairs: sided topologies, plain semi-implicit Euler");
   // contact points for the per-lane hit list of dynamics_core (lane-dependent index: shared memory)
   __shared__ double s_cp[(CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) ? kMaxCP * 4 : 1];
   if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) {
@@ -308,6 +465,9 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     }
     __syncthreads();
   }
+  // warp pairs: exchange buffers, [pair][2 halves][kXchSlots][32 lanes] doubles (dynamic shared memory,
+  // step_dynamic_smem below)
+  extern __shared__ double s_xch[];
 
   // Work item = (block of environments, range of the fused steps). Normally one per thread block: its own
   // environments, all the steps. In ticket mode (A.tickets, see gp_launch.h) a persistent grid draws items
@@ -348,129 +508,25 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
     }
     // threads past the end redo the last environment (and store nothing) so that the whole block
     // can meet at the per-step barrier below
-    const long long env_raw = group * blockDim.x + threadIdx.x;
-    const bool active = env_raw < A.n;
-    const long long env = active ? env_raw : A.n - 1;
-
-    double q[NQ], v[NV], tau_in[NV], tau[NV], vdot[NV];
-    if (A.q_aos_in && first_chunk) {
-      // one environment's values are contiguous: a warp reads one contiguous stretch, once per launch
-#pragma unroll U
-      for (int k = 0; k < nq; ++k) q[k] = A.q_aos_in[env * nq + k];
-#pragma unroll U
-      for (int k = 0; k < nv; ++k) v[k] = A.v_aos_in[env * nv + k];
+    if constexpr (PAIRS) {
+      // warps 2p and 2p+1 advance the same 32 environments, one half of the tree each
+      const int warp = (int)(threadIdx.x >> 5), pair = warp >> 1;
+      const long long env_raw = group * (long long)(blockDim.x >> 1) + pair * 32 + (int)(threadIdx.x & 31u);
+      const bool active = env_raw < A.n;
+      const long long env = active ? env_raw : A.n - 1;
+      double* xch = s_xch + (size_t)pair * (2 * kXchSlots * 32);
+      if (warp & 1)
+        step_item<typename Topo::template Half<1>, CONTACT, INTEG, TK, TAUSEQ>(P, A, env, active, step_begin, step_end, first_chunk,
+                                                                        last_chunk, s_cp, xch, 1 + pair);
+      else
+        step_item<typename Topo::template Half<0>, CONTACT, INTEG, TK, TAUSEQ>(P, A, env, active, step_begin, step_end, first_chunk,
+                                                                        last_chunk, s_cp, xch, 1 + pair);
     } else {
-#pragma unroll U
-      // (ticket mode: another SM may have written the planes during this launch, so read them at L2)
-      for (int k = 0; k < nq; ++k) q[k] = TK ? __ldcg(A.q + (long long)k * A.ld + env) : A.q[(long long)k * A.ld + env];
-#pragma unroll U
-      for (int k = 0; k < nv; ++k) v[k] = TK ? __ldcg(A.v + (long long)k * A.ld + env) : A.v[(long long)k * A.ld + env];
-    }
-#pragma unroll U
-    for (int k = 0; k < nv; ++k) {
-#ifdef GP_ZERO_TAU  // tuning builds only: what would the registers that hold the torques be worth?
-      tau_in[k] = 0.0;
-#else
-      tau_in[k] = A.tau ? A.tau[(long long)k * A.ld + env] : 0.0;
-#endif
-      tau[k] = tau_in[k];  // stays as loaded unless a controller overwrites it every step
-    }
-    unsigned status = 0u;
-    double cstate[2] = {0.0, 0.0};
-    if (A.ctrl_state) {
-      cstate[0] = TK ? __ldcg(A.ctrl_state + env) : A.ctrl_state[env];
-      cstate[1] = TK ? __ldcg(A.ctrl_state + A.ld + env) : A.ctrl_state[A.ld + env];
-    }
-    // (clones of the last environment in a partially filled block must not touch its spring-contact state)
-    DynOut none{nullptr, nullptr, nullptr, A.ld, env, active ? A.sc_state : nullptr};
-    if constexpr (CONTACT != 0 && GP_CONTACT_LIST && Topo::kContactList) none.cp_table = s_cp;
-
-#pragma unroll 1
-    for (int s = step_begin; s < step_end; ++s) {
-      if constexpr (GP_STEP_SYNC && Topo::kBlockSize >= 256) {
-      // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
-      // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
-      // then share instruction-cache lines instead of each streaming the whole body from L2
-      if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
-      }
-      if (A.tau_seq != nullptr) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("");  // a real (uniform) branch, not a predicated copy of the loads in every step
-#endif
-        const double* ts = A.tau_seq + (long long)s * A.tau_seq_step + env * A.tau_seq_env;
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) tau[k] = ts[(long long)k * A.tau_seq_k];
-      }
-      controller_tau<Topo>(P, A, q, v, tau_in, tau, cstate);
-      if (INTEG == IntegSIE) {
-        // semi_implicit_euler, reference integrators.rs:25-39, :276-319
-        status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) v[k] = v[k] + vdot[k] * A.dt;
-        advance_q<Topo>(P, q, v, A.dt, q);
-      } else {
-        // runge_kutta_2 / runge_kutta_4, reference integrators.rs:177-225 with euler_step :230-271
-        const bool rk4 = (A.integrator == GP_RUNGE_KUTTA_4);
-        const int n_stage = rk4 ? 4 : 2;
-        double q0[NQ], v0[NV], facc[NV];
-#pragma unroll U
-        for (int k = 0; k < nq; ++k) q0[k] = q[k];
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) { v0[k] = v[k]; facc[k] = 0.0; }
-#pragma unroll 1
-        for (int st = 0; st < n_stage; ++st) {
-          status |= dynamics_core<Topo, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
-          if (st + 1 < n_stage) {
-            // RK4: f1 + 2 f2 + 2 f3 (+ f4 below), stage steps dt/2, dt/2, dt ; RK2: stage step dt/2
-            const double wgt = (st == 0) ? 1.0 : 2.0;
-            const double h = (rk4 && st == 2) ? A.dt : A.dt / 2.0;
-#pragma unroll U
-            for (int k = 0; k < nv; ++k) facc[k] = facc[k] + vdot[k] * wgt;
-            advance_q<Topo>(P, q0, v0, h, q);
-#pragma unroll U
-            for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * h;
-          }
-        }
-        if (rk4) {
-#pragma unroll U
-          for (int k = 0; k < nv; ++k) vdot[k] = (facc[k] + vdot[k]) / 6.0;
-        }
-        advance_q<Topo>(P, q0, v0, A.dt, q);
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) v[k] = v0[k] + vdot[k] * A.dt;
-      }
-      if (A.hist_q != nullptr && active) {  // (uniform test; history launches are bandwidth-bound anyway)
-        double* hq = A.hist_q + ((long long)s * A.hist_n + env) * nq;
-#pragma unroll U
-        for (int k = 0; k < nq; ++k) hq[k] = q[k];
-        if (A.hist_v != nullptr) {
-          double* hv = A.hist_v + ((long long)s * A.hist_n + env) * nv;
-#pragma unroll U
-          for (int k = 0; k < nv; ++k) hv[k] = v[k];
-        }
-      }
-    }
-
-    if (active) {
-      if (A.ctrl_state) {
-        A.ctrl_state[env] = cstate[0];
-        A.ctrl_state[A.ld + env] = cstate[1];
-      }
-#pragma unroll U
-      for (int k = 0; k < nq; ++k) A.q[(long long)k * A.ld + env] = q[k];
-#pragma unroll U
-      for (int k = 0; k < nv; ++k) A.v[(long long)k * A.ld + env] = v[k];
-      if (A.q_aos_out && last_chunk) {
-#pragma unroll U
-        for (int k = 0; k < nq; ++k) A.q_aos_out[env * nq + k] = q[k];
-#pragma unroll U
-        for (int k = 0; k < nv; ++k) A.v_aos_out[env * nv + k] = v[k];
-      }
-      if (!all_finite(q, nq) || !all_finite(v, nv)) status |= kEnvNaN;
-      if (status) {
-        if constexpr (TK) atomicOr(A.status + env, status);  // (at L2: an earlier chunk may have run on another SM)
-        else A.status[env] |= status;
-      }
+      const long long env_raw = group * blockDim.x + threadIdx.x;
+      const bool active = env_raw < A.n;
+      const long long env = active ? env_raw : A.n - 1;
+      step_item<typename Topo::Whole, CONTACT, INTEG, TK, TAUSEQ>(P, A, env, active, step_begin, step_end, first_chunk, last_chunk,
+                                                         s_cp, nullptr, 0);
     }
     if (!TK || !A.tickets) return;
     // publish: every thread's stores, then the chunk count of this environment block
@@ -542,21 +598,39 @@ energy_kernel(const __grid_constant__ MechParams P, const __grid_constant__ Ener
 // with the run-time-compiled kernels of gp_jit.cpp.
 template <class Kernel>
 inline void launch_step_kernel(Kernel* kernel, int tuned_block, bool tickets_compiled_in, cudaStream_t s, const MechParams& P,
-                               const StepArgs& A0) {
+                               const StepArgs& A0, int lanes = 1) {
   StepArgs A = A0;
-  const StepLaunchPlan plan = plan_step_launch((const void*)kernel, tuned_block, tickets_compiled_in, s, A);
-  kernel<<<plan.grid, plan.block, 0, s>>>(P, A);
+  if (lanes == 2) {
+    // the exchange buffers of a full block of warp pairs exceed the 48 KB a kernel gets without asking
+    // (once per kernel and device; the attribute is per device, a batch may sit on any)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static thread_local Kernel* done_kernel[64] = {};
+    if (dev < 0 || dev >= 64 || done_kernel[dev] != kernel) {
+      cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dynamic_smem(tuned_block, 2));
+      if (dev >= 0 && dev < 64) done_kernel[dev] = kernel;
+    }
+  }
+  const StepLaunchPlan plan = plan_step_launch((const void*)kernel, tuned_block, tickets_compiled_in, s, A, lanes);
+  kernel<<<plan.grid, plan.block, plan.smem, s>>>(P, A);
 }
 
 // The Runge-Kutta step kernels of a topology live in their own translation unit (variants/*_rk.cu defines
 // GP_TU_RUNGE_KUTTA and instantiates launch_step_rk explicitly; the other unit only declares it), so that the
 // two halves of a big topology compile in parallel.
 template <class Topo>
-cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, const StepArgs& A);
+cudaError_t launch_step_rk(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A);
+// (integ_class IntegSIE here = the semi-implicit-Euler kernels that read a torque sequence, which share the unit)
 #ifdef GP_TU_RUNGE_KUTTA
 template <class Topo>
-cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, const StepArgs& A) {
+cudaError_t launch_step_rk(int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
   auto go = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A); };
+  if (integ_class == IntegSIE) {
+    if (contact == 0) go(&step_kernel<Topo, 0, IntegSIE, false, true>);
+    else if (contact == 1) go(&step_kernel<Topo, 1, IntegSIE, false, true>);
+    else go(&step_kernel<Topo, 2, IntegSIE, false, true>);
+    return cudaGetLastError();
+  }
   if (contact == 0) go(&step_kernel<Topo, 0, IntegRK>);
   else if (contact == 1) go(&step_kernel<Topo, 1, IntegRK>);
   else go(&step_kernel<Topo, 2, IntegRK>);
@@ -566,7 +640,16 @@ cudaError_t launch_step_rk(int contact, cudaStream_t s, const MechParams& P, con
 
 template <class Topo>
 cudaError_t launch_step(const KernelTable*, int contact, int integ_class, cudaStream_t s, const MechParams& P, const StepArgs& A) {
-  if (integ_class != IntegSIE) return launch_step_rk<Topo>(contact, s, P, A);
+  if (integ_class != IntegSIE || A.tau_seq != nullptr) return launch_step_rk<Topo>(contact, integ_class, s, P, A);
+  if constexpr (Topo::kHasSides) {
+    if (use_pairs(A.n, Topo::kBlockSize)) {
+      auto go2 = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A, 2); };
+      if (contact == 0) go2(&step_kernel<Topo, 0, IntegSIE, true>);
+      else if (contact == 1) go2(&step_kernel<Topo, 1, IntegSIE, true>);
+      else go2(&step_kernel<Topo, 2, IntegSIE, true>);
+      return cudaGetLastError();
+    }
+  }
   auto go = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A); };
   if (contact == 0) go(&step_kernel<Topo, 0, IntegSIE>);
   else if (contact == 1) go(&step_kernel<Topo, 1, IntegSIE>);
@@ -589,13 +672,13 @@ cudaError_t launch_energy(const KernelTable*, cudaStream_t s, const MechParams& 
 
 template <class Topo, class Spec>
 KernelTable make_static_table() {
-  return KernelTable{Spec::name(), Spec::data(), true, Topo::kBlockSize, Topo::kSprings, Topo::kTickets, &launch_step<Topo>, &launch_dynamics<Topo>,
-                     &launch_energy<Topo>};
+  return KernelTable{Spec::name(), Spec::data(), true, Topo::kBlockSize, Topo::kSprings, Topo::kTickets, Topo::kHasSides ? 2 : 1,
+                     &launch_step<Topo>, &launch_dynamics<Topo>, &launch_energy<Topo>};
 }
 template <class Topo>
 KernelTable make_generic_table() {
-  return KernelTable{"generic", TopoData{}, false, Topo::kBlockSize, true, Topo::kTickets, &launch_step<Topo>, &launch_dynamics<Topo>,
-                     &launch_energy<Topo>};
+  return KernelTable{"generic", TopoData{}, false, Topo::kBlockSize, true, Topo::kTickets, 1, &launch_step<Topo>,
+                     &launch_dynamics<Topo>, &launch_energy<Topo>};
 }
 
 #endif  // !__CUDACC_RTC__

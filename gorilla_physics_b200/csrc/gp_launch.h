@@ -113,15 +113,27 @@ inline int sm_count() {
   }();
   return n_sm;
 }
-inline int step_block_for(long long n, int tuned) {
+// (lanes = threads per environment: 1, or 2 for the warp-pair kernels, whose smallest block is one pair of warps)
+inline int step_block_for(long long n, int tuned, int lanes = 1) {
   const int n_sm = sm_count();
   static const bool fixed = std::getenv("GP_STEP_FIXED_BLOCK") != nullptr;  // tuning only
   static const char* forced = std::getenv("GP_STEP_BLOCK");                  // tuning only
   if (forced) return std::atoi(forced);
   int b = tuned;
-  while (!fixed && b > 32 && 4 * ((n + b - 1) / b) < 3 * n_sm) b /= 2;  // until 3/4 of the SMs have a block
+  // until 3/4 of the SMs have a block
+  while (!fixed && b > 32 * lanes && 4 * ((n + b / lanes - 1) / (b / lanes)) < 3 * n_sm) b /= 2;
   return b;
 }
+// Which mapping a semi-implicit-Euler step launch of a topology with halves uses (gp_kernels.cuh step_kernel):
+// warp pairs while all their blocks are resident at once (one block per SM), a thread per environment beyond.
+inline bool use_pairs(long long n, int tuned_block) {
+  static const char* forced = std::getenv("GP_STEP_PAIRS");  // tuning only: 0 never, 1 always
+  if (forced) return forced[0] == '1';
+  return 2 * n <= (long long)sm_count() * tuned_block;
+}
+// dynamic shared memory of a step launch: the exchange buffers of the warp pairs (gp_dynamics.cuh kXchSlots = 43
+// doubles per lane and half)
+inline size_t step_dynamic_smem(int block, int lanes) { return lanes == 2 ? (size_t)(block / 64) * 2 * 43 * 32 * sizeof(double) : 0; }
 
 // One step launch. Ticket mode (see step_kernel and gp_launch.h) when the blocks of the batch would leave
 // the last wave badly filled: the launch costs ceil(blocks / resident blocks) waves whatever the last one
@@ -130,18 +142,21 @@ inline int step_block_for(long long n, int tuned) {
 struct StepLaunchPlan {
   unsigned grid;
   int block;
+  size_t smem;  // dynamic shared memory
 };
 // (kernel = the __global__ function's address, or a cudaKernel_t of a run-time-compiled kernel: the occupancy
 // query takes either. Fills in the ticket fields of A.)
-inline StepLaunchPlan plan_step_launch(const void* kernel, int tuned_block, bool tickets_compiled_in, cudaStream_t s, StepArgs& A) {
-  const int block = step_block_for(A.n, tuned_block);
-  const long long groups = grid_for(A.n, block);
+inline StepLaunchPlan plan_step_launch(const void* kernel, int tuned_block, bool tickets_compiled_in, cudaStream_t s, StepArgs& A,
+                                       int lanes = 1) {
+  const int block = step_block_for(A.n, tuned_block, lanes);
+  const size_t smem = step_dynamic_smem(block, lanes);
+  const long long groups = grid_for(A.n, block / lanes);
   long long grid = groups;
   A.tickets = nullptr;
   static const bool off = std::getenv("GP_NO_TICKETS") != nullptr;  // tuning only
   if (!off && tickets_compiled_in && A.ticket_buf && A.n_steps >= 8 && groups + 1 <= A.ticket_capacity) {
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
     const long long slots = (long long)occ * sm_count();
     const long long waves = (groups + slots - 1) / slots;
     if (groups > slots && (double)(waves * slots) > 1.08 * (double)groups) {
@@ -158,7 +173,7 @@ inline StepLaunchPlan plan_step_launch(const void* kernel, int tuned_block, bool
       }
     }
   }
-  return StepLaunchPlan{(unsigned)grid, block};
+  return StepLaunchPlan{(unsigned)grid, block, smem};
 }
 
 
@@ -170,6 +185,7 @@ struct KernelTable {
   int block_size;  // threads per block of the step kernels
   bool springs;    // the general-contact kernels implement SpringContact
   bool tickets;    // the step kernels are compiled with ticket mode (StepArgs::tickets)
+  int lanes_sie;   // 2: the semi-implicit-Euler step kernels also exist in the warp-pair mapping (use_pairs picks)
   // (self = the table the pointer was taken from: the run-time-compiled tables of gp_jit.cpp keep their
   // kernel handles behind it, the build-time variants ignore it)
   cudaError_t (*step)(const KernelTable* self, int contact, int integ_class, cudaStream_t, const MechParams&, const StepArgs&);

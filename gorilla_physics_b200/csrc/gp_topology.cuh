@@ -41,6 +41,7 @@ struct TopoTables {
   int has_children[kMaxBodies];
   int anchored[kMaxBodies];  // rigidly attached to the world through fixed joints only: zero twist
   int dof_body[kMaxNV];
+  int q_body[kMaxNQ];  // body that owns entry k of the flat q vector
 };
 
 constexpr int joint_nq(int t) { return t == JFloating ? 7 : (t == JFixed ? 0 : 1); }
@@ -64,6 +65,7 @@ constexpr TopoTables make_tables(const TopoData& d) {
     for (int k = 0; k < kMaxBodies; ++k) t.anc_at[i][k] = -1;
   }
   for (int k = 0; k < kMaxNV; ++k) t.dof_body[k] = 0;
+  for (int k = 0; k < kMaxNQ; ++k) t.q_body[k] = 0;
   for (int i = 0; i < d.nb; ++i) {
     t.parent[i] = d.parent[i];
     t.jtype[i] = d.jtype[i];
@@ -72,6 +74,8 @@ constexpr TopoTables make_tables(const TopoData& d) {
     t.voff[i] = vo;
     for (int k = 0; k < joint_nv(d.jtype[i]); ++k)
       if (vo + k < kMaxNV) t.dof_body[vo + k] = i;
+    for (int k = 0; k < joint_nq(d.jtype[i]); ++k)
+      if (qo + k < kMaxNQ) t.q_body[qo + k] = i;
     qo += joint_nq(d.jtype[i]);
     vo += joint_nv(d.jtype[i]);
     int c = i, k = 0;
@@ -112,6 +116,15 @@ struct IC {
   static constexpr int value = I;
   GP_HD constexpr operator int() const { return I; }
 };
+// the literal behind a loop index: IC<I> -> I; a run-time int (run-time-topology loops) -> -1
+template <class T>
+struct ic_of {
+  static constexpr int value = -1;
+};
+template <int I>
+struct ic_of<IC<I>> {
+  static constexpr int value = I;
+};
 template <int B, int E, class F>
 GP_HD void static_for(F&& f) {
   if constexpr (B < E) {
@@ -126,11 +139,15 @@ GP_HD void static_rfor(F&& f) {  // E-1, E-2, ..., B
     static_rfor<B, E - 1>(f);
   }
 }
-// body loops: unrolled at compile time for static topologies, run-time loops otherwise
+// body loops: unrolled at compile time for static topologies, run-time loops otherwise. A sided topology
+// (StaticTopo<Spec, SIDE>, warp-pair mapping: see below) visits only the bodies / dofs of its own half of
+// the tree plus the root, which both halves carry.
 template <class Topo, class F>
 GP_HD void for_bodies(const MechParams& P, F&& f) {
   if constexpr (Topo::kStatic) {
-    static_for<0, Topo::NB>(f);
+    static_for<0, Topo::NB>([&](auto ii) {
+      if constexpr (Topo::mine_body(ic_of<decltype(ii)>::value)) f(ii);
+    });
   } else {
     for (int i = 0; i < P.nb; ++i) f(i);
   }
@@ -138,7 +155,9 @@ GP_HD void for_bodies(const MechParams& P, F&& f) {
 template <class Topo, class F>
 GP_HD void for_bodies_reverse(const MechParams& P, F&& f) {
   if constexpr (Topo::kStatic) {
-    static_rfor<0, Topo::NB>(f);
+    static_rfor<0, Topo::NB>([&](auto ii) {
+      if constexpr (Topo::mine_body(ic_of<decltype(ii)>::value)) f(ii);
+    });
   } else {
     for (int i = P.nb - 1; i >= 0; --i) f(i);
   }
@@ -146,7 +165,9 @@ GP_HD void for_bodies_reverse(const MechParams& P, F&& f) {
 template <class Topo, class F>
 GP_HD void for_dofs(const MechParams& P, F&& f) {
   if constexpr (Topo::kStatic) {
-    static_for<0, Topo::kNVreal>(f);
+    static_for<0, Topo::kNVreal>([&](auto kk) {
+      if constexpr (Topo::mine_dof(ic_of<decltype(kk)>::value)) f(kk);
+    });
   } else {
     for (int k = 0; k < P.n_v; ++k) f(k);
   }
@@ -154,13 +175,39 @@ GP_HD void for_dofs(const MechParams& P, F&& f) {
 template <class Topo, class F>
 GP_HD void for_dofs_reverse(const MechParams& P, F&& f) {
   if constexpr (Topo::kStatic) {
-    static_rfor<0, Topo::kNVreal>(f);
+    static_rfor<0, Topo::kNVreal>([&](auto kk) {
+      if constexpr (Topo::mine_dof(ic_of<decltype(kk)>::value)) f(kk);
+    });
   } else {
     for (int k = P.n_v - 1; k >= 0; --k) f(k);
   }
 }
+// entries of the flat q / v vectors (loads, stores, integration): every entry for a whole-tree thread; a sided
+// thread sees the entries of its own bodies and of the root
+template <class Topo, class F>
+GP_HD void for_q_entries(const MechParams& P, F&& f) {
+  if constexpr (Topo::kStatic) {
+    static_for<0, Topo::kNQreal>([&](auto kk) {
+      if constexpr (Topo::mine_body(Topo::tables().q_body[ic_of<decltype(kk)>::value])) f(kk);
+    });
+  } else {
+    for (int k = 0; k < P.n_q; ++k) f(k);
+  }
+}
+template <class Topo, class F>
+GP_HD void for_v_entries(const MechParams& P, F&& f) {
+  for_dofs<Topo>(P, f);
+}
 
-template <class Spec>
+// Warp-pair mapping (Spec::side_mask() != 0): the tree is cut at its root body (body 0) into two halves, each a
+// set of whole child subtrees of the root. Two warps advance the same 32 environments, one half each
+// (StaticTopo<Spec, 0> and StaticTopo<Spec, 1>), both carrying the root: half the bodies, columns of H and
+// live state per thread. Per time step they exchange, through shared memory behind a 64-thread named
+// barrier, what meets at the root: the halves' contributions to the root's composite inertia and force
+// (leaf-to-root pass) and to the root block of H and of the right-hand side (factorisation); everything
+// else - kinematics, contact, the columns of their own dofs, the back-substitution - is local.
+// side_mask: bit i set = body i belongs to half 1 (bit 0, the root, stays clear).
+template <class Spec, int SIDE = -1>
 struct StaticTopo {
   static constexpr bool kStatic = true;
   static constexpr TopoTables tables() { return make_tables(Spec::data()); }
@@ -168,6 +215,22 @@ struct StaticTopo {
   static constexpr int NQ = tables().nq > 0 ? tables().nq : 1;
   static constexpr int NV = tables().nv > 0 ? tables().nv : 1;
   static constexpr int kNVreal = tables().nv;
+  static constexpr int kNQreal = tables().nq;
+  // warp-pair mapping: SIDE -1 = the thread owns the whole tree; 0 / 1 = one half (plus the root)
+  static constexpr int kSide = SIDE;
+  static constexpr bool kSided = SIDE >= 0;
+  static constexpr unsigned kSideMask = Spec::side_mask();
+  static constexpr bool kHasSides = kSideMask != 0u;  // the step kernel of this topology runs warp pairs
+  static constexpr int kRootNV = joint_nv(tables().jtype[0]);
+  using Whole = StaticTopo<Spec, -1>;
+  template <int S> using Half = StaticTopo<Spec, S>;
+  // body i is advanced by this thread / is stored by this thread (the root is computed by both halves and
+  // stored by half 0)
+  GP_HD static constexpr bool mine_body(int i) { return SIDE < 0 || i == 0 || (int)((kSideMask >> i) & 1u) == SIDE; }
+  GP_HD static constexpr bool owns_body(int i) { return SIDE < 0 || (i == 0 ? SIDE == 0 : (int)((kSideMask >> i) & 1u) == SIDE); }
+  GP_HD static constexpr bool mine_dof(int k) { return mine_body(tables().dof_body[k]); }
+  GP_HD static constexpr bool owns_dof(int k) { return owns_body(tables().dof_body[k]); }
+  GP_HD static constexpr bool owns_q(int k) { return owns_body(tables().q_body[k]); }
   static constexpr int kUnroll = 64;
   static const char* name() { return Spec::name(); }
   static constexpr int min_blocks(int contact) { return Spec::min_blocks(contact); }
@@ -183,7 +246,7 @@ struct StaticTopo {
   GP_HD static constexpr bool contact_list(const MechParams&, int body, int /*n_points*/) { return Spec::contact_list(body); }
   // factorise H column by column inside the leaf-to-root pass (gp_dynamics.cuh): pays where the kernel
   // has registers to spare, i.e. everywhere but the 14-dof trees
-  static constexpr bool kColumnsInPass2 = tables().nv < 12;
+  static constexpr bool kColumnsInPass2 = tables().nv < 12 && !kSided;
 
   struct FParent { template <int K> static constexpr unsigned long long at() { return (unsigned long long)(tables().parent[K] + 1); } };
   struct FJtype { template <int K> static constexpr unsigned long long at() { return (unsigned long long)tables().jtype[K]; } };
@@ -245,6 +308,16 @@ struct StaticTopo {
 
 struct DynTopo {
   static constexpr bool kStatic = false;
+  static constexpr int kSide = -1;
+  static constexpr bool kSided = false;
+  static constexpr bool kHasSides = false;
+  static constexpr int kRootNV = 0;
+  using Whole = DynTopo;
+  GP_HD static constexpr bool mine_body(int) { return true; }
+  GP_HD static constexpr bool owns_body(int) { return true; }
+  GP_HD static constexpr bool mine_dof(int) { return true; }
+  GP_HD static constexpr bool owns_dof(int) { return true; }
+  GP_HD static constexpr bool owns_q(int) { return true; }
   static constexpr int NB = kMaxBodies;
   static constexpr int NQ = kMaxNQ;
   static constexpr int NV = kMaxNV;
@@ -296,6 +369,7 @@ struct SpecPendulum {  // helpers.rs:24 build_pendulum
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, configs 1-2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_R, GP_R}, {AxAny, AxAny}}; }
@@ -306,6 +380,7 @@ struct SpecDoublePendulum {  // helpers.rs:49 build_double_pendulum (acrobot, co
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr TopoData data() { return {2, {-1, 0}, {GP_P, GP_R}, {AxAny, AxAny}}; }
@@ -316,6 +391,7 @@ struct SpecCartPole {  // helpers.rs:111 build_cart_pole (config 2)
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(+z) chain (config 3)
   static constexpr TopoData data() {
@@ -331,6 +407,7 @@ struct SpecSO101 {  // builders/mod.rs:252 build_so101: fixed base + 6 revolute(
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, ball (config 4a)
   static constexpr TopoData data() { return {1, {-1}, {GP_F}, {AxAny}}; }
@@ -341,6 +418,7 @@ struct SpecFloating {  // helpers.rs:151 build_cube, :168 build_rimless_wheel, b
   static constexpr bool springs() { return true; }
   static constexpr bool tickets() { return true; }  // rimless wheel, 256 K: +3 %
   static constexpr bool contact_list(int) { return true; }  // cube corners, rimless-wheel spokes
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (config 4b)
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_P}, {AxAny, AxAny, AxAny}}; }
@@ -351,6 +429,7 @@ struct SpecHopper1D {  // examples/1D_hopper.rs: floating + 2 prismatic chain (c
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(spring) + revolute
   static constexpr TopoData data() { return {3, {-1, 0, 1}, {GP_F, GP_P, GP_R}, {AxAny, AxAny, AxAny}}; }
@@ -361,6 +440,7 @@ struct SpecHopper {  // helpers.rs:345 build_hopper: floating foot + prismatic(s
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return false; }
   static constexpr bool contact_list(int) { return false; }
+  static constexpr unsigned side_mask() { return 0u; }
 };
 struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, knee) revolute(-y)
   static constexpr TopoData data() {
@@ -376,6 +456,11 @@ struct SpecQuadruped {  // helpers.rs:423 build_quadruped: floating + 4 x (hip, 
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return true; }  // 64 K environments = 1.73 waves: +12 %
   static constexpr bool contact_list(int) { return false; }  // one or two points per body: the list only costs registers (-22 %)
+#ifndef GP_NO_SIDES
+  static constexpr unsigned side_mask() { return 0x1e0u; }  // half 0: legs 1-2, 3-4; half 1: legs 5-6, 7-8
+#else
+  static constexpr unsigned side_mask() { return 0u; }
+#endif
 };
 struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolute(+z) (config 5)
   static constexpr TopoData data() {
@@ -389,6 +474,12 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
   static constexpr bool springs() { return false; }
   static constexpr bool tickets() { return true; }  // 64 K environments = 1.73 waves: +12 %
   static constexpr bool contact_list(int body) { return body < 0 || body == 4 || body == 8; }  // the wheels (8 points on each rim)
+#ifndef GP_NO_SIDES
+  // half 0: leg 1 - foot 2 - wheel 4 and link 3; half 1: leg 5 - foot 6 - wheel 8 and link 7
+  static constexpr unsigned side_mask() { return (1u << 5) | (1u << 6) | (1u << 7) | (1u << 8); }
+#else
+  static constexpr unsigned side_mask() { return 0u; }
+#endif
 };
 
 // A specialisation for ONE more tree. Two users:
@@ -419,6 +510,9 @@ struct SpecNavbot {  // navbot_builder.rs:682 build_navbot: floating + 8 revolut
 #ifndef GP_CUSTOM_CONTACT_LIST_MASK
 #define GP_CUSTOM_CONTACT_LIST_MASK 0u  // bit b: body b runs the per-lane list of points in contact
 #endif
+#ifndef GP_CUSTOM_SIDE_MASK
+#define GP_CUSTOM_SIDE_MASK 0u  // bit b: body b belongs to half 1 of the warp-pair mapping (0: thread per environment)
+#endif
 struct SpecCustom {
   static constexpr TopoData data() {
     return {GP_CUSTOM_TOPO_NB, {GP_CUSTOM_TOPO_PARENTS}, {GP_CUSTOM_TOPO_JOINTS}, {GP_CUSTOM_TOPO_AXES}};
@@ -432,6 +526,7 @@ struct SpecCustom {
   static constexpr bool contact_list(int body) {
     return body < 0 ? (GP_CUSTOM_CONTACT_LIST_MASK) != 0u : (((GP_CUSTOM_CONTACT_LIST_MASK) >> body) & 1u) != 0u;
   }
+  static constexpr unsigned side_mask() { return GP_CUSTOM_SIDE_MASK; }
 };
 #endif
 

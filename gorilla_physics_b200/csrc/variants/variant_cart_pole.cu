@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_cart_pole_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecCartPole>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecCartPole>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_cart_pole() {
   static const KernelTable t = make_static_table<StaticTopo<SpecCartPole>, SpecCartPole>();
   return &t;

@@ -5,7 +5,7 @@
 namespace gp {
 #ifdef GP_CUSTOM_TOPO_NB
 // Runge-Kutta kernels: variant_custom_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecCustom>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecCustom>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_custom() {
   static const KernelTable t = make_static_table<StaticTopo<SpecCustom>, SpecCustom>();
   return &t;

@@ -4,6 +4,6 @@
 
 namespace gp {
 #ifdef GP_CUSTOM_TOPO_NB
-template cudaError_t launch_step_rk<StaticTopo<SpecCustom>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+template cudaError_t launch_step_rk<StaticTopo<SpecCustom>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 #endif
 }  // namespace gp

@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_double_pendulum_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecDoublePendulum>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecDoublePendulum>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_double_pendulum() {
   static const KernelTable t = make_static_table<StaticTopo<SpecDoublePendulum>, SpecDoublePendulum>();
   return &t;

@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_generic_rk.cu
-extern template cudaError_t launch_step_rk<DynTopo>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<DynTopo>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_generic() {
   static const KernelTable t = make_generic_table<DynTopo>();
   return &t;

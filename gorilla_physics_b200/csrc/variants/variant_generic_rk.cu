@@ -4,5 +4,5 @@
 #include "../gp_kernels.cuh"
 
 namespace gp {
-template cudaError_t launch_step_rk<DynTopo>(int, cudaStream_t, const MechParams&, const StepArgs&);
+template cudaError_t launch_step_rk<DynTopo>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 }  // namespace gp

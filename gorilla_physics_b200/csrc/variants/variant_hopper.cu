@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_hopper_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecHopper>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecHopper>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_hopper() {
   static const KernelTable t = make_static_table<StaticTopo<SpecHopper>, SpecHopper>();
   return &t;

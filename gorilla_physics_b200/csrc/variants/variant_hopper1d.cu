@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_hopper1d_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecHopper1D>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecHopper1D>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_hopper1d() {
   static const KernelTable t = make_static_table<StaticTopo<SpecHopper1D>, SpecHopper1D>();
   return &t;

@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_navbot_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecNavbot>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecNavbot>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_navbot() {
   static const KernelTable t = make_static_table<StaticTopo<SpecNavbot>, SpecNavbot>();
   return &t;

@@ -4,7 +4,7 @@
 
 namespace gp {
 // Runge-Kutta kernels: variant_pendulum_rk.cu
-extern template cudaError_t launch_step_rk<StaticTopo<SpecPendulum>>(int, cudaStream_t, const MechParams&, const StepArgs&);
+extern template cudaError_t launch_step_rk<StaticTopo<SpecPendulum>>(int, int, cudaStream_t, const MechParams&, const StepArgs&);
 const KernelTable* variant_pendulum() {
   static const KernelTable t = make_static_table<StaticTopo<SpecPendulum>, SpecPendulum>();
   return &t;

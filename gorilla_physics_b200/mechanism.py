@@ -57,7 +57,7 @@ class KernelMode(enum.IntEnum):
 
 
 # gp_mechanism_precompile kinds
-JIT_STEP_SIE, JIT_STEP_RK, JIT_DYNAMICS, JIT_ENERGY = 1, 2, 4, 8
+JIT_STEP_SIE, JIT_STEP_RK, JIT_DYNAMICS, JIT_ENERGY, JIT_STEP_TAU_SEQ = 1, 2, 4, 8, 16
 
 
 def jit_available() -> bool:
@@ -291,6 +291,12 @@ class MechanismState:
     @property
     def stream(self) -> int:
         return lib().gp_batch_stream(self._h)
+
+    @property
+    def step_lanes(self) -> int:
+        """threads per environment of a SemiImplicitEuler step of this batch: 1, or 2 (warp pairs: small batches of
+        trees that have two halves)"""
+        return lib().gp_batch_step_lanes(self._h)
 
     @property
     def launch_count(self) -> int:

@@ -210,8 +210,9 @@ int gp_jit_available(void);
 /* directory compiled kernels are written to (copied into buf, NUL-terminated); returns its length */
 size_t gp_jit_cache_dir(char* buf, size_t len);
 /* Compile (into the cache, without loading: needs NO GPU) the kernels this mechanism would launch:
- * kinds = bit mask of 1 step/SemiImplicitEuler, 2 step/Runge-Kutta, 4 dynamics (gp_batch_dynamics,
- * _mass_matrix, _free_velocity), 8 energy/poses. n_compiled (may be NULL) receives the number of
+ * kinds = bit mask of 1 step/SemiImplicitEuler (both mappings where the tree has halves), 2 step/Runge-Kutta,
+ * 4 dynamics (gp_batch_dynamics, _mass_matrix, _free_velocity), 8 energy/poses, 16 step/SemiImplicitEuler with a
+ * torque sequence (gp_batch_step_tau_sequence). n_compiled (may be NULL) receives the number of
  * kernels that were not cached yet. A no-op for mechanisms on shipped or generic kernels. */
 int gp_mechanism_precompile(const gp_mechanism* mech, unsigned kinds, int* n_compiled);
 
@@ -249,6 +250,10 @@ double* gp_batch_v_device(gp_batch* batch);
 double* gp_batch_tau_device(gp_batch* batch);
 void* gp_batch_stream(gp_batch* batch);
 int gp_batch_sync(gp_batch* batch);
+/* threads per environment a SemiImplicitEuler gp_batch_step of this batch runs with: 1, or 2 - trees that can be cut
+ * at their root into two halves (navbot, quadruped, run-time-compiled trees alike) run small batches as warp pairs,
+ * two warps per 32 environments with half the tree each, and batches that fill the GPU a thread per environment */
+int gp_batch_step_lanes(const gp_batch* batch);
 /* kernels launched on this batch's stream since creation (bench's gpu_launches) */
 int64_t gp_batch_launch_count(const gp_batch* batch);
 

@@ -797,7 +797,8 @@ def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
     cut into chunks that a persistent grid draws from a counter, the state of an environment block travelling
     through the q / v planes between chunks, possibly across SMs). The result must be what the plain mode
     gives: copies of the same states are bitwise equal wherever they sit in the batch, equal to a small
-    batch (one wave, plain mode) of the same states bit for bit, and within parity of the oracle."""
+    batch (one wave, plain mode) of the same states bit for bit (to rounding where the small batch runs the
+    warp-pair mapping), and within parity of the oracle."""
     factory, kw, _ = WORKLOADS[name]
     mech = factory()
     desc = mech.desc()
@@ -814,7 +815,16 @@ def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
     v1 = v1.reshape(n_copies, base_n, -1)
     same = lambda a, b: np.array_equal(a, b, equal_nan=True)  # (a few deep-penetration states blow up, as in the reference)
     assert all(same(q1[c], q1[0]) and same(v1[c], v1[0]) for c in range(n_copies))
-    assert same(q1[0][:256], qs) and same(v1[0][:256], vs)
+    if mech.kernel_variant in ("navbot_F8Rz", "quadruped_F8R"):
+        # topologies with halves: the small batch ran the warp-pair mapping (two warps per 32 environments, the
+        # halves' sums meeting at the root), the big one a thread per environment: same numbers to rounding
+        # (per environment; the few deep-penetration states in which the reference algorithm itself blows up amplify
+        # the last bit without bound and carry no information)
+        ok = np.isfinite(qs).all(axis=1) & np.isfinite(q1[0][:256]).all(axis=1)
+        eq, ev = rollout_errors(q1[0][:256][ok], qs[ok]), rollout_errors(v1[0][:256][ok], vs[ok], floor=1e-3)
+        assert ok.mean() > 0.97 and np.median(eq) < 1e-12 and np.quantile(eq, 0.9) < 1e-9 and np.quantile(ev, 0.9) < 1e-7
+    else:
+        assert same(q1[0][:256], qs) and same(v1[0][:256], vs)
     assert_rollout_parity(oracle_of(desc), q0[:512], v0[:512], q1[0][:512], v1[0][:512], dt, steps)
     # and through host buffers (simulate(): chunks on two streams, each with its own ticket scratch)
     q_in = np.tile(q0, (n_copies, 1))

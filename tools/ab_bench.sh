@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 for w in $W; do
   for rep in 1 2; do
     for lib in $LIBS; do
-      GP_LIB_PATH=$lib python bench.py --workload $w $ARGS --no-cpu-baseline 2>/dev/null \
+      GP_LIB_PATH=$lib python bench.py --workload $w $ARGS --no-cpu-baseline --sustain 0 2>/dev/null \
         | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('$w', '$lib', '%.4g' % d['value'], 'e2e %.4g' % d['e2e']['value'], d['clocks']['sm_mhz'])" >> gpurun_out/ab.txt
     done
   done
