@@ -302,6 +302,25 @@ GP_D V3 contact_force(double z, V3 n, V3 vel, double k, double alpha, double mu)
   return fma3(v_t, g, n * pi_n);
 }
 
+// the same law without a branch: everything is evaluated, a point that does not touch (z <= 0) selects zero at the
+// end (tuning: GP_CONTACT_BRANCHLESS, profiles/r2_tuning.md)
+GP_D V3 contact_force_select(double z, V3 n, V3 vel, double k, double alpha, double mu) {
+  const double z_dot = -dot(vel, n);
+  const double zn = z * (z * gp_rsqrt(fmax(z, 1e-280)));
+  const double lambda = 1.5 * alpha * k;
+  const double pi_n = fmax(zn * fma(lambda, z_dot, k), 0.0);
+  const V3 v_t = fma3(n, z_dot, vel);
+  const double vt2 = dot(v_t, v_t);
+  const double inv_norm = gp_rsqrt(fmax(vt2, 1e-6));
+  const double g = -mu * pi_n * ((vt2 > 1e-6) ? inv_norm : 1e3);
+  const V3 f = fma3(v_t, g, n * pi_n);
+  const bool on = z > 0.0;
+  return V3{on ? f.x : 0.0, on ? f.y : 0.0, on ? f.z : 0.0};
+}
+#ifndef GP_CONTACT_BRANCHLESS
+#define GP_CONTACT_BRANCHLESS 0
+#endif
+
 // ---- dynamics_continuous for one environment ------------------------------------------------
 // q[NQ], v[NV], tau[NV] (caller passes zeros for "no torque"); writes vdot[NV]; returns status.
 // CONTACT: 0 = no contact points / halfspaces, 1 = exactly one halfspace, 2 = up to kMaxHS.
@@ -487,7 +506,12 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
           for (int h = 0; h < NHS; ++h) {
             if (CONTACT == 1 || h < P.n_hs) {
               const double d = dot_add(-ho[i][h], hn[i][h], loc);
-              if (d <= 1e-8) {
+              if constexpr (GP_CONTACT_BRANCHLESS && !DUMP) {
+                const V3 vpt = cross_add(vi.l, vi.a, loc);
+                const V3 fc = contact_force_select(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
+                ka = cross_sub(ka, loc, fc);
+                kl -= fc;
+              } else if (d <= 1e-8) {
                 const V3 vpt = cross_add(vi.l, vi.a, loc);
                 const V3 fc = contact_force(-d, hn[i][h], vpt, P.cp_k[c], P.hs_alpha[h], P.hs_mu[h]);
                 ka = cross_sub(ka, loc, fc);

@@ -450,8 +450,11 @@ GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env,
 // instruction stream (navbot 8 K: +33 %, profiles/r2_tuning.md).
 // TAUSEQ: the kernel reads StepArgs::tau_seq (a torque vector per time step). The Runge-Kutta kernels always do;
 // the semi-implicit-Euler ones exist with and without (the launcher picks the one a launch needs).
+#ifndef GP_PAIRS_BLOCK
+#define GP_PAIRS_BLOCK 256  // threads per block of the warp-pair kernels (tuning: 384 = 168 registers, 12 warps per SM)
+#endif
 template <class Topo, int CONTACT, int INTEG, bool PAIRS = false, bool TAUSEQ = (INTEG != IntegSIE)>
-__global__ void __launch_bounds__(Topo::kBlockSize, (step_min_blocks<Topo, CONTACT>()))
+__global__ void __launch_bounds__((PAIRS ? GP_PAIRS_BLOCK : Topo::kBlockSize), (step_min_blocks<Topo, CONTACT>()))
 step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepArgs A) {
   static_assert(!PAIRS || (Topo::kHasSides && INTEG == IntegSIE && !TAUSEQ), "warp pairs: sided topologies, plain semi-implicit Euler");
   // contact points for the per-lane hit list of dynamics_core (lane-dependent index: shared memory)
@@ -643,7 +646,7 @@ cudaError_t launch_step(const KernelTable*, int contact, int integ_class, cudaSt
   if (integ_class != IntegSIE || A.tau_seq != nullptr) return launch_step_rk<Topo>(contact, integ_class, s, P, A);
   if constexpr (Topo::kHasSides) {
     if (use_pairs(A.n, Topo::kBlockSize)) {
-      auto go2 = [&](auto* kernel) { launch_step_kernel(kernel, Topo::kBlockSize, Topo::kTickets, s, P, A, 2); };
+      auto go2 = [&](auto* kernel) { launch_step_kernel(kernel, GP_PAIRS_BLOCK, Topo::kTickets, s, P, A, 2); };
       if (contact == 0) go2(&step_kernel<Topo, 0, IntegSIE, true>);
       else if (contact == 1) go2(&step_kernel<Topo, 1, IntegSIE, true>);
       else go2(&step_kernel<Topo, 2, IntegSIE, true>);

@@ -121,7 +121,8 @@ inline int step_block_for(long long n, int tuned, int lanes = 1) {
   if (forced) return std::atoi(forced);
   int b = tuned;
   // until 3/4 of the SMs have a block
-  while (!fixed && b > 32 * lanes && 4 * ((n + b / lanes - 1) / (b / lanes)) < 3 * n_sm) b /= 2;
+  while (!fixed && b > 32 * lanes && 4 * ((n + b / lanes - 1) / (b / lanes)) < 3 * n_sm)
+    b = (b == 384) ? 256 : b / 2;  // (384: a tuning size of the warp-pair kernels; blocks stay whole pairs of warps)
   return b;
 }
 // Which mapping a semi-implicit-Euler step launch of a topology with halves uses (gp_kernels.cuh step_kernel):

@@ -1068,3 +1068,33 @@ def test_config1_acrobot_swingup_30s():
     assert (err <= bound).all(), (float(err.max()), float(bound.min()))
     assert err[:41].max() < 1e-6
     assert abs(e_gpu[0]) < 1e-12 and abs(e_gpu[-1] - target) < abs(e_gpu[0] - target)
+
+
+@pytest.mark.parametrize("name", ["so101_contact", "navbot_contact", "quadruped"])
+def test_dynamics_parity_componentwise(name):
+    """north_star's 1e-10 is checked per environment against the largest component of vdot (rel_err above), under
+    which the small components ride on the largest one. Here every component is held against its OWN magnitude,
+    with a floor of 1 % of the environment's largest component (a component that happens to cross zero has no
+    relative error to speak of): 1e-8, i.e. each component keeps at least 6 more digits than the floor asks for.
+    Contact forces likewise. States: free fall and deep in contact (base dropped into the ground)."""
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 2048
+    worst = 0.0
+    for seed, extra in ((11, {}), (12, dict(q_range=2.5, v_range=3.0))):
+        q, v = random_states(desc, n, seed=seed, **{**kw, **extra})
+        st = MechanismState(mech, n)
+        st.update(q, v)
+        vdot, cf = st.dynamics(tau=None, contact_forces=True)
+        ref, cf_ref = orc.batch_dynamics(q, v)
+        for got, want in ((vdot, ref), (cf.reshape(n, -1), cf_ref.reshape(n, -1))):
+            if want.shape[1] == 0:
+                continue
+            scale = np.maximum(np.abs(want).max(axis=1, keepdims=True), 1e-9)
+            comp = np.abs(got - want) / np.maximum(np.abs(want), 1e-2 * scale)
+            worst = max(worst, float(comp.max()))
+            assert float((np.abs(got - want) / scale).max()) < TOL_DYN
+    print(f"{name}: worst componentwise relative error {worst:.2e}")
+    assert worst < 1e-8

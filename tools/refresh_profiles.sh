@@ -1,11 +1,13 @@
 #!/bin/bash
 # GPU box: one `ncu --set full` capture of the step kernel per bench workload, digested into
 # profiles/<round>_<workload>_step_kernel.json, plus the launch list of the default bench command and
-# profiles/flop_counts.json (what bench.py's roofline reads).   tools/refresh_profiles.sh r1
-R=${1:-r1}
+# profiles/flop_counts.json (what bench.py's roofline reads).   [W="workload ..."] tools/refresh_profiles.sh r2
+R=${1:-r2}
 mkdir -p gpurun_out profiles
-declare -A N=( [so101_contact]=262144 [so101]=262144 [double_pendulum]=1048576 [cart_pole]=1048576 [rimless_wheel]=262144 [hopper_1d]=262144 [quadruped]=65536 [navbot_contact]=65536 )
-for w in ${W:-so101_contact so101 double_pendulum cart_pole rimless_wheel hopper_1d quadruped navbot_contact}; do
+declare -A N
+ALL=$(python -c "from gorilla_physics_b200 import WORKLOADS; print(' '.join(WORKLOADS))")
+for w in $ALL; do N[$w]=$(python -c "from gorilla_physics_b200 import WORKLOADS; print(WORKLOADS['$w'].n_envs)"); done
+for w in ${W:-$ALL}; do
   tools/ncu_capture.sh $w ${N[$w]} $R > /dev/null 2>&1
   cp gpurun_out/${R}_$w.json gpurun_out/profile_${R}_${w}_step_kernel.json
   python tools/ncu_stall_map.py gpurun_out/${R}_$w.ncu-rep 300 > gpurun_out/profile_${R}_${w}_stall_map.txt 2>&1
@@ -14,7 +16,9 @@ for w in ${W:-so101_contact so101 double_pendulum cart_pole rimless_wheel hopper
   ncu --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum \
       --clock-control none -k regex:step_kernel --csv --log-file gpurun_out/${R}_${w}_flops.csv \
       python bench.py --workload $w --steps 40 --warmup 3 --no-cpu-baseline --sustain 0 > /dev/null 2>&1
-  python tools/ncu_flops_over_bench.py gpurun_out/${R}_${w}_flops.csv ${N[$w]} 128 > gpurun_out/profile_${R}_${w}_flops_over_bench.json
+  # (step-kernel launches before the timed ones: 3 warm-up launches, plus the settling rollout of the "resting" workloads)
+  SKIP=$(python -c "from gorilla_physics_b200 import WORKLOADS; print(3 + (1 if WORKLOADS['$w'].settle_steps else 0))")
+  python tools/ncu_flops_over_bench.py gpurun_out/${R}_${w}_flops.csv ${N[$w]} 128 40 $SKIP > gpurun_out/profile_${R}_${w}_flops_over_bench.json
   rm -f gpurun_out/${R}_${w}_flops.csv
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/profile_${R}_launches.csv \
