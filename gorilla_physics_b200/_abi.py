@@ -103,6 +103,8 @@ SYMBOLS = {
     "gp_batch_get_spring_contact_state": (C.c_int, [vp, vp]),
     "gp_batch_set_controller_state": (C.c_int, [vp, vp]),
     "gp_batch_get_controller_state": (C.c_int, [vp, vp]),
+    "gp_batch_set_controller_state_n": (C.c_int, [vp, vp, C.c_int]),
+    "gp_batch_get_controller_state_n": (C.c_int, [vp, vp, C.c_int]),
     "gp_batch_randomize": (C.c_int, [vp, C.c_uint64, C.POINTER(GpStateDist)]),
     "gp_batch_dynamics": (C.c_int, [vp, vp, vp]),
     "gp_batch_free_velocity": (C.c_int, [vp, C.c_double, C.c_int, vp]),

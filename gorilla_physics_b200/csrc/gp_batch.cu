@@ -25,7 +25,7 @@ struct gp_batch {
   double* tau = nullptr;     // [n_v][ld]
   bool tau_set = false;
   unsigned* status = nullptr;  // [ld]
-  double* ctrl_state = nullptr;  // [2][ld] controller state (GP_CTRL_HOPPER_1D), allocated on first use
+  double* ctrl_state = nullptr;  // [GP_CTRL_STATE_MAX][ld] controller state (GP_CTRL_HOPPER_1D: 2, GP_CTRL_QUADRUPED_TROT: 9), allocated on first use
   double* sc_state = nullptr;    // [n_sc*8][ld] spring-contact state (mechanisms with spring contacts)
   int n_sc = 0;                  // spring contacts sc_state was allocated for (refresh_batch)
   double* stage = nullptr;     // staging for AoS<->SoA and outputs
@@ -304,6 +304,15 @@ struct TauSeq {
   long long step, env, k;
 };
 
+int ensure_ctrl_state(gp_batch* b) {
+  if (b->ctrl_state) return GP_OK;
+  const size_t bytes = (size_t)GP_CTRL_STATE_MAX * b->ld * sizeof(double);
+  GP_CUDA(cudaMalloc((void**)&b->ctrl_state, bytes));
+  GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, bytes, b->stream));
+  GP_CUDA(cudaStreamSynchronize(b->stream));  // the first user may be a pipeline stream
+  return GP_OK;
+}
+
 int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int controller, const double* cp,
                  int n_cp, long long env0 = 0, long long n_sub = -1, cudaStream_t stream = nullptr,
                  double* q_aos = nullptr, double* v_aos = nullptr, double* hist_q = nullptr,
@@ -381,13 +390,21 @@ int launch_steps(gp_batch* b, double dt, int integrator, int n_steps, int contro
                   "[k_spring, h_setpoint, body_leg_length, leg_foot_length]");
         return GP_ERR_INVALID;
       }
-      if (!b->ctrl_state) {
-        GP_CUDA(cudaMalloc((void**)&b->ctrl_state, 2 * b->ld * sizeof(double)));
-        GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, 2 * b->ld * sizeof(double), b->stream));
-        GP_CUDA(cudaStreamSynchronize(b->stream));  // the first user may be a pipeline stream
-      }
+      if (const int rc2 = ensure_ctrl_state(b)) return rc2;
       A.ctrl_state = b->ctrl_state + env0;
       break;
+    case GP_CTRL_QUADRUPED_TROT: {
+      bool ok = m->table->is_static && td.nb == 9 && td.jtype[0] == JFloating && n_cp >= 3 && cp[0] > 0.0;
+      for (int i = 1; ok && i < 9; ++i) ok = td.jtype[i] == JRevolute && td.parent[i] == ((i & 1) ? 0 : i - 1);
+      if (!ok) {
+        set_error("GP_CTRL_QUADRUPED_TROT needs a floating base with four (hip, knee) revolute chains "
+                  "(build_quadruped) and [dt > 0, target_x, default_foot_z]");
+        return GP_ERR_INVALID;
+      }
+      if (const int rc2 = ensure_ctrl_state(b)) return rc2;
+      A.ctrl_state = b->ctrl_state + env0;
+      break;
+    }
     case GP_CTRL_PENDULUM_GRAVITY_INVERSION:
     case GP_CTRL_PENDULUM_ENERGY_SHAPING:
     case GP_CTRL_PENDULUM_SWINGUP_BALANCE:
@@ -669,33 +686,37 @@ int gp_batch_get_spring_contact_state(gp_batch* b, double* state_host) {
   return to_host_aos(b, b->sc_state, state_host, kSpringState * ns);
 }
 
-int gp_batch_set_controller_state(gp_batch* b, const double* state_host) {
+int gp_batch_set_controller_state_n(gp_batch* b, const double* state_host, int k) {
   int rc = check_batch(b, "gp_batch_set_controller_state");
   if (rc) return rc;
-  if (!b->ctrl_state) GP_CUDA(cudaMalloc((void**)&b->ctrl_state, 2 * b->ld * sizeof(double)));
-  if (!state_host) {
-    GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, 2 * b->ld * sizeof(double), b->stream));
-    GP_CUDA(cudaStreamSynchronize(b->stream));
-    return GP_OK;
+  if (k < 1 || k > GP_CTRL_STATE_MAX) {
+    set_error("gp_batch_set_controller_state: 1 <= k <= %d values per environment", GP_CTRL_STATE_MAX);
+    return GP_ERR_INVALID;
   }
-  if ((rc = to_device_soa(b, state_host, b->ctrl_state, 2))) return rc;
+  if ((rc = ensure_ctrl_state(b))) return rc;
+  // (values beyond k, and everything for NULL, return to zero: a fresh controller)
+  GP_CUDA(cudaMemsetAsync(b->ctrl_state, 0, (size_t)GP_CTRL_STATE_MAX * b->ld * sizeof(double), b->stream));
+  if (state_host && (rc = to_device_soa(b, state_host, b->ctrl_state, k))) return rc;
   GP_CUDA(cudaStreamSynchronize(b->stream));
   return GP_OK;
 }
 
-int gp_batch_get_controller_state(gp_batch* b, double* state_host) {
+int gp_batch_get_controller_state_n(gp_batch* b, double* state_host, int k) {
   int rc = check_batch(b, "gp_batch_get_controller_state");
   if (rc) return rc;
-  if (!state_host) {
-    set_error("gp_batch_get_controller_state: null output");
+  if (!state_host || k < 1 || k > GP_CTRL_STATE_MAX) {
+    set_error("gp_batch_get_controller_state: null output or k outside 1..%d", GP_CTRL_STATE_MAX);
     return GP_ERR_INVALID;
   }
   if (!b->ctrl_state) {
-    std::memset(state_host, 0, sizeof(double) * 2 * (size_t)b->n);
+    std::memset(state_host, 0, sizeof(double) * (size_t)k * (size_t)b->n);
     return GP_OK;
   }
-  return to_host_aos(b, b->ctrl_state, state_host, 2);
+  return to_host_aos(b, b->ctrl_state, state_host, k);
 }
+
+int gp_batch_set_controller_state(gp_batch* b, const double* state_host) { return gp_batch_set_controller_state_n(b, state_host, 2); }
+int gp_batch_get_controller_state(gp_batch* b, double* state_host) { return gp_batch_get_controller_state_n(b, state_host, 2); }
 
 int gp_batch_randomize(gp_batch* b, uint64_t seed, const gp_state_dist* dist) {
   int rc = check_batch(b, "gp_batch_randomize");

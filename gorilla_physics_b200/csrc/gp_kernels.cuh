@@ -135,9 +135,88 @@ GP_D void energy_core(const MechParams& P, const double* q, const double* v, dou
 }
 
 // ---- in-kernel controllers (reference closures Fn(&MechanismState) -> Vec<JointTorque>) -----
+// QuadrupedTrottingController, reference control/quadruped_control.rs:28-266, for one environment and one tick.
+// Its state (tick count, the four feet's targets) lives in the batch's controller-state planes and is read and
+// written there every tick (L2: a later chunk of a ticket-mode launch may run on another SM) - nine loop-carried
+// doubles in registers would cost the 14-dof kernels more than nine cached loads and stores per 3 600-instruction
+// step. cs[0] holds ticks + 1 as of the START of the launch (0: fresh controller); the tick of fused step s is
+// that + s, the launch's last work item writes the count back (step_item). A warp-pair half drives its own two legs.
+template <class Topo>
+GP_D void quadruped_trot_tau(const StepArgs& A, const double* q, const double* v, double* tau, long long env, int s) {
+#if defined(__CUDA_ARCH__)
+  double* cs = A.ctrl_state + env;
+  const double dtc = A.cp[0], target_x = A.cp[1], foot_z0 = A.cp[2];
+  const double stamp = __ldcg(cs);
+  const bool fresh = stamp == 0.0 && s == 0;
+  const long long ticks = (stamp > 0.0 ? (long long)stamp - 1 : 0) + s;
+  const long long overlap = (long long)(0.1 / dtc), swing = (long long)(0.15 / dtc);   // :218-226 (as usize)
+  const long long stance = 2 * overlap + swing, period = 2 * overlap + 2 * swing;      // :228-236
+  const long long phase_time = ticks % period;
+  // phases: all four feet down, (fl, br) down, all four, (fr, bl) down   (:76-81, :192-215)
+  int phase;
+  long long sub;
+  if (phase_time < overlap) { phase = 0; sub = phase_time; }
+  else if (phase_time < overlap + swing) { phase = 1; sub = phase_time - overlap; }
+  else if (phase_time < 2 * overlap + swing) { phase = 2; sub = phase_time - overlap - swing; }
+  else { phase = 3; sub = phase_time - 2 * overlap - swing; }
+  const double dx = q[4] - target_x;                                                   // :33-36
+  const double vx = -copysign(1.0, dx) * fmin(fabs(dx) * 10.0, 1.0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) tau[k] = 0.0;
+  static_for<0, 4>([&](auto ll) {
+    constexpr int leg = decltype(ll)::value;
+    if constexpr (Topo::mine_body(1 + 2 * leg)) {
+      double* fx = cs + (long long)(1 + 2 * leg) * A.ld;
+      double* fz = cs + (long long)(2 + 2 * leg) * A.ld;
+      const double x0 = fresh ? 0.0 : __ldcg(fx), z0 = fresh ? foot_z0 : __ldcg(fz);
+      const bool down = phase == 0 || phase == 2 || (phase == 1 ? (leg == 1 || leg == 2) : (leg == 0 || leg == 3));
+      double x, z;
+      if (down) {                                                                      // next_stance_foot_location :124-132
+        x = x0 + -vx * dtc;
+        z = z0 + 1.0 / 0.02 * (foot_z0 - z0) * dtc;
+      } else {                                                                         // next_swing_foot_location :135-160
+        const double swing_proportion = (double)sub / (double)swing;
+        const double height_proportion = (double)(sub + 1) / (double)swing;
+        const double swing_height = height_proportion < 0.5 ? 0.25 * height_proportion / 0.5
+                                                             : 0.25 * (1.0 - (height_proportion - 0.5) / 0.5);
+        const double delta_px = 0.5 * (double)stance * dtc * vx;                      // Raibert touchdown
+        const double time_left = dtc * (double)swing * (1.0 - swing_proportion);
+        x = x0 + ((0.0 + delta_px) - x0) / time_left * dtc;
+        z = swing_height + foot_z0;
+      }
+      __stcg(fx, x);
+      __stcg(fz, z);
+      // inverse_kinematics :163-189, l1 = l2 = l_leg / 2 = 0.5
+      const double l1 = 0.5, l2 = 0.5;
+      double c2 = (x * x + z * z - l1 * l1 - l2 * l2) / (2.0 * l1 * l2);
+      if (fabs(c2) <= 1.0 + 1e-15) c2 = fmin(fmax(c2, -1.0), 1.0);
+      const double theta2 = acos(c2);
+      double s2, cc2;
+      sincos(theta2, &s2, &cc2);
+      double theta1 = atan2(x, -z) - atan2(l2 * s2, l1 + l2 * cc2);
+      if (theta1 > 0.0) theta1 -= 3.14159265358979323846;
+      const int hq = 7 + 2 * leg, hv = 6 + 2 * leg;                                    // joint PD :52-68
+      tau[hv] = 150.0 * (theta1 - q[hq]) + 10.0 * -v[hv];
+      tau[hv + 1] = 150.0 * (theta2 - q[hq + 1]) + 10.0 * -v[hv + 1];
+    }
+  });
+#else
+  (void)A; (void)q; (void)v; (void)tau; (void)env; (void)s;
+#endif
+}
+
 template <class Topo>
 GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q, const double* v,
-                         const double* tau_in, double* tau, double* cstate) {
+                         const double* tau_in, double* tau, double* cstate, long long env, int s) {
+  if constexpr (Topo::kQuadrupedLike) {
+    if (A.controller == GP_CTRL_QUADRUPED_TROT) {
+#if defined(__CUDA_ARCH__)
+      asm volatile("");  // a real (uniform) branch
+#endif
+      quadruped_trot_tau<Topo>(A, q, v, tau, env, s);
+      return;
+    }
+  }
   constexpr int NV = Topo::NV;
   constexpr int U = Topo::kUnroll;
   if (A.controller == GP_CTRL_SO101_PD) {
@@ -328,7 +407,8 @@ GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env,
   });
   unsigned status = 0u;
   double cstate[2] = {0.0, 0.0};
-  if (A.ctrl_state) {
+  const bool two_value_state = A.ctrl_state && A.controller != GP_CTRL_QUADRUPED_TROT;  // (the trot controller keeps its own)
+  if (two_value_state) {
     cstate[0] = TK ? __ldcg(A.ctrl_state + env) : A.ctrl_state[env];
     cstate[1] = TK ? __ldcg(A.ctrl_state + A.ld + env) : A.ctrl_state[A.ld + env];
   }
@@ -358,7 +438,7 @@ GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env,
         for_v_entries<T>(P, [&](auto kk) { const int k = kk; tau[k] = ts[(long long)k * A.tau_seq_k]; });
       }
     }
-    controller_tau<T>(P, A, q, v, tau_in, tau, cstate);
+    controller_tau<T>(P, A, q, v, tau_in, tau, cstate, env, s);
     if (INTEG == IntegSIE) {
       // semi_implicit_euler, reference integrators.rs:25-39, :276-319
       status |= dynamics_core<T, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);
@@ -412,9 +492,14 @@ GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env,
   }
 
   if (active) {
-    if (A.ctrl_state && T::kSide <= 0) {
+    if (two_value_state && T::kSide <= 0) {
       A.ctrl_state[env] = cstate[0];
       A.ctrl_state[A.ld + env] = cstate[1];
+    }
+    if (A.ctrl_state && !two_value_state && last_chunk && T::kSide <= 0) {
+      // trot controller: ticks + 1 as of the end of this launch (no other work item of the launch reads it after this one)
+      const double stamp = __ldcg(A.ctrl_state + env);
+      __stcg(A.ctrl_state + env, (stamp > 0.0 ? stamp : 1.0) + (double)A.n_steps);
     }
     bool finite = true;
     for_q_entries<T>(P, [&](auto kk) {

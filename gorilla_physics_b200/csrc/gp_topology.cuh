@@ -222,6 +222,16 @@ struct StaticTopo {
   static constexpr unsigned kSideMask = Spec::side_mask();
   static constexpr bool kHasSides = kSideMask != 0u;  // the step kernel of this topology runs warp pairs
   static constexpr int kRootNV = joint_nv(tables().jtype[0]);
+  // floating base + four (hip, knee) revolute chains, the tree of build_quadruped (helpers.rs:423): the only one the
+  // in-kernel QuadrupedTrottingController is compiled into
+  static constexpr bool quadruped_like() {
+    const TopoTables t = tables();
+    if (t.nb != 9 || t.jtype[0] != JFloating || t.parent[0] != -1) return false;
+    for (int i = 1; i < 9; ++i)
+      if (t.jtype[i] != JRevolute || t.parent[i] != ((i & 1) ? 0 : i - 1)) return false;
+    return true;
+  }
+  static constexpr bool kQuadrupedLike = quadruped_like();
   using Whole = StaticTopo<Spec, -1>;
   template <int S> using Half = StaticTopo<Spec, S>;
   // body i is advanced by this thread / is stored by this thread (the root is computed by both halves and
@@ -312,6 +322,7 @@ struct DynTopo {
   static constexpr bool kSided = false;
   static constexpr bool kHasSides = false;
   static constexpr int kRootNV = 0;
+  static constexpr bool kQuadrupedLike = false;
   using Whole = DynTopo;
   GP_HD static constexpr bool mine_body(int) { return true; }
   GP_HD static constexpr bool owns_body(int) { return true; }

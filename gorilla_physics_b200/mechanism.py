@@ -46,6 +46,7 @@ class Controller(enum.IntEnum):
     PENDULUM_GRAVITY_INVERSION = 5   # reference control/mod.rs:57-67 (single revolute pendulum, no params)
     PENDULUM_ENERGY_SHAPING = 6      # reference control/mod.rs:78-96
     PENDULUM_SWINGUP_BALANCE = 7     # reference control/mod.rs:98-105
+    QUADRUPED_TROT = 8     # reference control/quadruped_control.rs:10-266 (stateful, 9 values), params [dt, target_x, default_foot_z]
 
 
 class KernelMode(enum.IntEnum):
@@ -355,14 +356,16 @@ class MechanismState:
         sa = None if state is None else np.ascontiguousarray(np.asarray(state, dtype=np.float64).reshape(self.n_envs, -1))
         check(lib().gp_batch_set_spring_contact_state(self._h, _ptr(sa)))
 
-    def set_controller_state(self, state=None):
-        """(leg_length_setpoint, v_vertical_prev) per environment of Controller.HOPPER_1D; None resets to 0."""
-        sa = None if state is None else self._rows(state, 2)
-        check(lib().gp_batch_set_controller_state(self._h, _ptr(sa)))
+    def set_controller_state(self, state=None, k: int = 2):
+        """per-environment controller state, k values each: Controller.HOPPER_1D (leg_length_setpoint,
+        v_vertical_prev), Controller.QUADRUPED_TROT k = 9 (ticks + 1, four feet's (x, z)); None resets to 0
+        (a fresh controller)."""
+        sa = None if state is None else self._rows(state, k)
+        check(lib().gp_batch_set_controller_state_n(self._h, _ptr(sa), int(k)))
 
-    def controller_state(self):
-        out = np.empty((self.n_envs, 2))
-        check(lib().gp_batch_get_controller_state(self._h, _ptr(out)))
+    def controller_state(self, k: int = 2):
+        out = np.empty((self.n_envs, k))
+        check(lib().gp_batch_get_controller_state_n(self._h, _ptr(out), int(k)))
         return out
 
     def randomize(self, seed: int, q_range=(-1.0, 1.0), v_range=(-1.0, 1.0), base_t=(0.0, 0.0, 0.0),

@@ -100,9 +100,17 @@ enum gp_controller {
      moment and joint axis are read from the mechanism like the reference reads state.bodies[0] */
   GP_CTRL_PENDULUM_GRAVITY_INVERSION = 5, /* u = 2 m g l_c sin q - 10 qd, control/mod.rs:57-67 */
   GP_CTRL_PENDULUM_ENERGY_SHAPING = 6,    /* u = -0.1 qd (KE + PE - m g l_c), control/mod.rs:78-96 */
-  GP_CTRL_PENDULUM_SWINGUP_BALANCE = 7    /* energy shaping while |q - pi| > 0.15, else gravity inversion,
+  GP_CTRL_PENDULUM_SWINGUP_BALANCE = 7,   /* energy shaping while |q - pi| > 0.15, else gravity inversion,
                                              control/mod.rs:98-105 */
+  GP_CTRL_QUADRUPED_TROT = 8   /* QuadrupedTrottingController, control/quadruped_control.rs:10-266: trot gait scheduler
+                                  (overlap 0.1 s, swing 0.15 s, clearance 0.25), Raibert touchdown, two-link inverse
+                                  kinematics (l_leg 1), joint PD (150, 10), forward speed from the distance to target_x;
+                                  floating base + 4 x (hip, knee) as built by build_quadruped (helpers.rs:423).
+                                  params: [dt of a controller tick, target_x, default_foot_z]. Stateful: nine f64 per
+                                  environment (GP_CTRL_STATE_MAX): [0] = ticks + 1 (0: a fresh controller, feet at the
+                                  default stance), then the four feet's target (x, z) */
 };
+#define GP_CTRL_STATE_MAX 9
 
 /* per-environment status bits (replace the reference's panics) */
 #define GP_ENV_NAN 1u         /* non-finite q, v or vdot */
@@ -329,6 +337,9 @@ int gp_batch_get_spring_contact_state(gp_batch* batch, double* state_host);
  * set: NULL resets every environment to (0, 0), the values examples/1D_hopper.rs starts from. */
 int gp_batch_set_controller_state(gp_batch* batch, const double* state_host);
 int gp_batch_get_controller_state(gp_batch* batch, double* state_host);
+/* the same with k values per environment, [n_envs][k], k <= GP_CTRL_STATE_MAX (GP_CTRL_QUADRUPED_TROT: 9) */
+int gp_batch_set_controller_state_n(gp_batch* batch, const double* state_host, int k);
+int gp_batch_get_controller_state_n(gp_batch* batch, double* state_host, int k);
 
 /* simulate(state, final_time, dt, control_fn, integrator) (simulate.rs:87-112) through
  * host buffers in one call: H2D of q/v (and tau when non-NULL), the rollout, D2H of the

@@ -1098,3 +1098,60 @@ def test_dynamics_parity_componentwise(name):
             assert float((np.abs(got - want) / scale).max()) < TOL_DYN
     print(f"{name}: worst componentwise relative error {worst:.2e}")
     assert worst < 1e-8
+
+
+def test_quadruped_trot_controller_in_kernel():
+    """QuadrupedTrottingController (reference control/quadruped_control.rs:10-266) evaluated inside the step kernel
+    (Controller.QUADRUPED_TROT, nine values of per-environment state in the batch): the reference's only test of the
+    14-dof + 12-contact-point model, quadruped_trot_to_position (:417-478), as fused launches instead of a launch and
+    two copies per time step. Against the host-closure path (tests/controllers_ref.py computing the torques on the
+    host, one step per launch) over the first 600 steps, in one environment per target (warp-pair mapping) and in a
+    batch that fills the GPU (thread per environment), state carried across launches; then the reference's
+    acceptance after 3 s: |x - target| < 0.1, |v_x| < 0.3."""
+    from tests.controllers_ref import QuadrupedTrottingController, quadruped_initial_state
+    mech = models.quadruped_on_ground()
+    dt = 1.0 / (60.0 * 50.0)
+    targets = [-0.2, -0.6, -1.5, -1.8]
+    q0, v0 = quadruped_initial_state()
+    # host closure, 600 steps, target -0.2
+    host = MechanismState(mech, 1)
+    host.update(q0[None], v0[None])
+    ctrl = QuadrupedTrottingController(dt, targets[0], -0.8)
+    q, v = host.state()
+    trace = {}
+    for step in range(600):
+        host.step(dt, tau=ctrl.control(q[0], v[0])[None])
+        q, v = host.state()
+        if step + 1 in (1, 10, 100, 250, 600):
+            trace[step + 1] = (q[0].copy(), v[0].copy(), [f.copy() for f in ctrl.foot_locations])
+    for n_copies in (1, 40000):   # 1: warp pairs (small batch); 40 000: thread per environment, ticket mode
+        st = MechanismState(mech, n_copies)
+        assert st.step_lanes == (2 if n_copies == 1 else 1)
+        st.update(np.tile(q0, (n_copies, 1)), np.tile(v0, (n_copies, 1)))
+        done = 0
+        for upto in (1, 10, 100, 250, 600):   # uneven launches: the controller state carries over
+            st.step(dt, n_steps=upto - done, controller=Controller.QUADRUPED_TROT, ctrl_params=(dt, targets[0], -0.8))
+            done = upto
+            qg, vg = st.state()
+            qh, vh, feet = trace[upto]
+            assert np.abs(qg[0] - qh).max() < 1e-9 * upto and np.abs(vg[0] - vh).max() < 1e-8 * upto, (n_copies, upto)
+            assert np.array_equal(qg[0], qg[-1])
+            cs = st.controller_state(9)
+            assert cs[0, 0] == upto + 1 and np.array_equal(cs[0], cs[-1])
+            got = cs[0, 1:].reshape(4, 2)
+            np.testing.assert_allclose(got, np.array([[f[0], f[2]] for f in feet]), rtol=0, atol=1e-12)
+        assert not st.status().any()
+    # the reference's acceptance for several targets (the target is a launch parameter), 9000 steps in 9 launches
+    for target in targets:
+        one = MechanismState(mech, 1)
+        one.update(q0[None], v0[None])
+        for _ in range(9):
+            one.step(dt, n_steps=1000, controller=Controller.QUADRUPED_TROT, ctrl_params=(dt, target, -0.8))
+        qf, vf = one.state()
+        assert not one.status().any()
+        assert abs(qf[0, 4] - target) < 1e-1, (target, qf[0, 4])
+        x, y, z, w = qf[0, 0:4]
+        Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                       [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                       [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        assert abs((Rq.T @ vf[0, 3:6])[0]) < 3e-1

@@ -24,6 +24,8 @@ run 8 --workload so101_contact --steps 20 --warmup 3
 python - <<PY
 import json
 for l in open("$OUT"):
+    if not l.startswith("{"):
+        continue  # (NCCL prints its version on stdout)
     d = json.loads(l)
     print(d["config"]["workload"], d["scaling"], "N=%d" % d["n_gpus"], "envs/GPU", d["config"]["n_envs_per_gpu"], "%.4g" % d["value"],
           "e2e %.4g" % d["e2e"]["value"], "ms/launch %.3f" % d["ms_per_step"], d["config"]["kernel"])
