@@ -142,7 +142,7 @@ GP_D void energy_core(const MechParams& P, const double* q, const double* v, dou
 // step. cs[0] holds ticks + 1 as of the START of the launch (0: fresh controller); the tick of fused step s is
 // that + s, the launch's last work item writes the count back (step_item). A warp-pair half drives its own two legs.
 template <class Topo>
-GP_D void quadruped_trot_tau(const StepArgs& A, const double* q, const double* v, double* tau, long long env, int s) {
+GP_D void quadruped_trot_tau(const StepArgs& A, const double* q, const double* v, double* tau, long long env, int s, bool active) {
 #if defined(__CUDA_ARCH__)
   double* cs = A.ctrl_state + env;
   const double dtc = A.cp[0], target_x = A.cp[1], foot_z0 = A.cp[2];
@@ -184,8 +184,10 @@ GP_D void quadruped_trot_tau(const StepArgs& A, const double* q, const double* v
         x = x0 + ((0.0 + delta_px) - x0) / time_left * dtc;
         z = swing_height + foot_z0;
       }
-      __stcg(fx, x);
-      __stcg(fz, z);
+      if (active) {  // (threads past the end of the batch re-run the last environment: they must not advance its feet again)
+        __stcg(fx, x);
+        __stcg(fz, z);
+      }
       // inverse_kinematics :163-189, l1 = l2 = l_leg / 2 = 0.5
       const double l1 = 0.5, l2 = 0.5;
       double c2 = (x * x + z * z - l1 * l1 - l2 * l2) / (2.0 * l1 * l2);
@@ -201,19 +203,19 @@ GP_D void quadruped_trot_tau(const StepArgs& A, const double* q, const double* v
     }
   });
 #else
-  (void)A; (void)q; (void)v; (void)tau; (void)env; (void)s;
+  (void)A; (void)q; (void)v; (void)tau; (void)env; (void)s; (void)active;
 #endif
 }
 
 template <class Topo>
 GP_D void controller_tau(const MechParams& P, const StepArgs& A, const double* q, const double* v,
-                         const double* tau_in, double* tau, double* cstate, long long env, int s) {
+                         const double* tau_in, double* tau, double* cstate, long long env, int s, bool active) {
   if constexpr (Topo::kQuadrupedLike) {
     if (A.controller == GP_CTRL_QUADRUPED_TROT) {
 #if defined(__CUDA_ARCH__)
       asm volatile("");  // a real (uniform) branch
 #endif
-      quadruped_trot_tau<Topo>(A, q, v, tau, env, s);
+      quadruped_trot_tau<Topo>(A, q, v, tau, env, s, active);
       return;
     }
   }
@@ -438,7 +440,7 @@ GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env,
         for_v_entries<T>(P, [&](auto kk) { const int k = kk; tau[k] = ts[(long long)k * A.tau_seq_k]; });
       }
     }
-    controller_tau<T>(P, A, q, v, tau_in, tau, cstate, env, s);
+    controller_tau<T>(P, A, q, v, tau_in, tau, cstate, env, s, active);
     if (INTEG == IntegSIE) {
       // semi_implicit_euler, reference integrators.rs:25-39, :276-319
       status |= dynamics_core<T, CONTACT, false, (GP_STEP_SYNC > 1 ? GP_STEP_SYNC - 1 : 0)>(P, q, v, tau, vdot, none);

@@ -1003,7 +1003,12 @@ def test_torque_sequence_is_the_per_step_control_closure(name, dt, steps):
     b.set_tau(np.full((n, desc.n_v), 123.0))  # must be ignored by the sequence and left alone
     b.step_tau_sequence(dt, tau_seq)
     qb, vb = b.state()
-    assert np.array_equal(qa, qb) and np.array_equal(va, vb)
+    if a.step_lanes == 2:
+        # (a small batch of a tree with halves steps as warp pairs, the torque-sequence kernels keep a thread per
+        # environment: the same numbers to rounding)
+        assert rel_err(qb, qa) < 1e-11 and rel_err(vb, va, floor=1e-3) < 1e-9
+    else:
+        assert np.array_equal(qa, qb) and np.array_equal(va, vb)
     # (2) oracle
     qo, vo = q.copy(), v.copy()
     for s in range(steps):
@@ -1018,8 +1023,9 @@ def test_torque_sequence_is_the_per_step_control_closure(name, dt, steps):
     torch.cuda.synchronize()
     c.step_tau_sequence_device(dt, dev.data_ptr(), steps)
     qc, vc = c.state()
-    assert np.array_equal(qa, qc) and np.array_equal(va, vc)
+    assert np.array_equal(qb, qc) and np.array_equal(vb, vc)
     # the batch's own torques were not touched: one more plain step uses them
+    a.update(qb, vb)
     b.step(dt, n_steps=1)
     a.step(dt, tau=np.full((n, desc.n_v), 123.0), n_steps=1)
     assert np.array_equal(a.q, b.q)
