@@ -470,7 +470,15 @@ JitPolicy jit_policy_for(const gp_mechanism* m, const TopoData& td) {
   // what the shipped specs converged to (gp_topology.cuh, profiles/r1_tuning.md)
   JitPolicy p;
   p.block_size = td.nb <= 3 ? 128 : 256;
-  p.min_blocks = 1;
+  // a double pendulum (with or without a fixed body) needs few registers: asking for six
+  // 128-thread blocks per SM is what the shipped double-pendulum spec runs with (gp_topology.cuh: +3.6 %, and 1.4x
+  // against the one-block default on its run-time-compiled twin, profiles/r2_static_generic_jit.jsonl)
+  int dofs = 0, revolute = 0;
+  for (int i = 0; i < td.nb; ++i) {
+    dofs += joint_nv(td.jtype[i]);
+    revolute += td.jtype[i] == JRevolute;
+  }
+  p.min_blocks = (td.nb <= 3 && dofs == 2 && revolute == 2 && m->n_sc() == 0) ? 6 : 1;
   p.tickets = td.nb > 3;
   p.springs = m->n_sc() > 0;
   // the per-lane hit list pays on bodies with many points, of which a few touch at a time (wheels, spokes, corners)
