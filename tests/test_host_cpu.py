@@ -363,3 +363,45 @@ def test_integration_md_binds_every_declared_symbol():
     assert "unimplemented!" not in text
     names = set(re.findall(r"pub fn (gp_[a-z0-9_]+)\(", text))
     assert names == set(_abi.SYMBOLS)
+
+
+def test_round2_entry_points_fail_loudly_without_a_gpu():
+    """the entry points added in round 2 keep the library's contract: argument errors are GP_ERR_INVALID, anything
+    that would compute returns GP_ERR_NO_DEVICE on a machine without a GPU - never a CPU substitute"""
+    lib = _abi.lib()
+    if lib.gp_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    mech = gp.Mechanism.from_model("navbot")
+    h = C.c_void_p()
+    ids = (C.c_int * 2)(0, 1)
+    assert lib.gp_sharded_create(mech._h, 100, ids, 2, C.byref(h)) == _abi.GP_ERR_NO_DEVICE
+    assert lib.gp_sharded_create(mech._h, 1, ids, 2, C.byref(h)) == _abi.GP_ERR_INVALID      # fewer environments than devices
+    assert lib.gp_sharded_create(None, 100, ids, 2, C.byref(h)) == _abi.GP_ERR_INVALID
+    assert lib.gp_sharded_n_shards(None) == 0 and lib.gp_sharded_n_envs(None) == 0
+    assert lib.gp_sharded_step(None, 1e-3, 0, 1, 0, None, 0) == _abi.GP_ERR_INVALID
+    ident = C.create_string_buffer(128)
+    assert lib.gp_comm_create(0, 2, ident, 0, C.byref(h)) == _abi.GP_ERR_NO_DEVICE
+    assert lib.gp_comm_create(3, 2, ident, 0, C.byref(h)) == _abi.GP_ERR_INVALID
+    out = (C.c_double * 4)()
+    assert lib.gp_batch_reduce_diagnostics(None, None, out) == _abi.GP_ERR_INVALID
+    assert lib.gp_batch_step_lanes(None) == 0
+    assert lib.gp_batch_step_tau_sequence(None, 1e-3, 0, 4, out) == _abi.GP_ERR_INVALID
+    n = C.c_int()
+    assert lib.gp_measure_fp64_peak_trace(0, 0.1, None, None, 0, C.byref(n)) == _abi.GP_ERR_NO_DEVICE and n.value == 0
+    with pytest.raises(GorillaError) as e:
+        gp.ShardedMechanismState(mech, 64, devices=[0, 1])
+    assert e.value.code == _abi.GP_ERR_NO_DEVICE
+
+
+def test_unlisted_trees_are_routed_to_run_time_compiled_kernels():
+    """a tree no shipped specialisation matches gets a kernel table of its own (compiled on first launch, nothing
+    here), unless the mechanism asks for the run-time-topology kernel"""
+    if not gp.jit_available():
+        pytest.skip("NVRTC not loadable")
+    from tests.test_parity_gpu import generic_twin
+    from gorilla_physics_b200 import KernelMode
+    nav = generic_twin(gp.WORKLOADS["navbot_contact"].mechanism(), KernelMode.JIT)
+    arm = generic_twin(gp.WORKLOADS["so101_contact"].mechanism(), KernelMode.AUTO)
+    assert nav.kernel_variant == "jit:FRRRRRRRRX" and arm.kernel_variant == "jit:XRRRRRRX"
+    assert generic_twin(gp.WORKLOADS["so101_contact"].mechanism(), KernelMode.GENERIC).kernel_variant == "generic"
+    assert gp.WORKLOADS["so101_contact"].mechanism().set_kernel_mode(KernelMode.JIT).kernel_variant == "jit:XRRRRRR"
