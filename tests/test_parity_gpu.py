@@ -1161,3 +1161,50 @@ def test_quadruped_trot_controller_in_kernel():
                        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
                        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
         assert abs((Rq.T @ vf[0, 3:6])[0]) < 3e-1
+
+
+@pytest.mark.parametrize("name", ["navbot_contact", "quadruped"])
+def test_warp_pair_mapping_through_every_entry_point(name):
+    """Small batches of the trees with halves run as warp pairs. Everything the step kernel does besides stepping
+    must work from both halves: host-buffer simulate() (environment-major staging copies in and out), recorded
+    history, per-environment torques, a ragged last block - bitwise equal to resident
+    stepping in the same mapping, and within parity of the oracle (thread-per-environment results: to rounding)."""
+    factory, kw, _ = WORKLOADS[name]
+    mech = factory()
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n, steps, dt = 333, 24, 1.0 / 6000.0
+    q, v = random_states(desc, n, seed=41, **kw)
+    tau = np.random.default_rng(41).uniform(-0.02, 0.02, size=(n, desc.n_v))
+    a = MechanismState(mech, n)
+    assert a.step_lanes == 2
+    a.update(q, v)
+    a.step(dt, tau=tau, n_steps=steps)
+    qa, va = a.state()
+    assert_rollout_parity(orc, q, v, qa, va, dt, steps, tau=tau)
+    # one step at a time == fused
+    b = MechanismState(mech, n)
+    b.update(q, v)
+    for _ in range(steps):
+        b.step(dt, tau=tau, n_steps=1)
+    assert np.array_equal(b.q, qa) and np.array_equal(b.v, va)
+    # simulate() through host buffers, with history
+    c = MechanismState(mech, n)
+    nst, hq, hv = c.simulate((steps - 0.5) * dt, dt, q.copy(), v.copy(), tau=tau, history=True)
+    assert nst == steps and np.array_equal(hq[0], q) and np.array_equal(hq[-1], qa) and np.array_equal(hv[-1], va)
+    b.update(q, v)
+    b.step(dt, tau=tau, n_steps=7)
+    assert np.array_equal(hq[7], b.q) and np.array_equal(hv[7], b.v)
+    nst, q_out, v_out = c.simulate((steps - 0.5) * dt, dt, q.copy(), v.copy(), tau=tau)
+    assert np.array_equal(q_out, qa) and np.array_equal(v_out, va)
+    # against the thread-per-environment mapping (a batch too large for pairs holding the same states)
+    big_n = 20000
+    reps = -(-big_n // n)
+    big = MechanismState(mech, big_n)
+    assert big.step_lanes == 1
+    big.update(np.tile(q, (reps, 1))[:big_n], np.tile(v, (reps, 1))[:big_n])
+    big.step(dt, tau=np.tile(tau, (reps, 1))[:big_n], n_steps=steps)
+    qb, vb = big.state()
+    ok = np.isfinite(qa).all(axis=1) & np.isfinite(qb[:n]).all(axis=1)
+    eq = rollout_errors(qb[:n][ok], qa[ok])
+    assert ok.mean() > 0.97 and np.median(eq) < 1e-12 and np.quantile(eq, 0.9) < 1e-9
