@@ -120,9 +120,17 @@ inline int step_block_for(long long n, int tuned, int lanes = 1) {
   static const char* forced = std::getenv("GP_STEP_BLOCK");                  // tuning only
   if (forced) return std::atoi(forced);
   int b = tuned;
-  // until 3/4 of the SMs have a block
-  while (!fixed && b > 32 * lanes && 4 * ((n + b / lanes - 1) / (b / lanes)) < 3 * n_sm)
+  // Thread per environment: until 3/4 of the SMs have a block (two warps on many SMs beat eight on a few).
+  // Warp pairs: only until 2/5 of them have one. A block of pairs runs two instruction streams (one per half of the
+  // tree), each fetched for half of its warps only, and the small batches that run pairs are bound by instruction
+  // fetch (43 % of the stall samples at 8 K environments, profiles/r2_pairs8k_*_stall_map.txt): four warps per
+  // stream on 64 SMs beat two per stream on 128 (navbot 8 K: 1.29e9 against 1.11e9; 4 K: 7.9e8 against 5.5e8 for
+  // one pair per block, profiles/r2_ab/n_pairs_block.txt).
+  while (!fixed && b > 32 * lanes) {
+    const long long blocks = (n + b / lanes - 1) / (b / lanes);
+    if (lanes == 1 ? 4 * blocks >= 3 * n_sm : 5 * blocks >= 2 * n_sm) break;
     b = (b == 384) ? 256 : b / 2;  // (384: a tuning size of the warp-pair kernels; blocks stay whole pairs of warps)
+  }
   return b;
 }
 // Which mapping a semi-implicit-Euler step launch of a topology with halves uses (gp_kernels.cuh step_kernel):
