@@ -606,6 +606,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(w, n_envs, inner, world, {
                 "envs_all_ranks": envs_all_ranks, "kernel": mech.kernel_variant,
+                "mapping": "warp pairs (two warps per 32 environments, half the tree each)" if st.step_lanes == 2 else "thread per environment",
                 "parallelism": f"env-sharded x{world}, no collective on the step path",
                 "l2": "192 MB flush written before every timed launch (outside the event pair)",
                 "contact_active": {"start": contact_start, "end": contact_end},
