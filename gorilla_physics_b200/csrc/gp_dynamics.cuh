@@ -48,6 +48,19 @@ struct DynOut {
 // root block of H (<= 21) + the root's part of the right-hand side (<= 6)
 constexpr int kXchSlotsA = 16, kXchSlotsB = 27, kXchSlots = kXchSlotsA + kXchSlotsB;
 
+// The named barriers of the warp-pair kernels. The two halves of a pair are different instantiations of the same
+// templates, so a barrier written inline would be reached from two program locations: legal for bar.sync with a
+// thread count (every warp arrives as a whole), but compute-sanitizer's synccheck reports "divergent threads in
+// block" for it (tools/probes/synccheck_probe.cu, variant A). Out of line there is ONE bar.sync per kernel that both
+// halves call (ptxas: MOV return address + CALL.REL.NOINC, no stack) and synccheck is clean (variant B).
+#if defined(__CUDACC__) && !defined(GP_HOST_DEBUG)
+static __device__ __noinline__ void gp_named_barrier(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+#else
+GP_D void gp_named_barrier(int, int) {}
+#endif
+
 // vals += the other half's vals, elementwise (IEEE addition commutes, so both halves end up with the same bits).
 // Each slot range is written once per time step; the other range's barrier sits between two uses of a range.
 template <int SIDE, int N>
@@ -58,7 +71,7 @@ GP_D void pair_exchange_sum(const DynOut& out, int slot0, double (&vals)[N]) {
   const double* theirs = out.xch + (((SIDE ^ 1) * kXchSlots + slot0) * 32 + lane);
 #pragma unroll
   for (int k = 0; k < N; ++k) mine[k * 32] = vals[k];
-  asm volatile("bar.sync %0, 64;" ::"r"(out.bar_id) : "memory");
+  gp_named_barrier(out.bar_id, 64);
 #pragma unroll
   for (int k = 0; k < N; ++k) vals[k] += theirs[k * 32];
 #else

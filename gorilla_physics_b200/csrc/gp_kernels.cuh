@@ -426,7 +426,18 @@ GP_D void step_item(const MechParams& P, const StepArgs& A, const long long env,
       // (large unrolled bodies only: for the 2-3 body kernels the barrier costs more than it saves)
       // keep the block's warps on the same stretch of the (large, fully unrolled) step body: they
       // then share instruction-cache lines instead of each streaming the whole body from L2
-      if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) __syncthreads();
+      if (GP_STEP_SYNC_EVERY == 1 || (s & (GP_STEP_SYNC_EVERY - 1)) == 0) {
+        if constexpr (T::kSided) {
+          // warp pairs: the two halves are different instantiations of this function, so a block-wide
+          // __syncthreads() would be reached from two program locations (compute-sanitizer's synccheck
+          // rejects that). The warps of one half share their code, not the other half's: a named barrier
+          // per half (ids 14 / 15; the pairs' exchange barriers use 1 ... blockDim.x / 64), through the
+          // kernel's one out-of-line bar.sync (gp_dynamics.cuh).
+          gp_named_barrier(14 + T::kSide, (int)(blockDim.x >> 1));
+        } else {
+          __syncthreads();
+        }
+      }
     }
     // a torque vector per time step (gp_batch_step_tau_sequence): its own instantiation of the semi-implicit-Euler
     // kernels - carried as a run-time branch by the plain rollout it cost the navbot kernel 5.5 % (spills), the
