@@ -580,12 +580,56 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
   // (compiled in only for the topologies that gain from it, Topo::kTickets: the others keep exactly the
   // plain kernel - the restructured loop cost the SO-101 contact kernel 5 % in instruction scheduling)
   constexpr bool TK = Topo::kTickets;
+  // Kernels whose blocks never meet at a barrier inside the steps (blocks below 256 threads, no warp pairs:
+  // ticket_warp_items, gp_launch.h) draw their tickets per WARP: a work item is 32 environments x a step chunk and
+  // nothing makes a warp wait for the slowest warp of its block between items (rimless wheel, 256 K environments:
+  // the block barriers of the item hand-over were 13 % of the stall samples, profiles/r2_rimless_wheel_stall_map.txt).
+  constexpr bool WARP_ITEMS = TK && !PAIRS && ticket_warp_items(Topo::kBlockSize, 1);
+  if constexpr (WARP_ITEMS) {
+    if (A.tickets) {
+      const unsigned lane = threadIdx.x & 31u;
+      for (;;) {
+        unsigned t = 0u;
+        if (lane == 0u) t = atomicAdd(A.tickets, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned)A.ticket_total) return;
+        const int chunk_index = (int)(t / (unsigned)A.ticket_groups);
+        const long long group = (long long)(t - (unsigned)chunk_index * (unsigned)A.ticket_groups);
+        if (chunk_index > 0) {
+          if (lane == 0u) {
+            const unsigned* done = A.tickets + 1 + group;
+            unsigned seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");
+              if (seen < (unsigned)chunk_index) __nanosleep(200);
+            } while (seen < (unsigned)chunk_index);
+            __threadfence();
+          }
+          __syncwarp();  // the predecessor's state is visible to every lane
+        }
+        const int step_begin = chunk_index * A.ticket_chunk;
+        const int step_end = min(step_begin + A.ticket_chunk, A.n_steps);
+        const long long env_raw = group * 32 + lane;
+        const bool active = env_raw < A.n;
+        step_item<typename Topo::Whole, CONTACT, INTEG, TK, TAUSEQ>(P, A, active ? env_raw : A.n - 1, active, step_begin, step_end,
+                                                                   chunk_index == 0, step_end == A.n_steps, s_cp, nullptr, 0);
+        // publish: every lane's stores, then the chunk count of these 32 environments
+        __threadfence();
+        __syncwarp();
+        if (lane == 0u) {
+          const unsigned done = (unsigned)chunk_index + 1u;
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.tickets + 1 + group), "r"(done) : "memory");
+        }
+      }
+    }
+  }
+  constexpr bool BLOCK_ITEMS = TK && !WARP_ITEMS;
   __shared__ unsigned s_ticket;
   long long group = blockIdx.x;
   int step_begin = 0, step_end = A.n_steps, chunk_index = 0;
   bool first_chunk = true, last_chunk = true;
   for (;;) {
-    if (TK && A.tickets) {
+    if (BLOCK_ITEMS && A.tickets) {
       if (threadIdx.x == 0) s_ticket = atomicAdd(A.tickets, 1u);
       __syncthreads();
       const unsigned t = s_ticket;
@@ -629,7 +673,7 @@ step_kernel(const __grid_constant__ MechParams P, const __grid_constant__ StepAr
       step_item<typename Topo::Whole, CONTACT, INTEG, TK, TAUSEQ>(P, A, env, active, step_begin, step_end, first_chunk, last_chunk,
                                                          s_cp, nullptr, 0);
     }
-    if (!TK || !A.tickets) return;
+    if (!BLOCK_ITEMS || !A.tickets) return;
     // publish: every thread's stores, then the chunk count of this environment block
     __threadfence();
     __syncthreads();

@@ -92,6 +92,15 @@ struct EnergyArgs {
   long long n, ld;
 };
 
+// Work items of a ticket-mode launch (step_kernel, gp_kernels.cuh): one warp's 32 environments where the kernel's
+// blocks never meet at a barrier inside the steps (tuned block below 256 threads - the bigger kernels keep their
+// warps in lockstep with a block barrier every few steps -, a thread per environment), a block of environments
+// otherwise. One rule for the kernel (compile time) and its launcher.
+#ifndef GP_TICKET_WARPS
+#define GP_TICKET_WARPS 1  // 0: tuning builds with block items everywhere
+#endif
+constexpr bool ticket_warp_items(int tuned_block, int lanes) { return GP_TICKET_WARPS && tuned_block < 256 && lanes == 1; }
+
 #if !defined(__CUDACC_RTC__)  // host side: not part of a run-time compilation (gp_jit.cpp)
 // ---- launch planning (host) ---------------------------------------------------------------------
 inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
@@ -163,7 +172,9 @@ inline StepLaunchPlan plan_step_launch(const void* kernel, int tuned_block, bool
   long long grid = groups;
   A.tickets = nullptr;
   static const bool off = std::getenv("GP_NO_TICKETS") != nullptr;  // tuning only
-  if (!off && tickets_compiled_in && A.ticket_buf && A.n_steps >= 8 && groups + 1 <= A.ticket_capacity) {
+  // (ticket groups: what a work item advances - the environments of one warp, or of one block)
+  const long long tgroups = ticket_warp_items(tuned_block, lanes) ? grid_for(A.n, 32) : groups;
+  if (!off && tickets_compiled_in && A.ticket_buf && A.n_steps >= 8 && tgroups + 1 <= A.ticket_capacity) {
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
     const long long slots = (long long)occ * sm_count();
@@ -172,12 +183,12 @@ inline StepLaunchPlan plan_step_launch(const void* kernel, int tuned_block, bool
       int chunk = (A.n_steps + 3) / 4;
       chunk = (chunk + 3) / 4 * 4;  // a multiple of the kernel's barrier cadence
       const int chunks = (A.n_steps + chunk - 1) / chunk;
-      if (chunks >= 2 && groups * chunks < 0x7fffffffLL &&
-          cudaMemsetAsync(A.ticket_buf, 0, (size_t)(1 + groups) * sizeof(unsigned), s) == cudaSuccess) {
+      if (chunks >= 2 && tgroups * chunks < 0x7fffffffLL &&
+          cudaMemsetAsync(A.ticket_buf, 0, (size_t)(1 + tgroups) * sizeof(unsigned), s) == cudaSuccess) {
         A.tickets = A.ticket_buf;
-        A.ticket_groups = (int)groups;
+        A.ticket_groups = (int)tgroups;
         A.ticket_chunk = chunk;
-        A.ticket_total = (int)(groups * chunks);
+        A.ticket_total = (int)(tgroups * chunks);
         grid = groups < slots ? groups : slots;
       }
     }
