@@ -791,6 +791,7 @@ def test_dynamics_against_independent_featherstone_derivation(name):
     ("navbot_contact", 32, 2048, 37, 1.0 / 6000.0),     # 65536 envs: 256 blocks on 148 one-block SMs -> ticket mode
     ("rimless_wheel", 64, 4096, 40, 1.0 / 600.0),       # 262144 envs, 2048 blocks on 592 slots -> ticket mode
     ("quadruped", 33, 2000, 16, 1.0 / 3000.0),          # ragged: 66000 envs, last block partly filled
+    ("so101_contact:generic", 33, 2000, 16, 1.0 / 6000.0),  # run-time-topology kernel: per-warp work items, ragged (66000 envs)
 ])
 def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
     """Batches whose blocks do not fill whole waves run in ticket mode (gp_kernels.cuh: the fused steps are
@@ -799,8 +800,9 @@ def test_ticket_mode_replication_property(name, n_copies, base_n, steps, dt):
     gives: copies of the same states are bitwise equal wherever they sit in the batch, equal to a small
     batch (one wave, plain mode) of the same states bit for bit (to rounding where the small batch runs the
     warp-pair mapping), and within parity of the oracle."""
+    name, _, flavour = name.partition(":")
     factory, kw, _ = WORKLOADS[name]
-    mech = factory()
+    mech = kernel_flavour(factory(), flavour or "static")
     desc = mech.desc()
     q0, v0 = random_states(desc, base_n, seed=5, **kw)
     small = MechanismState(mech, 256)
