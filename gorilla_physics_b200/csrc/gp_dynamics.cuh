@@ -170,8 +170,16 @@ GP_D void sincos_finish(int quad, double ks, double kc, double& sn, double& cs) 
     ks = kc;
     kc = t;
   }
+#if defined(__CUDA_ARCH__)
+  // the sign flips as integer operations on the high word: written as `-ks` each one is a DADD on the FP64 pipe
+  // (a negation that feeds a select cannot be folded into an operand modifier), twelve per step of a six-joint arm
+  const unsigned qs = (unsigned)quad;
+  sn = __hiloint2double(__double2hiint(ks) ^ (int)((qs & 2u) << 30), __double2loint(ks));
+  cs = __hiloint2double(__double2hiint(kc) ^ (int)(((qs + 1u) & 2u) << 30), __double2loint(kc));
+#else
   sn = (quad & 2) ? -ks : ks;
   cs = ((quad + 1) & 2) ? -kc : kc;
+#endif
 }
 GP_HD constexpr double sin_coef(int k) {
   return k == 0 ? -1.66666666666666324348e-01
