@@ -123,11 +123,34 @@ GP_D V3 cross_axis(const MechParams& P, int i, V3 v, double s) {
   if (Topo::axis_kind(P, i) == AxZ) return V3{v.y * s, -(v.x * s), 0.0};
   return cross(v, V3{P.axis[i][0] * s, P.axis[i][1] * s, P.axis[i][2] * s});
 }
+// acc + v x (axis * s). (+z: the z component is untouched - written as `acc += cross_axis(...)` it was `acc.z + 0.0`,
+// an FP64 instruction the compiler must keep: IEEE -0 + 0 is +0)
+template <class Topo>
+GP_D V3 cross_axis_add(const MechParams& P, int i, V3 acc, V3 v, double s) {
+  if (Topo::axis_kind(P, i) == AxZ) return V3{fma(v.y, s, acc.x), fma(-v.x, s, acc.y), acc.z};
+  return acc + cross(v, V3{P.axis[i][0] * s, P.axis[i][1] * s, P.axis[i][2] * s});
+}
 // J * axis
 template <class Topo>
 GP_D V3 sym_mul_axis(const MechParams& P, int i, const S3& J) {
   if (Topo::axis_kind(P, i) == AxZ) return V3{J.xz, J.yz, J.zz};
   return mul(J, V3{P.axis[i][0], P.axis[i][1], P.axis[i][2]});
+}
+
+// Which values of the root -> leaf pass are LITERAL zeros (the compiler must keep `0 * x` and `0 + x`: IEEE; found with
+// tools/sass_attribution.py --zero). Compile-time constants for the static topologies, false for run-time tables.
+// b has no moving parent (root, or child of a body that is fixed to the world): its bias acceleration is (0 ; a_l)
+template <class Topo>
+GP_D bool first_moving(const MechParams& P, int b) {
+  const int p = Topo::parent(P, b);
+  return !((p >= 0) && !Topo::anchored(P, p));
+}
+// b turns about its own +z behind a first moving body: the angular part of its bias acceleration is (x, y, 0)
+template <class Topo>
+GP_D bool acc_az_zero(const MechParams& P, int b) {
+  const int p = Topo::parent(P, b);
+  return (p >= 0) && !Topo::anchored(P, p) && first_moving<Topo>(P, p) && Topo::jtype(P, b) == JRevolute &&
+         Topo::axis_kind(P, b) == AxZ;
 }
 
 // ---- sin/cos of every revolute joint angle, evaluated together --------------------------------
@@ -390,9 +413,23 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     // has zero twist and a constant acceleration (0; g'): treat its children like root joints
     const bool moving_parent = (p >= 0) && !Topo::anchored(P, p);
     SV vi, ai;
+    // Literal zeros that a generic transform would multiply through (the compiler must keep 0 * x: IEEE), found with
+    // tools/sass_attribution.py --zero. A parent that is the first moving body of its chain has the bias acceleration
+    // (0 ; a_l); if it also turns about its own +z its twist is (0,0,w ; 0).
+    const bool parent_first = moving_parent && first_moving<Topo>(P, p);
+    const bool parent_spins_z = parent_first && Topo::jtype(P, p) == JRevolute && Topo::axis_kind(P, p) == AxZ;
     if (moving_parent) {
-      vi = motion_to_child(E, r, vel[p]);
-      ai = motion_to_child(E, r, acc[p]);
+      if (parent_spins_z) {
+        const double w = vel[p].a.z;
+        vi.a = V3{E.m[6] * w, E.m[7] * w, E.m[8] * w};  // E^T (0,0,w)
+        const double t0 = -(w * r.y), t1 = w * r.x;      // (0,0,w) x r = (t0, t1, 0)
+        vi.l = V3{E.m[0] * t0 + E.m[3] * t1, E.m[1] * t0 + E.m[4] * t1, E.m[2] * t0 + E.m[5] * t1};
+      } else {
+        vi = motion_to_child(E, r, vel[p]);
+      }
+      if (parent_first) ai = SV{v3z(), mulT(E, acc[p].l)};
+      else if (acc_az_zero<Topo>(P, p)) ai = motion_to_child_az0(E, r, acc[p]);
+      else ai = motion_to_child(E, r, acc[p]);
     } else if (p >= 0) {
       vi = svz();
       ai = SV{v3z(), mulT(E, acc[p].l)};
@@ -406,8 +443,8 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     if (jt == JRevolute) {
       const double qd = v[vo];
       if (moving_parent) {
-        ai.a += cross_axis<Topo>(P, i, vi.a, qd);  // w x (a qd)
-        ai.l += cross_axis<Topo>(P, i, vi.l, qd);  // vl x (a qd)
+        ai.a = cross_axis_add<Topo>(P, i, ai.a, vi.a, qd);  // w x (a qd)
+        ai.l = cross_axis_add<Topo>(P, i, ai.l, vi.l, qd);  // vl x (a qd)
         vi.a = axis_add<Topo>(P, i, vi.a, qd);
       } else {
         vi.a = axis_scaled<Topo>(P, i, qd);
@@ -415,7 +452,7 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     } else if (jt == JPrismatic) {
       const double qd = v[vo];
       if (moving_parent) {
-        ai.l += cross_axis<Topo>(P, i, vi.a, qd);  // w x (a qd)
+        ai.l = cross_axis_add<Topo>(P, i, ai.l, vi.a, qd);  // w x (a qd)
         vi.l = axis_add<Topo>(P, i, vi.l, qd);
       } else {
         vi.l = axis_scaled<Topo>(P, i, qd);
@@ -574,6 +611,16 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
       const SV h = mul(RBI{Ji, ci, mi}, vi);
       f.a = cross_add(cross_add(cross_add(ka, ci, ai.l), vi.a, h.a), vi.l, h.l);
       f.l = cross_add(fma3(ai.l, mi, kl), vi.a, h.l);
+    } else if (acc_az_zero<Topo>(P, i)) {
+      // ai.a = (x, y, 0): the same sums without the terms of the literal zero
+      const SV h = mul(RBI{Ji, ci, mi}, vi);
+      const V3 t = cross_add(ka, ci, ai.l);
+      const V3 Ja = V3{fma(Ji.xy, ai.a.y, fma(Ji.xx, ai.a.x, t.x)), fma(Ji.yy, ai.a.y, fma(Ji.xy, ai.a.x, t.y)),
+                       fma(Ji.yz, ai.a.y, fma(Ji.xz, ai.a.x, t.z))};
+      f.a = cross_add(cross_add(Ja, vi.a, h.a), vi.l, h.l);
+      const V3 u = fma3(ai.l, mi, kl);
+      const V3 ca = V3{fma(ci.z, ai.a.y, u.x), fma(-ci.z, ai.a.x, u.y), fma(ci.y, ai.a.x, fma(-ci.x, ai.a.y, u.z))};  // u - c x a
+      f.l = cross_add(ca, vi.a, h.l);
     } else {
       const SV h = mul(RBI{Ji, ci, mi}, vi);
       f.a = cross_add(cross_add(mul_add(cross_add(ka, ci, ai.l), Ji, ai.a), vi.a, h.a), vi.l, h.l);
@@ -762,7 +809,8 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
     if (jt == JRevolute) {
       SV F;
       F.a = sym_mul_axis<Topo>(P, i, Ic.J);
-      F.l = cross_axis<Topo>(P, i, Ic.c, -1.0);  // m*0 - c x a
+      if (Topo::axis_kind(P, i) == AxZ) F.l = V3{-Ic.c.y, Ic.c.x, 0.0};  // m*0 - c x a with a = +z
+      else F.l = cross_axis<Topo>(P, i, Ic.c, -1.0);
       H[hidx(vo, vo)] = axis_dot<Topo>(P, i, F.a);
       if constexpr (DUMP) {
         if (out.armature) H[hidx(vo, vo)] += P.armature[i];  // hybrid/articulated/mod.rs:247
@@ -812,7 +860,11 @@ GP_D unsigned dynamics_core(const MechParams& P, const double* q, const double* 
             H[hidx(d, vo + 3)] = F.l.x; H[hidx(d, vo + 4)] = F.l.y; H[hidx(d, vo + 5)] = F.l.z;
           }
         }
-        if (carry) Fd[d] = force_to_parent(E, r, Fd[d]);
+        if (carry) {
+          // (the column of this body's own +z revolute joint has no linear z component yet: a literal zero)
+          if (d == vo && jt == JRevolute && Topo::axis_kind(P, i) == AxZ) Fd[d] = force_to_parent_lz0(E, r, Fd[d]);
+          else Fd[d] = force_to_parent(E, r, Fd[d]);
+        }
       }
     });
     // the columns of this body's dofs are complete now (the parity kernels first report H and the bias)

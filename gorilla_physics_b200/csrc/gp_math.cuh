@@ -166,9 +166,20 @@ GP_HD SV svz() { return SV{v3z(), v3z()}; }
 GP_HD SV motion_to_child(const M3& E, V3 r, const SV& p) {
   return SV{mulT(E, p.a), mulT(E, cross_add(p.l, p.a, r))};
 }
+// the same for a motion vector whose angular part has no z component (p.a.z is a literal zero)
+GP_HD SV motion_to_child_az0(const M3& E, V3 r, const SV& p) {
+  const V3 a = V3{E.m[0] * p.a.x + E.m[3] * p.a.y, E.m[1] * p.a.x + E.m[4] * p.a.y, E.m[2] * p.a.x + E.m[5] * p.a.y};
+  const V3 t = V3{fma(p.a.y, r.z, p.l.x), fma(-p.a.x, r.z, p.l.y), fma(p.a.x, r.y, fma(-p.a.y, r.x, p.l.z))};  // p.l + p.a x r
+  return SV{a, mulT(E, t)};
+}
 // force vector from successor to predecessor coordinates
 GP_HD SV force_to_parent(const M3& E, V3 r, const SV& f) {
   V3 fl = mul(E, f.l);
+  return SV{mul_add(cross(r, fl), E, f.a), fl};
+}
+// the same for a force whose linear part has no z component (f.l.z is a literal zero)
+GP_HD SV force_to_parent_lz0(const M3& E, V3 r, const SV& f) {
+  V3 fl = V3{E.m[0] * f.l.x + E.m[1] * f.l.y, E.m[3] * f.l.x + E.m[4] * f.l.y, E.m[6] * f.l.x + E.m[7] * f.l.y};
   return SV{mul_add(cross(r, fl), E, f.a), fl};
 }
 // acc += (f expressed in predecessor coordinates)

@@ -17,12 +17,13 @@ static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }  // device-o
 
 #include "../gorilla_physics_b200/csrc/gp_host.h"
 #include "../gorilla_physics_b200/csrc/gp_dynamics.cuh"
+#include "../gorilla_physics_b200/csrc/gp_jit.h"
 
 using namespace gp;
 
 namespace gp {
 // the debug build has no kernels: satisfy the variant registry with empty tables
-static KernelTable dummy{"debug", TopoData{}, false, 128, true, nullptr, nullptr, nullptr};
+static KernelTable dummy{"debug", TopoData{}, false, 128, true, false, 1, nullptr, nullptr, nullptr};
 const KernelTable* variant_generic() { return &dummy; }
 const KernelTable* variant_pendulum() { return &dummy; }
 const KernelTable* variant_double_pendulum() { return &dummy; }
@@ -33,6 +34,14 @@ const KernelTable* variant_hopper1d() { return &dummy; }
 const KernelTable* variant_hopper() { return &dummy; }
 const KernelTable* variant_quadruped() { return &dummy; }
 const KernelTable* variant_navbot() { return &dummy; }
+const KernelTable* variant_custom() { return &dummy; }
+// ... and no run-time specialisation
+bool jit_available(std::string* why) { if (why) *why = "host debug build"; return false; }
+JitPolicy jit_policy_for(const gp_mechanism*, const TopoData&) { return JitPolicy{}; }
+const KernelTable* jit_table(const TopoData&, const JitPolicy&) { return &dummy; }
+bool is_jit_table(const KernelTable*) { return false; }
+int jit_precompile(const KernelTable*, int, unsigned, int* n) { if (n) *n = 0; return 0; }
+std::string jit_cache_dir() { return ""; }
 }  // namespace gp
 
 extern "C" int gpdbg_dynamics(const gp_mechanism* m, const double* q, const double* v, const double* tau,
