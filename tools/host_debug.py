@@ -22,8 +22,16 @@ dbg.gpdbg_dynamics_static.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp]
 
 
 def run(name):
-    factory, kw, _ = WORKLOADS[name]
-    desc = factory().desc()
+    if name.startswith("random_tree:"):
+        # random mechanisms (mixed joint types, fixed joints inside chains, floating joints off other bodies): the
+        # run-time-topology instantiation only, the static one has no specialisation for them
+        seed = int(name.split(":")[1])
+        desc, kw = models.random_tree(2000 + seed, 2 + (5 * seed + 3) % 8), {}
+        if desc.n_v == 0:  # (fixed joints only: nothing to solve)
+            return 0.0
+    else:
+        factory, kw, _ = WORKLOADS[name]
+        desc = factory().desc()
     # rebuild the mechanism inside the debug library from the flat description
     keep = {}
     d = _abi.GpMechanismDesc()
@@ -72,6 +80,6 @@ def run(name):
 
 
 if __name__ == "__main__":
-    names = [sys.argv[1]] if len(sys.argv) > 1 and sys.argv[1] != "all" else list(WORKLOADS)
+    names = [sys.argv[1]] if len(sys.argv) > 1 and sys.argv[1] != "all" else list(WORKLOADS) + [f"random_tree:{k}" for k in range(12)]
     for n in names:
         print(n, "worst vdot err", run(n))
