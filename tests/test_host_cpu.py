@@ -405,3 +405,38 @@ def test_unlisted_trees_are_routed_to_run_time_compiled_kernels():
     assert nav.kernel_variant == "jit:FRRRRRRRRX" and arm.kernel_variant == "jit:XRRRRRRX"
     assert generic_twin(gp.WORKLOADS["so101_contact"].mechanism(), KernelMode.GENERIC).kernel_variant == "generic"
     assert gp.WORKLOADS["so101_contact"].mechanism().set_kernel_mode(KernelMode.JIT).kernel_variant == "jit:XRRRRRR"
+
+
+def test_mechanism_create_rejects_partial_descriptions_and_non_unit_normals():
+    """A description that announces halfspaces / contact points / spring contacts but leaves their arrays NULL is
+    GP_ERR_INVALID, not a segfault; a halfspace normal must be a unit vector (the reference takes a UnitVector3,
+    halfspace.rs:6-22: a longer one would scale penetration and force silently)."""
+    m = gp.Mechanism.from_model("so101")
+    with pytest.raises(GorillaError) as e:
+        m.add_halfspace((0, 0, 2.0), 0.0)
+    assert e.value.code == _abi.GP_ERR_INVALID and "unit" in str(e.value)
+    d = m.desc()
+    d.add_halfspace((0, 0.6, 0.6), 0.0)
+    with pytest.raises(GorillaError) as e:
+        gp.Mechanism.from_desc(d)
+    assert e.value.code == _abi.GP_ERR_INVALID
+    # the same mechanism through the raw ABI, per-body arrays only
+    lib = _abi.lib()
+    good = gp.Mechanism.from_model("so101").desc()
+    raw, keep = _abi.GpMechanismDesc(), {}
+    raw.n_bodies = good.n_bodies
+    for f in ("parent", "joint_type", "has_spring"):
+        keep[f] = np.ascontiguousarray(getattr(good, f), dtype=np.int32)
+        setattr(raw, f, keep[f].ctypes.data_as(_abi.ip))
+    for f in ("axis", "init_iso", "moment", "cross_part", "mass", "spring_k", "spring_l"):
+        keep[f] = np.ascontiguousarray(getattr(good, f), dtype=np.float64)
+        setattr(raw, f, keep[f].ctypes.data_as(C.POINTER(C.c_double)))
+    h = C.c_void_p()
+    assert lib.gp_mechanism_create(C.byref(raw), C.byref(h)) == _abi.GP_OK  # complete as it is
+    lib.gp_mechanism_destroy(h)
+    for field in ("n_halfspaces", "n_contact_points", "n_spring_contacts"):
+        setattr(raw, field, 2)
+        h = C.c_void_p()
+        assert lib.gp_mechanism_create(C.byref(raw), C.byref(h)) == _abi.GP_ERR_INVALID, field
+        assert not h.value
+        setattr(raw, field, 0)
