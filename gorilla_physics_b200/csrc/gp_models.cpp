@@ -70,6 +70,15 @@ Inertia cube_inertia(double m, double l) {  // RigidBody::new_cube, rigid_body.r
   return diag_inertia(i, i, i, {0, 0, 0}, m);
 }
 
+// RigidBody::new_cuboid (rigid_body.rs:160-172): uniform cuboid about its centre, w x d x h along x, y, z
+Inertia cuboid_inertia(double m, double w, double d, double h) {
+  return diag_inertia(m * (d * d + h * h) / 12.0, m * (w * w + h * h) / 12.0, m * (w * w + d * d) / 12.0, {0, 0, 0}, m);
+}
+// RigidBody::new_cuboid_at (rigid_body.rs:175-195): the same cuboid with its centre at `com` of the body frame
+Inertia cuboid_inertia_at(Vec3 com, double m, double w, double d, double h) {
+  return com_inertia(m, com, m * (d * d + h * h) / 12.0, 0, 0, m * (w * w + h * h) / 12.0, 0, m * (w * w + d * d) / 12.0);
+}
+
 struct Builder {
   std::vector<int32_t> parent, jtype, has_spring, cp_body;
   std::vector<double> axis, iso, moment, cross, mass, sk, sl, cp_loc, cp_k;
@@ -142,6 +151,19 @@ void add_cube_contacts(Builder& b, int body, double l) {
   b.contact(body, {h, -h, h});
   b.contact(body, {-h, h, h});
   b.contact(body, {-h, -h, h});
+}
+
+// RigidBody::add_cuboid_contacts (rigid_body.rs:216-249): top face then bottom face, x fastest
+void add_cuboid_contacts(Builder& b, int body, double w, double d, double h) {
+  for (double sz : {1.0, -1.0})
+    for (double sy : {1.0, -1.0})
+      for (double sx : {-1.0, 1.0}) b.contact(body, {sx * w / 2.0, sy * d / 2.0, sz * h / 2.0});
+}
+// RigidBody::add_cuboid_contacts_with (rigid_body.rs:251-264): corners about `com`, z fastest
+void add_cuboid_contacts_with(Builder& b, int body, Vec3 com, double w, double d, double h) {
+  for (double i : {-1.0, 1.0})
+    for (double j : {-1.0, 1.0})
+      for (double k : {-1.0, 1.0}) b.contact(body, {com.x + i * w / 2.0, com.y + j * d / 2.0, com.z + k * h / 2.0});
 }
 
 int bad_params(const char* name, int got, int want) {
@@ -382,6 +404,54 @@ extern "C" int gp_model_create(const char* name_c, const double* p, int np, gp_m
     b.add(foot_right, REV, Z, iso_xyz_rpy(0.00991772, -0.0490065, -0.00035, -4.01485e-15, 1.79841e-15, -1.84321),
           com_inertia(0.0155748, {-1.61747e-09, -4.83102e-08, -0.00780743}, 1.75464e-06, 3.92314e-13, -1.18704e-13,
                       1.75465e-06, -3.65986e-12, 2.81671e-06));  // wheel_right
+    return b.create(out);
+  }
+  if (name == "biped") {  // builders/biped_builder.rs:12-187: floating base + two 6-joint legs, 13 bodies, 18 dof
+    if (np != 0) return bad_params(name_c, np, 0);
+    const double l1 = 0.05, l2 = 0.2, m = 0.1, w_foot = 0.2;
+    const int base = b.add(0, FLOAT, Z, iso_identity(), cuboid_inertia(m, l1, l1, l2));
+    for (double side : {1.0, -1.0}) {  // left (+x), then right
+      const int pelvis = b.add(base, REV, Z, iso_translation(side * (l1 + l1) / 2.0, 0, 0),
+                               cuboid_inertia_at({0, 0, -l2 / 2.0}, m, l1, l1, l2));
+      const int hip = b.add(pelvis, REV, NEG_Y, iso_translation(0, 0, -l2),
+                            cuboid_inertia_at({side * l2 / 2.0, 0, 0}, m, l2, l1, l1));
+      const int thigh = b.add(hip, REV, X, iso_translation(side * l2, 0, 0),
+                              cuboid_inertia_at({0, 0, -l2 / 2.0}, m, l1, l1, l2));
+      const int calf = b.add(thigh, REV, X, iso_translation(0, 0, -l2), cuboid_inertia_at({0, 0, -l2 / 2.0}, m, l1, l1, l2));
+      const int ankle = b.add(calf, REV, X, iso_translation(0, 0, -l2), cuboid_inertia(m, l1, l2, l1));
+      const int foot = b.add(ankle, REV, NEG_Y, iso_translation(0, 0, -(l1 + l1) / 2.0), cuboid_inertia(m, w_foot, l2, l1));
+      add_cuboid_contacts(b, foot, w_foot, l2, l1);
+    }
+    return b.create(out);
+  }
+  if (name == "leg") {  // builders/leg_builder.rs:8-104: floating base + one 5-joint leg, contacts on thigh, calf, foot
+    if (np != 0) return bad_params(name_c, np, 0);
+    const double l1 = 0.05, l2 = 0.2, m = 0.1, w_foot = 0.2;
+    const int base = b.add(0, FLOAT, Z, iso_identity(), cuboid_inertia(m, l1, l1, l2));
+    const int pelvis = b.add(base, REV, Z, iso_translation((l1 + l1) / 2.0, 0, 0), cuboid_inertia_at({0, 0, -l2 / 2.0}, m, l1, l1, l2));
+    const int hip = b.add(pelvis, REV, NEG_Y, iso_translation(0, 0, -l2), cuboid_inertia_at({l2 / 2.0, 0, 0}, m, l2, l1, l1));
+    const Vec3 down{0, 0, -l2 / 2.0};
+    const int thigh = b.add(hip, REV, X, iso_translation(l2, 0, 0), cuboid_inertia_at(down, m, l1, l1, l2));
+    add_cuboid_contacts_with(b, thigh, down, l1, l1, l2);
+    const int calf = b.add(thigh, REV, X, iso_translation(0, 0, -l2), cuboid_inertia_at(down, m, l1, l1, l2));
+    add_cuboid_contacts_with(b, calf, down, l1, l1, l2);
+    const int foot = b.add(calf, REV, X, iso_translation(0, 0, -l2), cuboid_inertia(m, w_foot, l2, l1));
+    add_cuboid_contacts(b, foot, w_foot, l2, l1);
+    return b.create(out);
+  }
+  if (name == "leg_from_foot") {  // builders/leg_builder.rs:106-211: the same leg rooted at its (floating) foot
+    if (np != 0) return bad_params(name_c, np, 0);
+    const double l1 = 0.05, l2 = 0.2, m = 0.1, w_foot = 0.2;
+    const int foot = b.add(0, FLOAT, Z, iso_identity(), cuboid_inertia(m, w_foot, l2, l1));
+    add_cuboid_contacts(b, foot, w_foot, l2, l1);
+    const Vec3 up{0, 0, l2 / 2.0};
+    const int calf = b.add(foot, REV, X, iso_identity(), cuboid_inertia_at(up, m, l1, l1, l2));
+    add_cuboid_contacts_with(b, calf, up, l1, l1, l2);
+    const int thigh = b.add(calf, REV, X, iso_translation(0, 0, l2), cuboid_inertia_at(up, m, l1, l1, l2));
+    add_cuboid_contacts_with(b, thigh, up, l1, l1, l2);
+    const int hip = b.add(thigh, REV, X, iso_translation(0, 0, l2), cuboid_inertia_at({-l2 / 2.0, 0, 0}, m, l2, l1, l1));
+    const int pelvis = b.add(hip, REV, NEG_Y, iso_translation(-l2, 0, 0), cuboid_inertia_at(up, m, l1, l1, l2));
+    b.add(pelvis, REV, Z, iso_translation(0, 0, l2), cuboid_inertia_at({-(l1 + l1) / 2.0, 0, 0}, m, l1, l1, l2));
     return b.create(out);
   }
   gp::set_error("unknown model '%s'", name_c);

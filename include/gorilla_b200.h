@@ -239,6 +239,9 @@ int gp_mechanism_precompile(const gp_mechanism* mech, unsigned kinds, int* n_com
  *   "slip"              [m, r, l_rest, angle, k_spring]                   helpers.rs:308
  *   "so101"             []                                                builders/mod.rs:252
  *   "navbot"            []                                                builders/navbot_builder.rs:682
+ *   "biped"             []  (floating base + two 6-joint legs: 13 bodies, 18 dof, 16 foot contact points)  builders/biped_builder.rs:12
+ *   "leg"               []  (floating base + one 5-joint leg, 24 contact points)                builders/leg_builder.rs:8
+ *   "leg_from_foot"     []  (the same leg rooted at its floating foot)                          builders/leg_builder.rs:106
  * Pass n_params == 0 to get the parameter values used by the reference's own
  * example / test of that model where the builder takes parameters. */
 int gp_model_create(const char* name, const double* params, int n_params, gp_mechanism** out);

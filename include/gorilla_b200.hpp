@@ -649,5 +649,8 @@ inline MechanismState build_hopper(Float m_foot, Float r_foot, Float m_hip, Floa
 inline MechanismState build_quadruped() { return MechanismState::from_model("quadruped"); }  // helpers.rs:423
 inline MechanismState build_so101() { return MechanismState::from_model("so101"); }          // builders/mod.rs:252 (meshes are visual only)
 inline MechanismState build_navbot() { return MechanismState::from_model("navbot"); }        // builders/navbot_builder.rs:682
+inline MechanismState build_biped() { return MechanismState::from_model("biped"); }          // builders/biped_builder.rs:12
+inline MechanismState build_leg() { return MechanismState::from_model("leg"); }              // builders/leg_builder.rs:8
+inline MechanismState build_leg_from_foot() { return MechanismState::from_model("leg_from_foot"); }  // builders/leg_builder.rs:106
 
 }  // namespace gorilla

@@ -15,18 +15,21 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.fixture(scope="module")
-def debug_library(tmp_path_factory):
+def build_debug_library(out, extra=()):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    out = tmp_path_factory.mktemp("gpdbg") / "libgpdbg.so"
     cuda = Path("/usr/local/cuda")
-    cmd = ["g++", "-DGP_HOST_DEBUG", "-std=c++17", "-O1", "-shared", "-fPIC", f"-I{cuda / 'include'}", "-x", "c++", "-o", str(out),
+    cmd = ["g++", "-DGP_HOST_DEBUG", *extra, "-std=c++17", "-O1", "-shared", "-fPIC", f"-I{cuda / 'include'}", "-x", "c++", "-o", str(out),
            str(ROOT / "tools" / "host_debug.cu"), str(ROOT / "gorilla_physics_b200" / "csrc" / "gp_mechanism.cpp"),
            str(ROOT / "gorilla_physics_b200" / "csrc" / "gp_models.cpp"), f"-L{cuda / 'lib64'}", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     return out
+
+
+@pytest.fixture(scope="module")
+def debug_library(tmp_path_factory):
+    return build_debug_library(tmp_path_factory.mktemp("gpdbg") / "libgpdbg.so")
 
 
 def test_device_dynamics_code_matches_the_oracle_on_the_host(debug_library):
@@ -42,3 +45,44 @@ def test_device_dynamics_code_matches_the_oracle_on_the_host(debug_library):
         assert err < 1e-10, f"{name}: vdot off by {err} (relative) against the oracle"
     for name, _, cf in static:
         assert float(cf) < 1e-9, f"{name}: contact forces of the static and run-time-topology instantiations differ by {cf}"
+
+
+def run_models(library, names):
+    out = ""
+    for name in names:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "host_debug.py"), name, str(library)], capture_output=True, text=True,
+                           cwd=ROOT, timeout=600)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+        out += r.stdout
+    return out
+
+
+def test_cuboid_built_models_on_the_host(debug_library):
+    """biped / leg / leg_from_foot (builders/biped_builder.rs, leg_builder.rs; 13 / 6 / 6 bodies, 16 / 24 / 24 contact
+    points) on the ground, through the run-time-topology instantiation of the device code, against the oracle"""
+    out = run_models(debug_library, ["model:biped", "model:leg", "model:leg_from_foot"])
+    worst = {m.group(1): float(m.group(2)) for m in re.finditer(r"^(model:\w+) worst vdot err (\S+)$", out, re.M)}
+    assert set(worst) == {"model:biped", "model:leg", "model:leg_from_foot"}, out[-2000:]
+    assert max(worst.values()) < 1e-10, worst
+
+
+def test_biped_run_time_specialisation_on_the_host(tmp_path):
+    """The biped has no shipped kernel: the library compiles StaticTopo<SpecCustom> for its tree at run time (gp_jit.cpp
+    hands NVRTC the SpecCustom macros + the kernel sources). The same instantiation, built here for the host from the
+    macros tools/custom_topo.py derives for the tree, against the oracle and against the run-time-topology one."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    from custom_topo import custom_topo_vars
+
+    import gorilla_physics_b200 as gp
+    kv = dict(x.split("=") for x in custom_topo_vars(gp.Mechanism.from_model("biped").desc(), "biped").split())
+    assert kv["CUSTOM_NB"] == "13" and kv["CUSTOM_PARENTS"] == "-1,0,1,2,3,4,5,0,7,8,9,10,11"
+    header = tmp_path / "custom_biped.h"
+    header.write_text(f'#define GP_CUSTOM_TOPO_NB {kv["CUSTOM_NB"]}\n#define GP_CUSTOM_TOPO_PARENTS {kv["CUSTOM_PARENTS"]}\n'
+                      f'#define GP_CUSTOM_TOPO_JOINTS {kv["CUSTOM_JOINTS"]}\n#define GP_CUSTOM_TOPO_AXES {kv["CUSTOM_AXES"]}\n'
+                      '#define GP_CUSTOM_TOPO_NAME "biped"\n')
+    lib = build_debug_library(tmp_path / "libgpdbg_biped.so", ("-include", str(header)))
+    out = run_models(lib, ["model:biped"])
+    static = re.findall(r"^model:biped env 0: static-topology vdot err (\S+), contact force vs generic (\S+)$", out, re.M)
+    assert len(static) == 1, out[-2000:]
+    assert float(static[0][0]) < 1e-10 and float(static[0][1]) < 1e-9
+    assert float(re.search(r"^model:biped worst vdot err (\S+)$", out, re.M).group(1)) < 1e-10

@@ -193,6 +193,35 @@ def test_model_literals_match_reference_sources():
                 np.testing.assert_array_equal(d.axis[i], b["axis"])
 
 
+def test_cuboid_models_match_reference_sources():
+    """biped / leg / leg_from_foot (builders/biped_builder.rs, leg_builder.rs) are arithmetic over a few lengths, not
+    literals: tests/golden/cuboid_models.json holds the reference's statements EVALUATED by
+    tools/extract_reference_cuboid_models.py (per body the cuboid's m, w, d, h and centre, the joint, its origin, the
+    contact points in the reference's order); the product's builders must produce exactly that mechanism, with
+    RigidBody::new_cuboid / new_cuboid_at's inertia (rigid_body.rs:160-195) applied here in numpy."""
+    gold = json.loads((ROOT / "tests" / "golden" / "cuboid_models.json").read_text())
+    for model, n_bodies, n_v, n_cp in (("biped", 13, 18, 16), ("leg", 6, 11, 24), ("leg_from_foot", 6, 11, 24)):
+        d = gp.Mechanism.from_model(model).desc()
+        g = gold[model]["bodies"]
+        assert d.n_bodies == len(g) == n_bodies and d.n_v == n_v and d.n_contact_points == n_cp
+        cps = []
+        for i, b in enumerate(g):
+            m, w, dd, h, com = b["m"], b["w"], b["d"], b["h"], np.array(b["com"])
+            mc = np.diag([m * (dd * dd + h * h) / 12.0, m * (w * w + h * h) / 12.0, m * (w * w + dd * dd) / 12.0])
+            moment = mc + m * (com @ com * np.eye(3) - np.outer(com, com))
+            assert d.mass[i] == m
+            np.testing.assert_allclose(d.cross_part[i], m * com, rtol=1e-15, atol=0)
+            np.testing.assert_allclose(d.moment[i].reshape(3, 3), moment, rtol=1e-14, atol=1e-20)
+            assert int(d.parent[i]) == b["parent"] and int(d.joint_type[i]) == b["joint_type"]
+            np.testing.assert_array_equal(d.init_iso[i], [0.0, 0.0, 0.0, 1.0] + b["xyz"])
+            if b["axis"] is not None:
+                np.testing.assert_array_equal(d.axis[i], b["axis"])
+            cps += [(i + 1, c) for c in b["contacts"]]
+        assert [int(x) for x in d.cp_body] == [body for body, _ in cps]  # the reference's order (body-major already)
+        np.testing.assert_allclose(np.asarray(d.cp_location).reshape(-1, 3), [c for _, c in cps], rtol=1e-15, atol=0)
+        assert all(k == 50e3 for k in np.asarray(d.cp_k))  # ContactPoint::new's default stiffness, contact.rs:24-30
+
+
 def test_shard_ranges_cover_everything():
     for n, w in ((65536, 8), (262144, 3), (7, 8), (1, 1), (1000003, 8)):
         ranges = [shard_range(n, r, w) for r in range(w)]

@@ -57,6 +57,18 @@ CASES = {
     "double_pendulum": (lambda: Mechanism.from_model("double_pendulum").desc(), dict(q_range=math.pi), False),
     "cart_pole": (lambda: Mechanism.from_model("cart_pole").desc(), dict(q_range=math.pi), False),
 }
+
+
+def _grounded(model):
+    m = Mechanism.from_model(model)
+    m.add_halfspace((0, 0, 1), 0.0)
+    return m.desc()
+
+
+# the reference's cuboid-built trees (builders/biped_builder.rs, leg_builder.rs): 13 / 6 / 6 bodies, 16 / 24 / 24 contact points
+CASES["biped"] = (lambda: _grounded("biped"), dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5), True)
+CASES["leg"] = (lambda: _grounded("leg"), dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5), True)
+CASES["leg_from_foot"] = (lambda: _grounded("leg_from_foot"), dict(base_t=(0, 0, 0.02), t_jitter=0.05, rpy_jitter=0.3, q_range=0.5), True)
 for _s in range(8):
     CASES[f"random_tree_{_s}"] = ((lambda s=_s: models.random_tree(s, 3 + s)), dict(), False)
 
@@ -164,7 +176,7 @@ def test_counting_build_is_the_same_arithmetic():
     assert 5e3 < per_step < 2e4, per_step  # ~9e3 flop per SO-101 step in the reference's formulation
 
 
-@pytest.mark.parametrize("name", ["so101", "navbot", "quadruped_free", "double_pendulum", "hopper_1d_free"])
+@pytest.mark.parametrize("name", ["so101", "navbot", "quadruped_free", "double_pendulum", "hopper_1d_free", "biped_free"])
 def test_energy_is_conserved_along_oracle_rollouts(name):
     """A physics pin that needs no second implementation of the dynamics: without contact and torques the
     total energy KE + PE is constant along the true trajectory. The reference's Runge-Kutta 4 advances the
@@ -176,6 +188,9 @@ def test_energy_is_conserved_along_oracle_rollouts(name):
     if name == "quadruped_free":
         desc = Mechanism.from_model("quadruped").desc()
         kw = dict(base_t=(0, 0, 1.0), t_jitter=0.1, rpy_jitter=0.3)
+    elif name == "biped_free":
+        desc = Mechanism.from_model("biped").desc()
+        kw = dict(base_t=(0, 0, 1.0), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5)
     elif name == "hopper_1d_free":
         desc = Mechanism.from_model("hopper_1d").desc()
         kw = dict(base_t=(0, 0, 1.0), t_jitter=0.1, rpy_jitter=0.3, q_range=0.2)
@@ -199,7 +214,8 @@ def test_energy_is_conserved_along_oracle_rollouts(name):
         assert abs(drift[1]) <= 1e-3 * scale
 
 
-@pytest.mark.parametrize("name", ["so101_contact", "navbot_contact", "quadruped", "hopper_1d", "rimless_wheel", "spring_pair"])
+@pytest.mark.parametrize("name", ["so101_contact", "navbot_contact", "quadruped", "hopper_1d", "rimless_wheel", "spring_pair", "biped",
+                                  "leg_from_foot"])
 def test_semi_implicit_euler_step_matches_its_definition(name):
     """I1 (integrators.rs:25-39, :276-319) through the oracle against the update written out from its
     definition on top of the independent dynamics: scalar joints and the quaternion / translation update of

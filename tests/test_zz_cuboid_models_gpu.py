@@ -1,0 +1,162 @@
+"""GPU parity of the reference's cuboid-built trees - build_biped (builders/biped_builder.rs:12-187: floating base +
+two 6-joint legs, 13 bodies, 18 dof, 16 foot-corner contact points: the largest tree the reference builds),
+build_leg and build_leg_from_foot (builders/leg_builder.rs:8-211, 24 contact points) - on the ground z = 0.
+
+None of them has a shipped kernel specialisation: they run on kernels compiled at run time for their own topology
+(gp_jit.cpp), the biped in the warp-pair mapping at these batch sizes (two legs = two halves), and on the
+run-time-topology kernel when forced to. Same bars as tests/test_parity_gpu.py: vdot / contact force / one step 1e-10
+relative against the oracle; rollouts within the oracle's own sensitivity. (This file sorts last on purpose: it was
+added after the round's GPU budget was spent, developed against the oracle on the host build of the device code,
+tests/test_device_code_on_host.py.)
+"""
+import math
+
+import numpy as np
+import pytest
+
+from gorilla_physics_b200 import Integrator, KernelMode, Mechanism, MechanismState, jit_available
+from gorilla_physics_b200.workloads import biped_on_ground, biped_standing_pose
+from tests.models import oracle_of
+from tests.test_parity_gpu import TOL_DYN, TOL_STEP, assert_rollout_parity, random_states, rel_err
+
+pytestmark = pytest.mark.gpu
+
+STATES = {"biped": dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5),
+          "leg": dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5),
+          "leg_from_foot": dict(base_t=(0, 0, 0.02), t_jitter=0.05, rpy_jitter=0.3, q_range=0.5)}
+VARIANT = {"biped": "jit:FRRRRRRRRRRRR", "leg": "jit:FRRRRR", "leg_from_foot": "jit:FRRRRR"}
+
+
+def on_ground(name, kernel=KernelMode.AUTO):
+    m = Mechanism.from_model(name)
+    m.add_halfspace((0, 0, 1), 0.0)
+    if kernel != KernelMode.AUTO:
+        m.set_kernel_mode(kernel)
+    return m
+
+
+def flavoured(name, flavour):
+    if flavour == "generic":
+        m = on_ground(name, KernelMode.GENERIC)
+        assert m.kernel_variant == "generic"
+        return m
+    if not jit_available():
+        pytest.skip("NVRTC not loadable: no run-time specialisation on this machine")
+    m = on_ground(name)
+    assert m.kernel_variant == VARIANT[name]  # what AUTO picks for an unlisted tree
+    return m
+
+
+@pytest.mark.parametrize("name", list(STATES))
+@pytest.mark.parametrize("flavour", ["jit", "generic"])
+def test_cuboid_model_dynamics_parity(name, flavour):
+    mech = flavoured(name, flavour)
+    desc = on_ground(name).desc()
+    orc = oracle_of(desc)
+    n = 512
+    q, v = random_states(desc, n, seed=1234, **STATES[name])
+    tau = np.random.default_rng(7).uniform(-1.0, 1.0, size=(n, desc.n_v))
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    vdot, cf = st.dynamics(tau=tau, contact_forces=True)
+    vdot_ref, cf_ref = orc.batch_dynamics(q, v, tau)
+    assert np.abs(cf_ref).max() > 0.0, "never touches the ground: contact path untested"
+    assert rel_err(vdot, vdot_ref) < TOL_DYN
+    assert rel_err(cf, cf_ref) < TOL_DYN
+    vdot0 = st.dynamics(tau=None)
+    assert rel_err(vdot0, orc.batch_dynamics(q, v, None)[0]) < TOL_DYN
+    assert not st.status().any()
+
+
+def test_biped_mass_matrix_energy_and_poses():
+    mech = flavoured("biped", "jit")
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 32
+    q, v = random_states(desc, n, seed=99, **STATES["biped"])
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    M, c = st.mass_matrix()
+    ke, pe, se = st.energies()
+    poses = st.poses()
+    for e in range(n):
+        ref = orc.dynamics(q[e], v[e], None, want="all")
+        assert M[e].shape == (18, 18)
+        assert rel_err(M[e][None], ref["mass_matrix"][None]) < 1e-12
+        assert rel_err(c[e][None], ref["bias"][None]) < TOL_DYN
+        assert abs(ke[e] - orc.kinetic_energy(q[e], v[e])) <= 1e-11 * max(1.0, abs(ke[e]))
+        assert abs(pe[e] - orc.gravitational_energy(q[e])) <= 1e-11 * max(1.0, abs(pe[e]))
+        np.testing.assert_allclose(poses[e], orc.poses(q[e]), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(STATES))
+@pytest.mark.parametrize("integrator", [Integrator.SemiImplicitEuler, Integrator.RungeKutta2, Integrator.RungeKutta4])
+def test_cuboid_model_single_step_parity(name, integrator):
+    mech = flavoured(name, "jit")
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 256
+    q, v = random_states(desc, n, seed=4321, **STATES[name])
+    dt = 1.0 / 6000.0
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    st.step(dt, tau=None, integrator=integrator)
+    q1, v1 = st.state()
+    q_ref, v_ref = orc.batch_rollout(q, v, dt, 1, integrator=int(integrator))
+    assert rel_err(q1, q_ref) < TOL_STEP
+    assert rel_err(v1, v_ref) < TOL_STEP
+
+
+def test_biped_settles_from_the_standing_pose_of_the_reference():
+    """interface/biped.rs:16-57 createBiped: knees bent, feet on the ground; 400 fused steps at dt = 1/6000 without
+    torques (the legs start to fold), against the oracle stepping one at a time; fused == unfused bitwise."""
+    mech = flavoured("biped", "jit")
+    desc = mech.desc()
+    orc = oracle_of(desc)
+    n = 96
+    rng = np.random.default_rng(5)
+    q = np.tile(biped_standing_pose(), (n, 1))
+    q[:, 7:] += rng.uniform(-0.02, 0.02, size=(n, 12))
+    q[:, 4:6] += rng.uniform(-0.01, 0.01, size=(n, 2))
+    v = np.zeros((n, desc.n_v))
+    # the pose of the reference: both feet level, their centres at z = 0 (soles 0.025 inside the ground)
+    foot = np.asarray(orc.poses(biped_standing_pose()))[-1]
+    assert abs(foot[6]) < 1e-12 and abs(foot[3] - 1.0) < 1e-12
+    _, cf0 = orc.batch_dynamics(q, v, None)
+    assert (np.abs(cf0).reshape(n, -1).max(axis=1) > 0).all()
+    dt, steps = 1.0 / 6000.0, 400
+    st = MechanismState(mech, n)
+    st.update(q, v)
+    st.step(dt, n_steps=steps)
+    q1, v1 = st.state()
+    assert_rollout_parity(orc, q, v, q1, v1, dt, steps, integrator=0)
+    st2 = MechanismState(mech, n)
+    st2.update(q, v)
+    for _ in range(10):
+        st2.step(dt, n_steps=1)
+    st3 = MechanismState(mech, n)
+    st3.update(q, v)
+    st3.step(dt, n_steps=10)
+    np.testing.assert_array_equal(st2.q, st3.q)
+    np.testing.assert_array_equal(st2.v, st3.v)
+
+
+def test_biped_workload_of_the_package():
+    """gorilla_physics_b200.WORKLOADS['biped'] (bench.py --workload biped): device-randomised states, one launch of 64
+    fused steps, against the oracle on the first environments."""
+    from gorilla_physics_b200 import WORKLOADS
+    w = WORKLOADS["biped"]
+    mech = w.mechanism()
+    if not jit_available():
+        pytest.skip("NVRTC not loadable")
+    assert mech.kernel_variant == VARIANT["biped"] and biped_on_ground().desc().n_v == 18
+    orc = oracle_of(mech.desc())
+    n = 4096
+    st = MechanismState(mech, n)
+    st.randomize(seed=3, **w.randomize)
+    q0, v0 = st.state()
+    st.step(w.dt, n_steps=64)
+    q1, v1 = st.state()
+    k = 128
+    assert_rollout_parity(orc, q0[:k], v0[:k], q1[:k], v1[:k], w.dt, 64, integrator=0)
+    assert math.isfinite(float(np.abs(q1).max())) and not st.status().any()

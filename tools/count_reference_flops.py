@@ -44,6 +44,7 @@ def main():
         "quadruped": dict(base_t=(0, 0, 0.8), t_jitter=0.01, rpy_jitter=0.1, q_range=0.2),
         "navbot_contact": dict(base_t=(0, 0, 0.075), t_jitter=0.01, rpy_jitter=0.1, q_range=0.2),
         "hopper_1d": dict(base_t=(0, 0, 2.5), t_jitter=1.0, rpy_jitter=0.0, q_range=0.0),
+        "biped": dict(base_t=(0, 0, 0.72), t_jitter=0.02, rpy_jitter=0.1, q_range=0.3),
     }
     out = {"_how": "python tools/count_reference_flops.py: oracle/gp_oracle_count.cpp (the oracle with a counting scalar "
                    "type, reference operation order, no FMA) stepping 16 environments of each bench workload for 2000 "

@@ -85,6 +85,10 @@ extern "C" int gpdbg_dynamics_static(const gp_mechanism* m, const double* q, con
 #define GP_TRY(Spec) if (topo_matches(Spec::data(), td)) return run_static<Spec>(m, q, v, tau, vdot, H, bias, cf);
   GP_TRY(SpecPendulum) GP_TRY(SpecDoublePendulum) GP_TRY(SpecCartPole) GP_TRY(SpecSO101) GP_TRY(SpecFloating)
   GP_TRY(SpecHopper1D) GP_TRY(SpecHopper) GP_TRY(SpecQuadruped) GP_TRY(SpecNavbot)
+#ifdef GP_CUSTOM_TOPO_NB
+  // built with the SpecCustom macros of one more tree (what gp_jit.cpp hands to NVRTC for it; g++ -include <header>)
+  GP_TRY(SpecCustom)
+#endif
 #undef GP_TRY
   return -1;
 }

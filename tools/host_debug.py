@@ -12,6 +12,10 @@ from oracle.binding import OracleMechanism
 from tests import models
 from tests.test_parity_gpu import WORKLOADS, random_states
 
+MODEL_STATES = {"biped": dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5),
+                "leg": dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5),
+                "leg_from_foot": dict(base_t=(0, 0, 0.02), t_jitter=0.05, rpy_jitter=0.3, q_range=0.5)}
+
 dbg = C.CDLL(sys.argv[2] if len(sys.argv) > 2 else "/tmp/proto/libgpdbg.so")
 dp = C.POINTER(C.c_double)
 for n in ("gp_model_create", "gp_mechanism_create", "gp_mechanism_add_halfspace", "gp_mechanism_add_contact_point"):
@@ -29,6 +33,12 @@ def run(name):
         desc, kw = models.random_tree(2000 + seed, 2 + (5 * seed + 3) % 8), {}
         if desc.n_v == 0:  # (fixed joints only: nothing to solve)
             return 0.0
+    elif name.startswith("model:"):
+        # the cuboid-built models of the reference (biped / leg / leg_from_foot) on the ground, around it; their
+        # compile-time-topology instantiation exists only in a build with that tree's SpecCustom macros
+        mech = Mechanism.from_model(name.split(":")[1])
+        mech.add_halfspace((0, 0, 1), 0.0)
+        desc, kw = mech.desc(), MODEL_STATES[name.split(":")[1]]
     else:
         factory, kw, _ = WORKLOADS[name]
         desc = factory().desc()

@@ -43,6 +43,14 @@ def mechanisms():
     # bench.py --workload jit_* (the twins again, plus their energy kernels for the diagnostics)
     for name in ("so101_contact", "navbot_contact"):
         out["bench:" + name] = (lambda f=WORKLOADS[name][0]: generic_twin(f(), KernelMode.JIT), SIE | DYN | ENERGY)
+    # the reference's cuboid-built trees on the ground (tests/test_zz_cuboid_models_gpu.py, bench.py --workload biped)
+    def grounded(name):
+        m = Mechanism.from_model(name)
+        m.add_halfspace((0, 0, 1), 0.0)
+        return m
+    out["model:biped"] = (lambda: grounded("biped"), SIE | RK | DYN | ENERGY)
+    out["model:leg"] = (lambda: grounded("leg"), SIE | RK | DYN)
+    out["model:leg_from_foot"] = (lambda: grounded("leg_from_foot"), SIE | RK | DYN)
     return out
 
 
