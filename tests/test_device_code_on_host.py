@@ -79,7 +79,9 @@ def test_biped_run_time_specialisation_on_the_host(tmp_path):
     header = tmp_path / "custom_biped.h"
     header.write_text(f'#define GP_CUSTOM_TOPO_NB {kv["CUSTOM_NB"]}\n#define GP_CUSTOM_TOPO_PARENTS {kv["CUSTOM_PARENTS"]}\n'
                       f'#define GP_CUSTOM_TOPO_JOINTS {kv["CUSTOM_JOINTS"]}\n#define GP_CUSTOM_TOPO_AXES {kv["CUSTOM_AXES"]}\n'
-                      '#define GP_CUSTOM_TOPO_NAME "biped"\n')
+                      '#define GP_CUSTOM_TOPO_NAME "biped"\n'
+                      # the per-body contact policy gp_jit.cpp picks for it: per-lane hit lists on the two feet (8 corners each)
+                      '#define GP_CUSTOM_CONTACT_LIST_MASK 0x1040u\n')
     lib = build_debug_library(tmp_path / "libgpdbg_biped.so", ("-include", str(header)))
     out = run_models(lib, ["model:biped"])
     static = re.findall(r"^model:biped env 0: static-topology vdot err (\S+), contact force vs generic (\S+)$", out, re.M)
