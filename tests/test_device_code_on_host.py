@@ -15,13 +15,13 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def build_debug_library(out, extra=()):
+def build_debug_library(out, extra=(), tree=ROOT):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     cuda = Path("/usr/local/cuda")
     cmd = ["g++", "-DGP_HOST_DEBUG", *extra, "-std=c++17", "-O1", "-shared", "-fPIC", f"-I{cuda / 'include'}", "-x", "c++", "-o", str(out),
-           str(ROOT / "tools" / "host_debug.cu"), str(ROOT / "gorilla_physics_b200" / "csrc" / "gp_mechanism.cpp"),
-           str(ROOT / "gorilla_physics_b200" / "csrc" / "gp_models.cpp"), f"-L{cuda / 'lib64'}", "-lcudart"]
+           str(tree / "tools" / "host_debug.cu"), str(tree / "gorilla_physics_b200" / "csrc" / "gp_mechanism.cpp"),
+           str(tree / "gorilla_physics_b200" / "csrc" / "gp_models.cpp"), f"-L{cuda / 'lib64'}", "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     return out
@@ -66,10 +66,29 @@ def test_cuboid_built_models_on_the_host(debug_library):
     assert max(worst.values()) < 1e-10, worst
 
 
-def test_biped_run_time_specialisation_on_the_host(tmp_path):
+def patched_source_tree(dst):
+    """A copy of the sources in which the HOST stub of pair_exchange_sum (gp_dynamics.cuh; on the device: shared-memory
+    exchange + named barrier between the two warps of a pair) calls the hook of tools/host_debug.cu instead of doing
+    nothing. Nothing else differs, and the product's files are not touched."""
+    (dst / "tools").mkdir(parents=True)
+    shutil.copy(ROOT / "tools" / "host_debug.cu", dst / "tools")
+    shutil.copytree(ROOT / "gorilla_physics_b200" / "csrc", dst / "gorilla_physics_b200" / "csrc")
+    shutil.copytree(ROOT / "include", dst / "include")
+    f = dst / "gorilla_physics_b200" / "csrc" / "gp_dynamics.cuh"
+    text, stub = f.read_text(), "  (void)out; (void)slot0; (void)vals;\n"
+    assert text.count(stub) == 1
+    f.write_text(text.replace(stub, "  gp_host_pair_exchange(out.xch, SIDE, slot0, vals, N);\n"))
+    return dst
+
+
+def test_biped_run_time_specialisation_and_warp_pairs_on_the_host(tmp_path):
     """The biped has no shipped kernel: the library compiles StaticTopo<SpecCustom> for its tree at run time (gp_jit.cpp
-    hands NVRTC the SpecCustom macros + the kernel sources). The same instantiation, built here for the host from the
-    macros tools/custom_topo.py derives for the tree, against the oracle and against the run-time-topology one."""
+    hands NVRTC the SpecCustom macros + the kernel sources), and small batches run it as WARP PAIRS (one leg per warp).
+    Both instantiations are built here for the host from the macros the run-time specialisation derives for the tree
+    (tools/custom_topo.py + the policy of gp_jit.cpp jit_policy_for: per-lane contact lists on the two feet, the
+    right leg = half 1) and held against the oracle. The two halves of a pair run as two threads that meet at the
+    exchange points (a pthread barrier for the named barrier, an array for the shared-memory buffer); the shipped pair
+    kernels' instantiations (quadruped, navbot) ride along."""
     sys.path.insert(0, str(ROOT / "tools"))
     from custom_topo import custom_topo_vars
 
@@ -80,11 +99,17 @@ def test_biped_run_time_specialisation_on_the_host(tmp_path):
     header.write_text(f'#define GP_CUSTOM_TOPO_NB {kv["CUSTOM_NB"]}\n#define GP_CUSTOM_TOPO_PARENTS {kv["CUSTOM_PARENTS"]}\n'
                       f'#define GP_CUSTOM_TOPO_JOINTS {kv["CUSTOM_JOINTS"]}\n#define GP_CUSTOM_TOPO_AXES {kv["CUSTOM_AXES"]}\n'
                       '#define GP_CUSTOM_TOPO_NAME "biped"\n'
-                      # the per-body contact policy gp_jit.cpp picks for it: per-lane hit lists on the two feet (8 corners each)
-                      '#define GP_CUSTOM_CONTACT_LIST_MASK 0x1040u\n')
-    lib = build_debug_library(tmp_path / "libgpdbg_biped.so", ("-include", str(header)))
-    out = run_models(lib, ["model:biped"])
+                      '#define GP_CUSTOM_CONTACT_LIST_MASK 0x1040u\n'  # bodies 6, 12: the feet (8 corners each)
+                      '#define GP_CUSTOM_SIDE_MASK 0x1f80u\n')         # bodies 7..12: the right leg
+    tree = patched_source_tree(tmp_path / "src")
+    lib = build_debug_library(tmp_path / "libgpdbg_biped.so", ("-DGP_HOST_PAIRS", "-include", str(header)), tree)
+    out = run_models(lib, ["model:biped", "quadruped", "navbot_contact"])
     static = re.findall(r"^model:biped env 0: static-topology vdot err (\S+), contact force vs generic (\S+)$", out, re.M)
     assert len(static) == 1, out[-2000:]
     assert float(static[0][0]) < 1e-10 and float(static[0][1]) < 1e-9
-    assert float(re.search(r"^model:biped worst vdot err (\S+)$", out, re.M).group(1)) < 1e-10
+    pairs = dict(re.findall(r"^([\w:]+) env 0: warp-pair vdot err \S+, root copies differ by (\S+)$", out, re.M))
+    assert set(pairs) == {"model:biped", "quadruped", "navbot_contact"}, out[-2000:]
+    assert all(float(x) == 0.0 for x in pairs.values())  # IEEE sums commute: both halves hold the same root bits
+    # (worst covers the run-time-topology, static and warp-pair instantiations of all 8 sampled states)
+    worst = {m.group(1): float(m.group(2)) for m in re.finditer(r"^([\w:]+) worst vdot err (\S+)$", out, re.M)}
+    assert set(worst) == set(pairs) and max(worst.values()) < 1e-10, worst

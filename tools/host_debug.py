@@ -23,6 +23,9 @@ for n in ("gp_model_create", "gp_mechanism_create", "gp_mechanism_add_halfspace"
 dbg.gp_mechanism_create.argtypes = [C.POINTER(_abi.GpMechanismDesc), C.POINTER(C.c_void_p)]
 dbg.gpdbg_dynamics.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp]
 dbg.gpdbg_dynamics_static.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp]
+HAVE_PAIRS = hasattr(dbg, "gpdbg_dynamics_pair")  # a -DGP_HOST_PAIRS build (tests/test_device_code_on_host.py)
+if HAVE_PAIRS:
+    dbg.gpdbg_dynamics_pair.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
 
 
 def run(name):
@@ -75,6 +78,17 @@ def run(name):
             if e == 0 or es > 1e-9:
                 print(f"{name} env {e}: static-topology vdot err {es:.2e}, contact force vs generic {ecf:.1e}")
             worst = max(worst, es)
+        if HAVE_PAIRS:
+            # the warp-pair mapping: the tree's two halves as two threads that meet at the exchange barriers
+            vp = np.zeros(nv)
+            mism = C.c_double(0.0)
+            rc = dbg.gpdbg_dynamics_pair(h, qq.ctypes.data_as(dp), vv.ctypes.data_as(dp), tt.ctypes.data_as(dp),
+                                         vp.ctypes.data_as(dp), C.byref(mism))
+            if rc >= 0:
+                ep = np.abs(vp - ref["vdot"]).max() / max(np.abs(ref["vdot"]).max(), 1e-9)
+                if e == 0 or ep > 1e-9:
+                    print(f"{name} env {e}: warp-pair vdot err {ep:.2e}, root copies differ by {mism.value:.1e}")
+                worst = max(worst, ep, 1.0 if mism.value != 0.0 else 0.0)
         eM = np.abs(H - ref["mass_matrix"]).max() / np.abs(ref["mass_matrix"]).max()
         eb = np.abs(b - ref["bias"]).max() / max(np.abs(ref["bias"]).max(), 1e-9)
         ev = np.abs(vdot - ref["vdot"]).max() / max(np.abs(ref["vdot"]).max(), 1e-9)
