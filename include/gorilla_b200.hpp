@@ -448,7 +448,7 @@ class MechanismState {
     }
     return out;
   }
-  bool has_spring_contacts() const { return false; }  // SpringContact is a "next" row
+  bool has_spring_contacts() const { return false; }  // (this facade builds none; the C ABI has them: gp_mechanism_add_spring_contact)
 
   // ---- used by step / simulate / dynamics_continuous below
   gp_batch* batch() { sync_to_device(); return batch_.get(); }

@@ -469,3 +469,24 @@ def test_mechanism_create_rejects_partial_descriptions_and_non_unit_normals():
         assert lib.gp_mechanism_create(C.byref(raw), C.byref(h)) == _abi.GP_ERR_INVALID, field
         assert not h.value
         setattr(raw, field, 0)
+
+
+def test_examples_build_against_the_facade_and_fail_loudly_without_a_gpu(tmp_path):
+    """examples/*.cpp restate the reference's examples (examples/rimless_wheel.rs, examples/cube.rs, interface/biped.rs
+    createBiped) against include/gorilla_b200.hpp. They must compile and link against the library; on a machine without a
+    GPU they stop at the first device call with GP_ERR_NO_DEVICE (exit code 2) - there is no CPU path to fall back to."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import torch
+    lib_dir = ROOT / "gorilla_physics_b200" / "lib"
+    for src in sorted((ROOT / "examples").glob("*.cpp")):
+        exe = tmp_path / src.stem
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                            "-L", str(lib_dir), "-lgorilla_b200", f"-Wl,-rpath,{lib_dir}", "-ldl", "-lpthread", "-lrt"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        if not torch.cuda.is_available():
+            r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+            assert r.returncode == 2 and "no CUDA device" in r.stderr, (src.name, r.returncode, r.stderr[-500:])

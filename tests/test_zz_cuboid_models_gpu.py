@@ -160,3 +160,38 @@ def test_biped_workload_of_the_package():
     k = 128
     assert_rollout_parity(orc, q0[:k], v0[:k], q1[:k], v1[:k], w.dt, 64, integrator=0)
     assert math.isfinite(float(np.abs(q1).max())) and not st.status().any()
+
+
+def test_examples_run_on_the_gpu(tmp_path):
+    """examples/*.cpp (the reference's examples/rimless_wheel.rs, examples/cube.rs and interface/biped.rs createBiped
+    against the C++ facade) run to the end on the GPU and print what the oracle gets for the same runs: the rimless
+    wheel's limit cycle (oracle: pitch rate 0.302 ... 0.726 over the last 2 s of 20), the cube at rest on the ground
+    (oracle: x = 0.322, z = -0.504; a tumbling cube amplifies a 1e-15 perturbation to 2e-4 in 5 s, hence loose bounds), the
+    biped 0.1 s after it was set down (oracle: base z 0.47817, feet z 0.047587, kinetic energy 0.35401; sensitivity 4e-15)."""
+    import re
+    import shutil
+    import subprocess
+    from pathlib import Path
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = Path(__file__).resolve().parent.parent
+    lib_dir = root / "gorilla_physics_b200" / "lib"
+    out = {}
+    for name in ("rimless_wheel", "cube", "biped"):
+        exe = tmp_path / name
+        subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(root / "examples" / f"{name}.cpp"), "-o", str(exe),
+                        "-L", str(lib_dir), "-lgorilla_b200", f"-Wl,-rpath,{lib_dir}", "-ldl", "-lpthread", "-lrt"], check=True)
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout[-500:], r.stderr[-500:])
+        out[name] = r.stdout
+    num = r"(-?[\d.]+(?:e[-+]?\d+)?)"
+    lo, hi = map(float, re.search(rf"last 2 s: {num} \.\.\. {num}", out["rimless_wheel"]).groups())
+    assert "kernel: floating_F" in out["rimless_wheel"] and 0.25 < lo < 0.36 and 0.65 < hi < 0.80, out["rimless_wheel"]
+    x, z = map(float, re.search(rf"x = {num}, z = {num}", out["cube"]).groups())
+    speed = float(re.search(rf"final speed {num}", out["cube"]).group(1))
+    assert "25001 states" in out["cube"] and 0.2 < x < 0.45 and abs(z + 0.5) < 0.02 and speed < 0.05, out["cube"]
+    assert "kernel: jit:FRRRRRRRRRRRR" in out["biped"] or not jit_available(), out["biped"]
+    assert abs(float(re.search(rf"base lifted by {num}", out["biped"]).group(1)) - 0.532843) < 1e-5
+    bz, lz, rz, ke = map(float, re.search(rf"base z = {num}, left foot z = {num}, right foot z = {num}, kinetic energy {num}",
+                                          out["biped"]).groups())
+    assert abs(bz - 0.478170) < 1e-5 and abs(lz - 0.0475871) < 1e-6 and abs(rz - 0.0475871) < 1e-6 and abs(ke - 0.354009) < 1e-5
