@@ -19,7 +19,9 @@ from gorilla_physics_b200.workloads import biped_on_ground, biped_standing_pose
 from tests.models import oracle_of
 from tests.test_parity_gpu import TOL_DYN, TOL_STEP, assert_rollout_parity, random_states, rel_err
 
-pytestmark = pytest.mark.gpu
+# (a test of this file that has not returned after ten minutes ends the pytest process - method "thread" works even
+# while the main thread sits in a CUDA call - instead of holding the GPU box until the driver's own limit)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 STATES = {"biped": dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5),
           "leg": dict(base_t=(0, 0, 0.6), t_jitter=0.1, rpy_jitter=0.3, q_range=0.5),
