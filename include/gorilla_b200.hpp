@@ -448,6 +448,34 @@ class MechanismState {
     }
     return out;
   }
+  // simulate() (simulate.rs:87-112) when the control law needs no host closure: zero torques, or one of the reference's
+  // controllers that the library evaluates in-kernel (GP_CTRL_*, e.g. swingup_acrobot with {m, l}). Every state of the
+  // rollout comes back - row 0 the initial state, then the state after each step, like the reference's vectors - but
+  // the steps run fused on the device (gp_batch_simulate) instead of one launch and two copies per step.
+  std::pair<std::vector<std::vector<JointPosition>>, std::vector<std::vector<JointVelocity>>> simulate_fused(
+      Float final_time, Float dt, int integrator, int controller = GP_CTRL_NONE, const std::vector<Float>& ctrl_params = {}) {
+    sync_to_device();
+    const size_t nq = (size_t)n_q(), nv = (size_t)n_v();
+    const size_t n = (size_t)gp_simulate_step_count(final_time, dt);
+    std::vector<double> qf = to_float_vec(q), vf = to_float_vec(v);
+    std::vector<double> hq((n + 1) * nq + 1), hv((n + 1) * nv + 1), dummy(1, 0.0);
+    int64_t steps = 0;
+    check(gp_batch_simulate(batch_.get(), nq ? qf.data() : dummy.data(), nv ? vf.data() : dummy.data(), nullptr, final_time, dt,
+                            integrator, controller, ctrl_params.empty() ? nullptr : ctrl_params.data(), (int)ctrl_params.size(),
+                            &steps, hq.data(), hv.data()));
+    std::vector<std::vector<JointPosition>> qs;
+    std::vector<std::vector<JointVelocity>> vs;
+    qs.reserve(n + 1);
+    vs.reserve(n + 1);
+    for (size_t s = 0; s <= (size_t)steps; ++s) {
+      unpack(std::vector<double>(hq.begin() + s * nq, hq.begin() + (s + 1) * nq),
+             std::vector<double>(hv.begin() + s * nv, hv.begin() + (s + 1) * nv));
+      qs.push_back(q);
+      vs.push_back(v);
+    }
+    state_dirty_ = false;  // q, v and the device hold the final state
+    return {qs, vs};
+  }
   bool has_spring_contacts() const { return false; }  // (this facade builds none; the C ABI has them: gp_mechanism_add_spring_contact)
 
   // ---- used by step / simulate / dynamics_continuous below
@@ -609,6 +637,12 @@ std::pair<std::vector<std::vector<JointPosition>>, std::vector<std::vector<Joint
     t += dt;
   }
   return {qs, vs};
+}
+
+// simulate(state, final_time, dt, |_| vec![], integrator): the closure that returns no torques needs no host round trip
+inline std::pair<std::vector<std::vector<JointPosition>>, std::vector<std::vector<JointVelocity>>> simulate(
+    MechanismState& state, Float final_time, Float dt, Integrator integrator) {
+  return state.simulate_fused(final_time, dt, (int)integrator);
 }
 
 // ---------------------------------------------------------------- builders (helpers.rs, builders/*.rs)
