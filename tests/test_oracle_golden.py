@@ -321,6 +321,30 @@ def test_cart_pole_swingup():  # control/swingup.rs:190-261 (RK4, dt=1e-2, 30 s)
     assert abs(E - m_pole * l_pole * GRAVITY) < 2.0
 
 
+def test_acrobot_lqr():  # control/lqr.rs:78-124 (RK4, dt = 1e-2, 100 s): the hard-coded gain holds the upright acrobot, 1e-3
+    m, l = 5.0, 7.0
+    o = oracle_of(models.double_pendulum_hanging(m, l))
+    K = np.array([-14067.26123453, -4689.08739542, -15265.74479887, -5803.13757768])  # lqr.rs:10-15
+    q1_upright = -PI
+    q, v = np.array([q1_upright - 0.03, 0.03]), np.array([0.03, 0.03])
+    for _ in range(simulate_step_count(100.0, 0.01)):
+        xbar = np.array([q[0] - q1_upright, q[1], v[0], v[1]])
+        q, v = o.step(q, v, [0.0, -float(K @ xbar)], 0.01, RK4)
+    np.testing.assert_allclose(q, [q1_upright, 0.0], atol=1e-3)
+    np.testing.assert_allclose(v, [0.0, 0.0], atol=1e-3)
+
+
+def test_cart_pole_lqr():  # control/lqr.rs:126-186 (RK4, dt = 1e-2, 50 s): from 0.5 rad off upright back to it, 2e-3 / 1e-3
+    o = oracle_of(models.cart_pole(3.0, 1.0, 5.0, 7.0, (0, -1, 0)))
+    K = np.array([-1.0, 210.06025784, -5.27501096, 129.54543534])  # lqr.rs:40-43
+    q, v = np.array([-1.0, PI + 0.5]), np.array([1.0, 0.5])
+    for _ in range(simulate_step_count(50.0, 0.01)):
+        xbar = np.array([q[0], q[1] - PI, v[0], v[1]])
+        q, v = o.step(q, v, [-float(K @ xbar), 0.0], 0.01, RK4)
+    np.testing.assert_allclose(q, [0.0, PI], atol=2e-3)
+    np.testing.assert_allclose(v, [0.0, 0.0], atol=1e-3)
+
+
 def test_acrobot_example_energy_trace():  # examples/acrobot.rs: config 1 (SemiImplicitEuler, dt=1e-3)
     """The swing-up controller pumps the total energy towards m g (l + 2l) (swingup.rs:20)."""
     m, l = 1.0, 7.0
@@ -498,6 +522,76 @@ def test_SLIP_hopping():  # contact.rs:836-903: SpringContact (stateful leg), Se
     assert len(energies) > 0
     assert max(abs(e - e0) for e in energies) < 1e-2
     assert abs(hs[-3] - hs[-2]) < 1e-3 and abs(hs[-2] - hs[-1]) < 1e-3
+
+
+class _SLIPController:
+    """control/SLIP_control.rs:6-61 restated test-side: touch-down angle from a PID on the forward speed"""
+
+    def __init__(self, k_q, speed_bound, k_v_p, k_v_i, k_v_d):
+        self.k_q, self.speed_bound, self.k_v_p, self.k_v_i, self.k_v_d = k_q, speed_bound, k_v_p, k_v_i, k_v_d
+        self.v_integral, self.v_diff_prev = 0.0, 0.0
+
+    def control_to_pos(self, q, v, x_target):
+        v_x_target = -self.k_q * (q[4] - x_target)
+        if abs(v_x_target) > self.speed_bound:
+            v_x_target = math.copysign(self.speed_bound, v_x_target)
+        return self.control_to_velocity(q, v, v_x_target)
+
+    def control_to_velocity(self, q, v, v_x_target):
+        v_diff = _world_linear_velocity(q, v)[0] - v_x_target
+        self.v_integral += v_diff
+        degree = self.k_v_p * v_diff + self.k_v_i * self.v_integral + self.k_v_d * (v_diff - self.v_diff_prev)
+        self.v_diff_prev = v_diff
+        return math.radians(degree)
+
+
+def _world_linear_velocity(q, v):
+    x, y, z, w = q[0:4]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    return R @ v[3:6]
+
+
+def _slip_controlled_hopping(controller_gains, final_time, angle_of):
+    """the common loop of control/SLIP_control.rs:78-131 and :133-189: build_SLIP(m 0.54, r 1, l_rest 0.2, angle 0,
+    k 2000) above ground z = -0.5, SemiImplicitEuler at dt = 1/600, at every apex (world v_z turning negative) the
+    test swings the leg to the commanded touch-down angle and restores its rest length by hand"""
+    l_rest = 0.2
+    m = Mechanism.from_model("slip", [0.54, 1.0, l_rest, 0.0, 2000.0])
+    m.add_halfspace((0, 0, 1), -0.5)
+    o = oracle_of(m)
+    ctrl = _SLIPController(*controller_gains)
+    q, v = pose_q(), np.zeros(6)
+    st = o.spring_state_init()
+    dt = 1.0 / 600.0
+    vz_prev, vx_at_apex = 0.0, []
+    for _ in range(int(final_time / dt)):
+        q, v, st, flags = o.step_sc(q, v, st, dt)
+        assert flags == 0
+        v_lin = _world_linear_velocity(q, v)
+        if vz_prev >= 0.0 and v_lin[2] < 0.0:  # apex
+            angle = angle_of(ctrl, q, v)
+            d = np.array([math.sin(angle), 0.0, -math.cos(angle)])
+            st[0, 4:7] = d / np.linalg.norm(d)
+            st[0, 7] = l_rest
+            vx_at_apex.append(v_lin[0])
+        vz_prev = v_lin[2]
+    return q, vx_at_apex
+
+
+def test_SLIP_position_control():  # control/SLIP_control.rs:78-131: hops to x = 2 and stays there, 1e-3 after 10 s
+    x_target = 2.0
+    q, _ = _slip_controlled_hopping((1.0, 0.5, 20.0, 0.0, 0.0), 10.0, lambda c, q, v: c.control_to_pos(q, v, x_target))
+    assert abs(abs(q[4]) - x_target) < 1e-3
+
+
+def test_SLIP_speed_control():  # control/SLIP_control.rs:133-189: the last three apexes pass at 0.3 m/s, 1e-3
+    v_x_target = 0.3
+    _, vx = _slip_controlled_hopping((1.0, 0.5, 11.0, 1.5, 1.5), 15.0, lambda c, q, v: c.control_to_velocity(q, v, v_x_target))
+    assert len(vx) >= 3
+    for k in (1, 2, 3):
+        assert abs(vx[-k] - v_x_target) < 1e-3
 
 
 def test_quadruped_inverse_kinematics():  # control/quadruped_control.rs:318-413
