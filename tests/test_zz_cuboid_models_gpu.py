@@ -197,3 +197,47 @@ def test_examples_run_on_the_gpu(tmp_path):
     bz, lz, rz, ke = map(float, re.search(rf"base z = {num}, left foot z = {num}, right foot z = {num}, kinetic energy {num}",
                                           out["biped"]).groups())
     assert abs(bz - 0.478170) < 1e-5 and abs(lz - 0.0475871) < 1e-6 and abs(rz - 0.0475871) < 1e-6 and abs(ke - 0.354009) < 1e-5
+
+
+def test_reference_lqr_tests_through_the_host_closure_path():
+    """control/lqr.rs:78-186 acrobot_lqr / cart_pole_lqr on the GPU: the controller is a host closure (set_tau + one
+    Runge-Kutta-4 step per call, like the reference's simulate()), several perturbed starts at once; the reference's
+    own start must end within the reference's tolerances, and the first 200 steps agree with the oracle."""
+    from tests import models
+    PI = math.pi
+    cases = [
+        # (description, K, operating point (q), actuated dof, start q, start v, final time, tolerance on q, perturbation of the
+        #  other starts: the acrobot's LQR has a narrow basin - 0.01 rad more already diverges, in the oracle as well)
+        (models.double_pendulum_hanging(5.0, 7.0), np.array([-14067.26123453, -4689.08739542, -15265.74479887, -5803.13757768]),
+         np.array([-PI, 0.0]), 1, np.array([-PI - 0.03, 0.03]), np.array([0.03, 0.03]), 100.0, 1e-3, 0.002),
+        (models.cart_pole(3.0, 1.0, 5.0, 7.0, (0, -1, 0)), np.array([-1.0, 210.06025784, -5.27501096, 129.54543534]),
+         np.array([0.0, PI]), 0, np.array([-1.0, PI + 0.5]), np.array([1.0, 0.5]), 50.0, 2e-3, 0.01),
+    ]
+    for desc, K, q_op, actuated, q0, v0, final_time, tol_q, amp in cases:
+        mech = Mechanism.from_desc(desc)
+        orc = oracle_of(desc)
+        n = 8
+        rng = np.random.default_rng(1)
+        q = np.tile(q0, (n, 1))
+        v = np.tile(v0, (n, 1))
+        q[1:] += rng.uniform(-amp, amp, size=(n - 1, 2))  # environment 0 is the reference's own start
+        st = MechanismState(mech, n)
+        st.update(q, v)
+        qo, vo = q0.copy(), v0.copy()
+        dt = 0.01
+        from oracle.binding import simulate_step_count
+        for step in range(simulate_step_count(final_time, dt)):
+            x = np.concatenate([q - q_op, v], axis=1)
+            tau = np.zeros((n, 2))
+            tau[:, actuated] = -(x @ K)
+            st.step(dt, tau=tau, integrator=Integrator.RungeKutta4)
+            q, v = st.state()
+            if step < 200:
+                to = np.zeros(2)
+                to[actuated] = -float(K @ np.concatenate([qo - q_op, vo]))
+                qo, vo = orc.step(qo, vo, to, dt, 2)
+                assert np.abs(q[0] - qo).max() < 1e-9 and np.abs(v[0] - vo).max() < 1e-9, step
+        assert not st.status().any()
+        np.testing.assert_allclose(q[0], q_op, atol=tol_q)
+        np.testing.assert_allclose(v[0], [0.0, 0.0], atol=1e-3)
+        np.testing.assert_allclose(q, np.tile(q_op, (n, 1)), atol=5 * tol_q)  # the perturbed starts settle as well
