@@ -5,9 +5,10 @@ build_leg and build_leg_from_foot (builders/leg_builder.rs:8-211, 24 contact poi
 None of them has a shipped kernel specialisation: they run on kernels compiled at run time for their own topology
 (gp_jit.cpp), the biped in the warp-pair mapping at these batch sizes (two legs = two halves), and on the
 run-time-topology kernel when forced to. Same bars as tests/test_parity_gpu.py: vdot / contact force / one step 1e-10
-relative against the oracle; rollouts within the oracle's own sensitivity. (This file sorts last on purpose: it was
-added after the round's GPU budget was spent, developed against the oracle on the host build of the device code,
-tests/test_device_code_on_host.py.)
+relative against the oracle; rollouts within the oracle's own sensitivity. Also here: the examples/ programs against
+the oracle's numbers, and the reference's LQR tests through the host-closure path. (This file sorts last on purpose:
+it was added after the round's GPU budget was spent, developed against the oracle on the host build of the device
+code, tests/test_device_code_on_host.py, and has not run on a B200 yet.)
 """
 import math
 

@@ -4,7 +4,7 @@
 #   gpurun --timeout 900 -- 'bash tools/gpu_run_z.sh'
 mkdir -p gpurun_out
 # 1. their parity tests alone, then the whole suite
-(time timeout 300 python -m pytest tests/test_zz_cuboid_models_gpu.py -q) > gpurun_out/z_pytest_cuboid.log 2>&1
+(time timeout 300 python -m pytest tests/test_zz_widening_gpu.py -q) > gpurun_out/z_pytest_cuboid.log 2>&1
 grep -E "passed|failed|error" gpurun_out/z_pytest_cuboid.log | tail -2
 (time timeout 200 python -m pytest tests -x -q -m gpu) > gpurun_out/z_pytest.log 2>&1; grep -E "passed|failed|error" gpurun_out/z_pytest.log | tail -2
 # 2. the bench line of record of the biped workload (64 K environments, thread per environment)

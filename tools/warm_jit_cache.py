@@ -43,7 +43,7 @@ def mechanisms():
     # bench.py --workload jit_* (the twins again, plus their energy kernels for the diagnostics)
     for name in ("so101_contact", "navbot_contact"):
         out["bench:" + name] = (lambda f=WORKLOADS[name][0]: generic_twin(f(), KernelMode.JIT), SIE | DYN | ENERGY)
-    # the reference's cuboid-built trees on the ground (tests/test_zz_cuboid_models_gpu.py, bench.py --workload biped)
+    # the reference's cuboid-built trees on the ground (tests/test_zz_widening_gpu.py, bench.py --workload biped)
     def grounded(name):
         m = Mechanism.from_model(name)
         m.add_halfspace((0, 0, 1), 0.0)
