@@ -242,3 +242,41 @@ def test_reference_lqr_tests_through_the_host_closure_path():
         np.testing.assert_allclose(q[0], q_op, atol=tol_q)
         np.testing.assert_allclose(v[0], [0.0, 0.0], atol=1e-3)
         np.testing.assert_allclose(q, np.tile(q_op, (n, 1)), atol=5 * tol_q)  # the perturbed starts settle as well
+
+
+def test_reference_slip_position_control_on_the_gpu():
+    """control/SLIP_control.rs:78-131 position_control on the GPU: the SpringContact leg, semi-implicit Euler at
+    dt = 1/600 for 10 s, the touch-down angle set by the controller on the host at every apex (through the batch's
+    spring-contact state, as the reference edits state.bodies[0].spring_contacts[0]); the reference's target x = 2
+    and two more at once, each to the reference's 1e-3 (oracle: 2.4e-4, 2.2e-5, 3.7e-5)."""
+    from tests.test_oracle_golden import _SLIPController, _world_linear_velocity
+    l_rest = 0.2
+    mech = Mechanism.from_model("slip", [0.54, 1.0, l_rest, 0.0, 2000.0])
+    mech.add_halfspace((0, 0, 1), -0.5)
+    assert mech.kernel_variant == "floating_F" and mech.n_spring_contacts == 1
+    targets = [2.0, 1.0, -1.5]
+    n = len(targets)
+    ctrls = [_SLIPController(1.0, 0.5, 20.0, 0.0, 0.0) for _ in targets]
+    st = MechanismState(mech, n)
+    st.update(np.tile(np.array([0, 0, 0, 1.0, 0, 0, 0]), (n, 1)), np.zeros((n, 6)))
+    dt = 1.0 / 600.0
+    vz_prev = np.zeros(n)
+    apexes = 0
+    for _ in range(int(10.0 / dt)):
+        st.step(dt)
+        q, v = st.state()
+        v_lin = np.stack([_world_linear_velocity(q[e], v[e]) for e in range(n)])
+        apex = (vz_prev >= 0.0) & (v_lin[:, 2] < 0.0)
+        if apex.any():
+            sc = st.spring_contact_state()
+            for e in np.nonzero(apex)[0]:
+                angle = ctrls[e].control_to_pos(q[e], v[e], targets[e])
+                d = np.array([math.sin(angle), 0.0, -math.cos(angle)])
+                sc[e, 0, 4:7] = d / np.linalg.norm(d)
+                sc[e, 0, 7] = l_rest
+                apexes += 1
+            st.set_spring_contact_state(sc)
+        vz_prev = v_lin[:, 2]
+    assert apexes > 3 * 10 and not st.status().any()
+    for e, t in enumerate(targets):
+        assert abs(q[e, 4] - t) < 1e-3, (t, q[e, 4])
