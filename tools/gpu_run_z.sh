@@ -4,9 +4,9 @@
 #   gpurun --timeout 900 -- 'bash tools/gpu_run_z.sh'
 mkdir -p gpurun_out
 # 1. their parity tests alone, then the whole suite
-(time timeout 300 python -m pytest tests/test_zz_widening_gpu.py -q) > gpurun_out/z_pytest_cuboid.log 2>&1
+(time timeout 600 python -m pytest tests/test_zz_widening_gpu.py -q) > gpurun_out/z_pytest_cuboid.log 2>&1
 grep -E "passed|failed|error" gpurun_out/z_pytest_cuboid.log | tail -2
-(time timeout 200 python -m pytest tests -x -q -m gpu) > gpurun_out/z_pytest.log 2>&1; grep -E "passed|failed|error" gpurun_out/z_pytest.log | tail -2
+(time timeout 600 python -m pytest tests -x -q -m gpu) > gpurun_out/z_pytest.log 2>&1; grep -E "passed|failed|error" gpurun_out/z_pytest.log | tail -2
 # 2. the bench line of record of the biped workload (64 K environments, thread per environment)
 timeout 300 python bench.py --workload biped --steps 20 --warmup 3 > gpurun_out/z_bench_biped.json 2> gpurun_out/z_bench_biped.err
 # 3. which mapping should a 13-body tree run at 64 K? its whole-tree kernel carries 1.7 KB of stack, the halves 168 B:
