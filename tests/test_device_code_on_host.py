@@ -57,6 +57,17 @@ def run_models(library, names):
     return out
 
 
+def test_device_dynamics_code_on_many_random_trees(debug_library):
+    """120 more random mechanisms (2 ... 9 bodies, mixed joint types, fixed joints inside chains, floating joints off
+    other bodies, springs, 1 ... 8 contact points, one or two halfspaces) through the run-time-topology instantiation
+    of the device code, 8 states each, against the oracle"""
+    out = run_models(debug_library, ["random_trees:100:120"])
+    worst = {m.group(1): float(m.group(2)) for m in re.finditer(r"^(random_tree:\d+) worst vdot err (\S+)$", out, re.M)}
+    assert len(worst) == 120, out[-2000:]
+    # (1e-9: the conditioning of H of a random tree - light bodies at the end of long chains - is part of the error)
+    assert max(worst.values()) < 1e-9, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
 def test_cuboid_built_models_on_the_host(debug_library):
     """biped / leg / leg_from_foot (builders/biped_builder.rs, leg_builder.rs; 13 / 6 / 6 bodies, 16 / 24 / 24 contact
     points) on the ground, through the run-time-topology instantiation of the device code, against the oracle"""

@@ -105,5 +105,8 @@ def run(name):
 
 if __name__ == "__main__":
     names = [sys.argv[1]] if len(sys.argv) > 1 and sys.argv[1] != "all" else list(WORKLOADS) + [f"random_tree:{k}" for k in range(12)]
+    if len(names) == 1 and names[0].startswith("random_trees:"):  # random_trees:<first>:<count> in one process
+        _, first, count = names[0].split(":")
+        names = [f"random_tree:{k}" for k in range(int(first), int(first) + int(count))]
     for n in names:
         print(n, "worst vdot err", run(n))
