@@ -276,6 +276,15 @@ size_t gp_last_error(char* buf, size_t len) {
   return e.size();
 }
 
+// Every constant of a description ends up as an operand of the step kernels: a NaN or an infinity among them would
+// not fail anywhere, it would turn every environment's state into NaNs at the first step. (The reference does not
+// check either - f64 fields - but a C caller's uninitialised array is a likelier accident than a Rust one.)
+static bool all_finite(const double* x, int n) {
+  for (int k = 0; k < n; ++k)
+    if (!std::isfinite(x[k])) return false;
+  return true;
+}
+
 int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
   if (!d || !out) {
     set_error("gp_mechanism_create: null argument");
@@ -340,6 +349,14 @@ int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
       return GP_ERR_INVALID;
     }
     const double* J = d->moment + 9 * i;
+    const bool sp_i = d->has_spring && d->has_spring[i] != 0;
+    if (!all_finite(q, 7) || !all_finite(J, 9) || !all_finite(d->cross_part + 3 * i, 3) || !std::isfinite(d->mass[i]) ||
+        d->mass[i] < 0.0 || (sp_i && d->spring_k && !std::isfinite(d->spring_k[i])) ||
+        (sp_i && d->spring_l && !std::isfinite(d->spring_l[i]))) {
+      set_error("body %d: joint origin, inertia, mass (>= 0) and joint spring must be finite numbers", i + 1);
+      delete m;
+      return GP_ERR_INVALID;
+    }
     double jmax = 0.0;
     for (int k = 0; k < 9; ++k) jmax = std::fmax(jmax, std::fabs(J[k]));
     if (std::fabs(J[1] - J[3]) > 1e-12 * jmax || std::fabs(J[2] - J[6]) > 1e-12 * jmax ||
@@ -373,6 +390,11 @@ int gp_mechanism_create(const gp_mechanism_desc* d, gp_mechanism** out) {
     const double n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
     if (!(std::fabs(n2 - 1.0) < 1e-9)) {  // the reference takes a UnitVector3 (halfspace.rs:6-11)
       set_error("halfspace %d: normal is not a unit vector (|n|^2 = %.17g)", h, n2);
+      delete m;
+      return GP_ERR_INVALID;
+    }
+    if (!all_finite(d->hs_point + 3 * h, 3) || !std::isfinite(d->hs_alpha[h]) || !std::isfinite(d->hs_mu[h])) {
+      set_error("halfspace %d: point, alpha and mu must be finite numbers", h);
       delete m;
       return GP_ERR_INVALID;
     }
@@ -446,6 +468,10 @@ int gp_mechanism_add_halfspace(gp_mechanism* m, const double point[3], const dou
     set_error("halfspace normal is not a unit vector (|n|^2 = %.17g)", hn2);
     return GP_ERR_INVALID;
   }
+  if (!all_finite(point, 3) || !std::isfinite(alpha) || !std::isfinite(mu)) {
+    set_error("halfspace point, alpha and mu must be finite numbers");
+    return GP_ERR_INVALID;
+  }
   if (m->n_hs() >= kMaxHS) {
     set_error("more than %d halfspaces", kMaxHS);
     return GP_ERR_LIMIT;
@@ -464,6 +490,10 @@ int gp_mechanism_add_contact_point(gp_mechanism* m, int32_t body, const double l
   }
   if (body < 1 || body > m->nb) {  // reference mechanism.rs:384-391 silently ignores unknown frames
     set_error("contact point on unknown body %d", body);
+    return GP_ERR_INVALID;
+  }
+  if (!all_finite(location, 3) || !std::isfinite(k)) {
+    set_error("contact point location and stiffness must be finite numbers");
     return GP_ERR_INVALID;
   }
   if (m->n_cp() >= kMaxCP) {
@@ -491,6 +521,10 @@ int gp_mechanism_add_spring_contact(gp_mechanism* m, int32_t body, double l_rest
   const double n2 = direction[0] * direction[0] + direction[1] * direction[1] + direction[2] * direction[2];
   if (!(std::fabs(n2 - 1.0) < 1e-9)) {
     set_error("spring contact direction is not a unit vector");
+    return GP_ERR_INVALID;
+  }
+  if (!std::isfinite(l_rest) || !std::isfinite(k)) {
+    set_error("spring contact rest length and stiffness must be finite numbers");
     return GP_ERR_INVALID;
   }
   if (m->n_sc() >= kMaxSC) {

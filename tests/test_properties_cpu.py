@@ -99,3 +99,54 @@ def test_host_code_round_trips_descriptions_and_derives_the_reference_topology(t
     variant = mech.kernel_variant
     assert variant == "generic" or variant.startswith("jit:") or any(
         variant == k for k in ("pendulum_R", "double_pendulum_RR", "cart_pole_PR", "floating_F", "hopper1d_FPP", "hopper_FPR"))
+
+
+_ALWAYS_USED = ("init_iso", "moment", "cross_part", "mass", "cp_location", "cp_k", "hs_point", "hs_normal", "hs_alpha", "hs_mu")
+
+
+@settings(max_examples=200, **COMMON)
+@given(trees, st.sampled_from(_ALWAYS_USED), st.sampled_from([float("nan"), float("inf"), float("-inf")]), st.integers(0, 10 ** 6))
+def test_non_finite_constants_are_rejected_not_stepped(tree, field, bad, where):
+    """Every constant of a description becomes an operand of the step kernels; a NaN or an infinity among them is
+    GP_ERR_INVALID at gp_mechanism_create (raw C ABI, as a C caller with an uninitialised array would hit it), never a
+    mechanism that turns every environment into NaNs at its first step - and never a crash."""
+    import ctypes as C
+
+    from gorilla_physics_b200 import _abi
+    seed, n_bodies = tree
+    desc = models.random_tree(seed, n_bodies)
+    lib = _abi.lib()
+    raw, keep = _abi.GpMechanismDesc(), {}
+    raw.n_bodies, raw.n_contact_points, raw.n_halfspaces = desc.n_bodies, desc.n_contact_points, desc.n_halfspaces
+    for f in ("parent", "joint_type", "has_spring", "cp_body"):
+        keep[f] = np.ascontiguousarray(getattr(desc, f), dtype=np.int32).copy()
+        setattr(raw, f, keep[f].ctypes.data_as(_abi.ip))
+    for f in ("axis", "init_iso", "moment", "cross_part", "mass", "spring_k", "spring_l", "cp_location", "cp_k", "hs_point", "hs_normal",
+              "hs_alpha", "hs_mu"):
+        keep[f] = np.ascontiguousarray(getattr(desc, f), dtype=np.float64).copy()
+        setattr(raw, f, keep[f].ctypes.data_as(C.POINTER(C.c_double)))
+    h = C.c_void_p()
+    assert lib.gp_mechanism_create(C.byref(raw), C.byref(h)) == _abi.GP_OK  # the description itself is fine
+    lib.gp_mechanism_destroy(h)
+    keep[field].flat[where % keep[field].size] = bad
+    h = C.c_void_p()
+    assert lib.gp_mechanism_create(C.byref(raw), C.byref(h)) == _abi.GP_ERR_INVALID, (field, bad)
+    assert not h.value
+
+
+def test_negative_mass_and_non_finite_additions_are_rejected():
+    import pytest
+
+    from gorilla_physics_b200._abi import GP_ERR_INVALID, GorillaError
+    d = models.random_tree(5, 4)
+    d._mass[2] = -0.5
+    with pytest.raises(GorillaError) as e:
+        Mechanism.from_desc(d)
+    assert e.value.code == GP_ERR_INVALID
+    m = Mechanism.from_model("cube")
+    for call in (lambda: m.add_halfspace((0, 0, 1), float("nan")), lambda: m.add_halfspace((0, 0, 1), 0.0, alpha=float("inf")),
+                 lambda: m.add_contact_point(1, (0.0, float("nan"), 0.0)), lambda: m.add_contact_point(1, (0, 0, 0), k=float("inf"))):
+        with pytest.raises(GorillaError) as e:
+            call()
+        assert e.value.code == GP_ERR_INVALID
+    assert m.n_halfspaces == 0 and m.n_contact_points == 8  # nothing was added
