@@ -289,10 +289,17 @@ bool has_contact(const gp_mechanism* m) { return contact_mode(m) != 0; }
 
 int64_t step_count(double final_time, double dt) {
   // reference simulate.rs:97-109: `let mut t = 0.0; while t < final_time { ...; t += dt; }`
+  // The reference's loop never ends for dt <= 0, for a NaN-free but infinite final_time, or once t + dt == t; and
+  // two billion steps are more than one launch sequence can count. All of these are -1 here, before any looping.
+  if (!(dt > 0.0) || !(final_time == final_time) || final_time > 1.7e308) return -1;
+  if (!(final_time > 0.0)) return 0;
+  if (final_time / dt > 2147483647.0) return -1;
   double t = 0.0;
   int64_t n = 0;
   while (t < final_time) {
-    t += dt;
+    const double t_next = t + dt;
+    if (t_next == t) return -1;
+    t = t_next;
     ++n;
   }
   return n;
@@ -919,8 +926,8 @@ int gp_batch_simulate(gp_batch* b, double* q_host, double* v_host, const double*
   }
   const int64_t n_steps = step_count(final_time, dt);
   if (n_steps_out) *n_steps_out = n_steps;
-  if (n_steps > 2147483647LL) {
-    set_error("too many steps");
+  if (n_steps < 0 || n_steps > 2147483647LL) {
+    set_error("gp_batch_simulate: final_time / dt gives no countable number of steps (at most 2^31 - 1)");
     return GP_ERR_INVALID;
   }
   const gp_mechanism* m = b->mech;

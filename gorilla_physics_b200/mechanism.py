@@ -455,6 +455,8 @@ class MechanismState:
         hq = hv = None
         if history:
             n = int(lib().gp_simulate_step_count(final_time, dt))
+            if n < 0:
+                raise ValueError(f"simulate: final_time={final_time!r} / dt={dt!r} gives no countable number of steps")
             hq = np.empty((n + 1, self.n_envs, self.n_q))
             hv = np.empty((n + 1, self.n_envs, self.n_v))
         check(lib().gp_batch_simulate(self._h, _ptr(qa), _ptr(va), _ptr(ta), final_time, dt, int(integrator),

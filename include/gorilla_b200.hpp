@@ -456,7 +456,9 @@ class MechanismState {
       Float final_time, Float dt, int integrator, int controller = GP_CTRL_NONE, const std::vector<Float>& ctrl_params = {}) {
     sync_to_device();
     const size_t nq = (size_t)n_q(), nv = (size_t)n_v();
-    const size_t n = (size_t)gp_simulate_step_count(final_time, dt);
+    const int64_t n_counted = gp_simulate_step_count(final_time, dt);
+    if (n_counted < 0) throw Error(GP_ERR_INVALID, "simulate: final_time / dt gives no countable number of steps");
+    const size_t n = (size_t)n_counted;
     std::vector<double> qf = to_float_vec(q), vf = to_float_vec(v);
     std::vector<double> hq((n + 1) * nq + 1), hv((n + 1) * nv + 1), dummy(1, 0.0);
     int64_t steps = 0;

@@ -167,6 +167,11 @@ def test_simulate_step_count():
     from oracle.binding import simulate_step_count
     for ft, dt in ((2.0, 1e-3), (30.0, 1e-3), (20.0, 1.0 / 600.0), (0.01, 1.0 / 6000.0)):
         assert f(ft, dt) == simulate_step_count(ft, dt)
+    # where the reference's loop would never end, or count past what a launch sequence can hold: -1, at once
+    for ft, dt in ((1.0, 0.0), (1.0, -1e-3), (1.0, float("nan")), (float("nan"), 1e-3), (float("inf"), 1e-3), (1e20, 1.0),
+                   (1.0, 1e-300), (1e6, 1e-4)):
+        assert f(ft, dt) == -1, (ft, dt)
+    assert f(-1.0, 1e-3) == 0 and f(1e3, 1e-3) in (1000000, 1000001)
 
 
 def test_model_literals_match_reference_sources():
