@@ -495,3 +495,8 @@ def test_examples_build_against_the_facade_and_fail_loudly_without_a_gpu(tmp_pat
         if not torch.cuda.is_available():
             r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
             assert r.returncode == 2 and "no CUDA device" in r.stderr, (src.name, r.returncode, r.stderr[-500:])
+    if not torch.cuda.is_available():  # the batched Python example: the same, through the ctypes mirror
+        import sys
+        r = subprocess.run([sys.executable, str(ROOT / "examples" / "batched_so101.py"), "1024", "2"], capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 2 and "so101_X6Rz" in r.stdout and "no CUDA device" in r.stderr, (r.stdout[-300:], r.stderr[-500:])

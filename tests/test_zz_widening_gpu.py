@@ -187,6 +187,10 @@ def test_examples_run_on_the_gpu(tmp_path):
         r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, (name, r.stdout[-500:], r.stderr[-500:])
         out[name] = r.stdout
+    import sys
+    r = subprocess.run([sys.executable, str(root / "examples" / "batched_so101.py"), "8192", "3"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "env-steps/s" in r.stdout and " 0 flagged environments" in r.stdout, (r.stdout[-500:], r.stderr[-500:])
     num = r"(-?[\d.]+(?:e[-+]?\d+)?)"
     lo, hi = map(float, re.search(rf"last 2 s: {num} \.\.\. {num}", out["rimless_wheel"]).groups())
     assert "kernel: floating_F" in out["rimless_wheel"] and 0.25 < lo < 0.36 and 0.65 < hi < 0.80, out["rimless_wheel"]
